@@ -1,0 +1,115 @@
+"""ctypes front end of the C restatement (oracle/ref_single_phase.c, ref_two_phase.c).
+
+TEST INFRASTRUCTURE ONLY (see oracle/ref_single_phase.py).  ``RefSinglePhaseC`` has the
+same surface as ``ref_single_phase.RefSinglePhase`` but runs the C code, which is fast
+enough for 131^3 x 1000-step parity runs and serves as the CPU timing baseline.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+from . import ref_single_phase as _np_ref
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_BUILD = os.path.join(_HERE, "_build")
+
+
+def build(force=False):
+    """Compile the C oracle (gcc, OpenMP) into oracle/_build/."""
+    targets = [os.path.join(_BUILD, n) for n in ("libref_strict.so", "libref_fast.so")]
+    if force or not all(os.path.exists(t) for t in targets):
+        subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), check=True,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    return targets
+
+
+_libs = {}
+
+
+def load(kind="strict"):
+    if kind not in _libs:
+        path = os.path.join(_BUILD, "libref_%s.so" % kind)
+        if not os.path.exists(path):
+            build()
+        _libs[kind] = ctypes.CDLL(path)
+    return _libs[kind]
+
+
+def _params_struct(ctype):
+    class P(ctypes.Structure):
+        _fields_ = [("nx", ctypes.c_int), ("ny", ctypes.c_int), ("nz", ctypes.c_int),
+                    ("force_flag", ctypes.c_int), ("bc_type", ctypes.c_int * 6),
+                    ("S", ctype * 19), ("invM", ctype * 361), ("w", ctype * 19),
+                    ("force", ctype * 3), ("bc_rho", ctype * 6), ("bc_vel", (ctype * 3) * 6)]
+    return P
+
+
+_P32 = _params_struct(ctypes.c_float)
+_P64 = _params_struct(ctypes.c_double)
+
+
+class RefSinglePhaseC(_np_ref.RefSinglePhase):
+    """Same state and setters as the NumPy oracle; the four passes run in C."""
+
+    def __init__(self, nx, ny, nz, dtype=np.float32, tau_mode="class", kind="strict"):
+        super().__init__(nx, ny, nz, dtype=dtype, tau_mode=tau_mode)
+        self._lib = load(kind)
+        self._suf = "f32" if self.dtype == np.float32 else "f64"
+        self._ct = ctypes.c_float if self.dtype == np.float32 else ctypes.c_double
+        P = _P32 if self.dtype == np.float32 else _P64
+        sz = getattr(self._lib, "ref_sp_sizeof_params_" + self._suf)
+        sz.restype = ctypes.c_size_t
+        assert sz() == ctypes.sizeof(P), "ctypes mirror of ref_params out of date"
+        self._P = P
+
+    def _fn(self, name):
+        fn = getattr(self._lib, "%s_%s" % (name, self._suf))
+        fn.restype = None
+        return fn
+
+    def _ptr(self, a):
+        assert a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data_as(ctypes.c_void_p)
+
+    def init_simulation(self):
+        super().init_simulation()
+        p = self._P()
+        p.nx, p.ny, p.nz = self.nx, self.ny, self.nz
+        p.force_flag = self.force_flag
+        for i in range(6):
+            p.bc_type[i] = self.bc_type[i]
+            p.bc_rho[i] = self.dtype.type(self.bc_rho[i])
+            for c in range(3):
+                p.bc_vel[i][c] = self.dtype.type(self.bc_vel[i][c])
+        for s in range(19):
+            p.S[s] = self.S[s]
+            p.w[s] = self.w[s]
+        flat = self.inv_M.reshape(-1)
+        for i in range(361):
+            p.invM[i] = flat[i]
+        for c in range(3):
+            p.force[c] = self.ext_f[c]
+        self._p = p
+
+    def colission(self):
+        self._fn("ref_sp_colission")(ctypes.byref(self._p), self._ptr(self.solid), self._ptr(self.F),
+                                     self._ptr(self.rho), self._ptr(self.v), self._ptr(self.f))
+
+    def streaming1(self):
+        self._fn("ref_sp_streaming1")(ctypes.byref(self._p), self._ptr(self.solid), self._ptr(self.f),
+                                      self._ptr(self.F))
+
+    def Boundary_condition(self):
+        self._fn("ref_sp_boundary_condition")(ctypes.byref(self._p), self._ptr(self.solid),
+                                              self._ptr(self.v), self._ptr(self.F))
+
+    def streaming3(self):
+        self._fn("ref_sp_streaming3")(ctypes.byref(self._p), self._ptr(self.solid), self._ptr(self.F),
+                                      self._ptr(self.f), self._ptr(self.rho), self._ptr(self.v))
+
+    def run(self, nsteps):
+        self._fn("ref_sp_step")(ctypes.byref(self._p), self._ptr(self.solid), self._ptr(self.f),
+                                self._ptr(self.F), self._ptr(self.rho), self._ptr(self.v),
+                                ctypes.c_int(int(nsteps)))
