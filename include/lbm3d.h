@@ -1,0 +1,170 @@
+/* lbm3d.h -- C ABI of the B200-native D3Q19 MRT lattice-Boltzmann time step.
+ *
+ * This is the drop-in boundary for the hot path of yjhp1016/taichi_LBM3D.  The
+ * reference has no FFI: its "kernels" are the @ti.kernel methods of
+ *   Single_phase/LBM_3D_SinglePhase_Solver.py  (class LB3D_Solver_Single_Phase)
+ * called from step() (:477-481).  Each entry point below names the reference method
+ * it replaces (file:line relative to that file unless another file is given).  The
+ * Python class in taichi_lbm3d_b200/LBM_3D_SinglePhase_Solver.py binds these through
+ * ctypes (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *  - every function returns 0 on success or a negative lbm_status; nothing throws
+ *    across the ABI; lbm_last_error(ctx) gives the message of the last failure.
+ *  - a context owns its device buffers on ONE GPU; one context per GPU; a context is
+ *    not thread-safe.  Pointers passed in are borrowed for the duration of the call.
+ *  - "host_or_dev" pointers may be host or device memory (cudaMemcpyDefault).
+ *  - dense user-visible arrays use the layout the reference's to_numpy() exposes:
+ *    C order [nx][ny][nz] (z fastest), vectors with a trailing component axis.
+ *  - all arithmetic is fp32 (ti.f32 in the reference, :32-35); geometry is int8 (:57).
+ *  - work is enqueued on the stream given to lbm_step; getters synchronise it.
+ */
+#ifndef LBM3D_H
+#define LBM3D_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LBM3D_ABI_VERSION 1
+
+typedef struct lbm_ctx lbm_ctx;
+
+typedef enum {
+    LBM_OK = 0,
+    LBM_ERR_INVALID = -1,   /* bad argument / call order */
+    LBM_ERR_CUDA = -2,      /* CUDA runtime error (message in lbm_last_error) */
+    LBM_ERR_NOMEM = -3,
+    LBM_ERR_STATE = -4      /* e.g. step before init */
+} lbm_status;
+
+/* faces: order of the reference's Boundary_condition kernel (:272-370); on shared
+ * edges/corners the LATER face wins because the reference runs the face loops in
+ * this order. */
+enum { LBM_FACE_X0 = 0, LBM_FACE_X1, LBM_FACE_Y0, LBM_FACE_Y1, LBM_FACE_Z0, LBM_FACE_Z1 };
+/* :22  "0=periodic, 1= fix pressure, 2=fix velocity" */
+enum { LBM_BC_PERIODIC = 0, LBM_BC_PRESSURE = 1, LBM_BC_VELOCITY = 2 };
+
+typedef struct {
+    int32_t nx, ny, nz;   /* lattice extents of this context (ctor :11) */
+    int32_t sparse;       /* 0: direct-addressed dense lattice (:31-35);
+                             1: compacted fluid-node list + 18-neighbour table, replaces the
+                                pointer/dense SNode tree (:36-44) */
+    int32_t strict;       /* 0: factored MRT transform, FMA allowed (production);
+                             1: oracle evaluation order, no FMA contraction -> bit-identical
+                                to oracle/ref_single_phase.c (verification mode) */
+    int32_t halo_x;       /* 0: periodic_index wraps x (:250-251);
+                             1: planes x=0 and x=nx-1 are ghost planes owned by the x-slab
+                                neighbours (multi-GPU); they are read, never updated */
+    int32_t device;       /* CUDA device ordinal */
+    int32_t x_face_mask;  /* halo_x=1 only: bit0 = this slab holds the global x0 face (its first owned
+                             plane), bit1 = it holds the global x1 face (its last owned plane) */
+} lbm_config;
+
+/* ---- lifetime ---------------------------------------------------------------------- */
+int lbm_abi_version(void);
+/* replaces LB3D_Solver_Single_Phase.__init__ (:11-114): allocates solid, rho, v, populations */
+int lbm_create(const lbm_config *cfg, lbm_ctx **out);
+int lbm_destroy(lbm_ctx *ctx);
+const char *lbm_last_error(const lbm_ctx *ctx);   /* ctx may be NULL: last create error */
+
+/* ---- parameters (setters :405-458; all must precede lbm_init) ------------------------- */
+/* solid.from_numpy / init_geo (:173-177): int8 [nx][ny][nz], >0 = solid */
+int lbm_set_geometry(lbm_ctx *ctx, const int8_t *solid_host_or_dev);
+/* set_bc_vel_* / set_bc_rho_* (:405-451): type 2 uses vel (rho ignored), type 1 uses rho */
+int lbm_set_bc(lbm_ctx *ctx, int face, int type, float rho, const float vel[3]);
+/* set_force (:457); force_flag as :137-140 */
+int lbm_set_force(lbm_ctx *ctx, const float force[3]);
+/* set_viscosity + the relaxation rates of init_simulation (:126-131), evaluated in
+ * double exactly as the Python source does, rounded once to fp32.
+ * textbook_tau = 0: tau = niu/3 + 0.5 (the class, :127); 1: tau = 3 niu + 0.5 (:126,
+ * the form every other copy of the solver uses). */
+int lbm_set_viscosity(lbm_ctx *ctx, double niu, int textbook_tau);
+/* alternatively give the 19 diagonal rates S_dig (:131) directly */
+int lbm_set_relaxation(lbm_ctx *ctx, const float S[19]);
+
+/* ---- init_simulation (:118-149): static_init + init (:160-170) ------------------------- */
+/* builds the link flags (dense) or the compacted fluid list + neighbour table (sparse)
+ * from the geometry, and sets rho=1, v=0, f=F=w. */
+int lbm_init(lbm_ctx *ctx);
+
+/* ---- step (:477-481): colission -> streaming1 -> Boundary_condition -> streaming3 ------- */
+/* nsteps reference steps, fused: one kernel launch per step on `cuda_stream`
+ * (a cudaStream_t, NULL = default stream).  Asynchronous. */
+int lbm_step(lbm_ctx *ctx, int nsteps, void *cuda_stream);
+/* number of kernels the context has launched so far (bench evidence) */
+int64_t lbm_launch_count(const lbm_ctx *ctx);
+/* wait for all enqueued work */
+int lbm_synchronize(lbm_ctx *ctx);
+
+/* ---- fields (what rho.to_numpy(), v.to_numpy(), F.to_numpy() return) ------------------ */
+/* each getter first brings the user-visible state up to date (the streaming3 pass
+ * :372-392 of the last step) and synchronises. */
+int lbm_get_rho(lbm_ctx *ctx, float *dst_host_or_dev);              /* [nx][ny][nz]     */
+int lbm_get_v(lbm_ctx *ctx, float *dst_host_or_dev);                /* [nx][ny][nz][3]  */
+int lbm_get_F(lbm_ctx *ctx, float *dst_host_or_dev);                /* [nx][ny][nz][19] */
+int lbm_get_solid(lbm_ctx *ctx, int8_t *dst_host_or_dev);           /* [nx][ny][nz]     */
+/* F.from_numpy / rho.from_numpy / v.from_numpy: overwrite one field of the state */
+int lbm_set_rho(lbm_ctx *ctx, const float *src_host_or_dev);
+int lbm_set_v(lbm_ctx *ctx, const float *src_host_or_dev);
+int lbm_set_F(lbm_ctx *ctx, const float *src_host_or_dev);
+/* get_max_v + cal_max_v (:394-402) */
+int lbm_get_max_v(lbm_ctx *ctx, float *out);
+
+/* ---- sparse storage tables (bit-exact compaction tests; north_star item 1) ------------ */
+int lbm_get_num_fluid(lbm_ctx *ctx, int64_t *n_fluid);
+/* linear index i*ny*nz + j*nz + k of every stored fluid node, ascending; [n_fluid] */
+int lbm_get_fluid_index(lbm_ctx *ctx, int64_t *dst_host_or_dev);
+/* pull table [18][n_fluid]: row s-1 holds, for direction s=1..18, the compact index of
+ * the node i - e_s (periodic_index wrapped, :247-257) or -1 when that node is solid
+ * (half-way bounce-back, :267-268) */
+int lbm_get_neighbor_table(lbm_ctx *ctx, int32_t *dst_host_or_dev);
+/* dense mode: per-node link word [nx][ny][nz]; bit s (1..18) set = pull source of
+ * direction s is solid; bit 19 = node solid; bits 20-22 = winning BC face + 1;
+ * bit 23 = pressure BC uses the (zero) velocity of a solid inward neighbour (:278) */
+int lbm_get_link_flags(lbm_ctx *ctx, uint32_t *dst_host_or_dev);
+
+/* ---- multi-GPU x-slabs (halo_x = 1) -----------------------------------------------------
+ * The reference is single-device; this is the new decomposition.  A context
+ * then holds one x-slab plus one ghost plane on each side.  The five populations with
+ * e_x = +1 (s = 1,7,9,11,13) leave through the right face and the five with e_x = -1
+ * (s = 2,8,10,12,14) through the left face (:183-187); nothing else crosses a cut.
+ *
+ * plane ids: 0 = left ghost (x=0), 1 = first owned (x=1), 2 = last owned (x=nx-2),
+ *            3 = right ghost (x=nx-1).  lbm_halo_count = stored nodes in that plane
+ *            (dense: ny*nz; sparse: its fluid nodes).
+ * lbm_halo_pack(side)   side 0: e_x=-1 populations of plane 1 -> dst (goes to the LEFT rank)
+ *                       side 1: e_x=+1 populations of plane 2 -> dst (goes to the RIGHT rank)
+ *                       dst holds 5*count floats, [5][count].
+ * lbm_halo_unpack(side) side 0: src (sent by the LEFT rank's pack(1)) -> e_x=+1 of plane 0
+ *                       side 1: src (sent by the RIGHT rank's pack(0)) -> e_x=-1 of plane 3
+ * Both act on the CURRENT post-collision buffer, so the sequence per step is
+ *   [lbm_step_begin once] ; repeat { pack, exchange, unpack ; lbm_step(1) }
+ * and one more exchange before fields are read.  For overlap, lbm_step_planes updates a
+ * range of owned x planes without advancing the buffers; lbm_step_flip advances them. */
+int64_t lbm_halo_count(lbm_ctx *ctx, int plane);
+int lbm_halo_pack(lbm_ctx *ctx, int side, float *dst_dev, void *cuda_stream);
+int lbm_halo_unpack(lbm_ctx *ctx, int side, const float *src_dev, void *cuda_stream);
+/* first collision of the user-visible state (:222-241) if the pipeline is not running
+ * yet; counts as the collision half of the next step.  Returns 1 if already running. */
+int lbm_step_begin(lbm_ctx *ctx, void *cuda_stream);
+int lbm_step_planes(lbm_ctx *ctx, int x_begin, int x_end, void *cuda_stream);
+int lbm_step_flip(lbm_ctx *ctx);
+
+/* verification mode only: the 19x19 inv_M (:83,:110) as the caller's np.linalg.inv
+ * produced it (LAPACK leaves 1e-17 noise in the structural zeros); default = exact. */
+int lbm_set_inverse_matrix(lbm_ctx *ctx, const float invM[361]);
+
+/* raw device pointers for zero-copy wrapping (torch.as_tensor via __cuda_array_interface__) */
+enum { LBM_BUF_F_CUR = 0, LBM_BUF_F_NEXT = 1, LBM_BUF_RHO = 2, LBM_BUF_V = 3, LBM_BUF_FLAGS = 4 };
+int lbm_get_device_ptr(lbm_ctx *ctx, int which, void **ptr, size_t *bytes);
+/* elements between consecutive population planes of LBM_BUF_F_* (SoA [19][stride]) */
+int64_t lbm_get_stride(lbm_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LBM3D_H */

@@ -1,0 +1,110 @@
+"""ctypes binding of liblbm3d_b200.so (the C ABI declared in include/lbm3d.h).
+
+There is no CPU fallback: if the CUDA library cannot be loaded, importing this module
+raises, and every call that needs a GPU returns the library's own error when none is
+present.
+"""
+import ctypes
+import os
+
+from . import build as _build
+
+_c = ctypes
+
+LBM_OK = 0
+
+
+class LbmConfig(ctypes.Structure):
+    """lbm_config (include/lbm3d.h)."""
+    _fields_ = [("nx", _c.c_int32), ("ny", _c.c_int32), ("nz", _c.c_int32),
+                ("sparse", _c.c_int32), ("strict", _c.c_int32), ("halo_x", _c.c_int32),
+                ("device", _c.c_int32), ("x_face_mask", _c.c_int32)]
+
+
+class Lbm2pConfig(ctypes.Structure):
+    """lbm2p_config (include/lbm3d_2phase.h)."""
+    _fields_ = [("nx", _c.c_int32), ("ny", _c.c_int32), ("nz", _c.c_int32),
+                ("sparse", _c.c_int32), ("strict", _c.c_int32), ("device", _c.c_int32)]
+
+
+class LbmError(RuntimeError):
+    pass
+
+
+_VP = _c.c_void_p
+_I = _c.c_int
+_I64 = _c.c_int64
+_FP = _c.POINTER(_c.c_float)
+
+# name -> (restype, argtypes); every symbol include/lbm3d.h declares
+SIGNATURES = {
+    "lbm_abi_version": (_I, []),
+    "lbm_create": (_I, [_c.POINTER(LbmConfig), _c.POINTER(_VP)]),
+    "lbm_destroy": (_I, [_VP]),
+    "lbm_last_error": (_c.c_char_p, [_VP]),
+    "lbm_set_geometry": (_I, [_VP, _VP]),
+    "lbm_set_bc": (_I, [_VP, _I, _I, _c.c_float, _FP]),
+    "lbm_set_force": (_I, [_VP, _FP]),
+    "lbm_set_viscosity": (_I, [_VP, _c.c_double, _I]),
+    "lbm_set_relaxation": (_I, [_VP, _FP]),
+    "lbm_set_inverse_matrix": (_I, [_VP, _FP]),
+    "lbm_init": (_I, [_VP]),
+    "lbm_step": (_I, [_VP, _I, _VP]),
+    "lbm_launch_count": (_I64, [_VP]),
+    "lbm_synchronize": (_I, [_VP]),
+    "lbm_get_rho": (_I, [_VP, _VP]),
+    "lbm_get_v": (_I, [_VP, _VP]),
+    "lbm_get_F": (_I, [_VP, _VP]),
+    "lbm_get_solid": (_I, [_VP, _VP]),
+    "lbm_set_rho": (_I, [_VP, _VP]),
+    "lbm_set_v": (_I, [_VP, _VP]),
+    "lbm_set_F": (_I, [_VP, _VP]),
+    "lbm_get_max_v": (_I, [_VP, _FP]),
+    "lbm_get_num_fluid": (_I, [_VP, _c.POINTER(_I64)]),
+    "lbm_get_fluid_index": (_I, [_VP, _VP]),
+    "lbm_get_neighbor_table": (_I, [_VP, _VP]),
+    "lbm_get_link_flags": (_I, [_VP, _VP]),
+    "lbm_halo_count": (_I64, [_VP, _I]),
+    "lbm_halo_pack": (_I, [_VP, _I, _VP, _VP]),
+    "lbm_halo_unpack": (_I, [_VP, _I, _VP, _VP]),
+    "lbm_step_begin": (_I, [_VP, _VP]),
+    "lbm_step_planes": (_I, [_VP, _I, _I, _VP]),
+    "lbm_step_flip": (_I, [_VP]),
+    "lbm_get_device_ptr": (_I, [_VP, _I, _c.POINTER(_VP), _c.POINTER(_c.c_size_t)]),
+    "lbm_get_stride": (_I64, [_VP]),
+}
+
+_lib = None
+
+
+def library_path():
+    return _build.LIB
+
+
+def load():
+    """Load (building first if the sources are newer and nvcc exists) the CUDA library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if not os.path.exists(path):
+        try:
+            _build.build()
+        except Exception as e:  # noqa: BLE001
+            raise ImportError(
+                "taichi_lbm3d_b200: %s is missing and could not be built (%s). Run "
+                "`python -m taichi_lbm3d_b200.build`; there is no CPU fallback." % (path, e))
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)        # AttributeError = ABI mismatch, fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(lib, ctx, status, what):
+    if status < 0:
+        msg = lib.lbm_last_error(ctx)
+        raise LbmError("%s failed (%d): %s" % (what, status, msg.decode() if msg else "?"))
+    return status

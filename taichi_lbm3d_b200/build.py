@@ -1,0 +1,92 @@
+"""Build liblbm3d_b200.so (hand-written sm_100a CUDA + the C ABI of include/lbm3d.h) in-tree.
+
+    python -m taichi_lbm3d_b200.build [--force]
+
+nvcc cross-compiles without a GPU.  The kernel translation units are compiled twice:
+production arithmetic (namespace lbm_fast) and, with -DLBM_STRICT -fmad=false, the
+oracle-order verification arithmetic (namespace lbm_strict).
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+OBJDIR = os.path.join(LIBDIR, "obj")
+LIB = os.path.join(LIBDIR, "liblbm3d_b200.so")
+
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
+                 "-Wno-deprecated-gpu-targets"]
+
+# (object name, source, extra flags)
+UNITS = [
+    ("lbm_kernels_fast.o", "lbm_kernels.cu", []),
+    ("lbm_kernels_strict.o", "lbm_kernels.cu", ["-DLBM_STRICT=1", "-fmad=false"]),
+    ("lbm2p_kernels_fast.o", "lbm2p_kernels.cu", []),
+    ("lbm2p_kernels_strict.o", "lbm2p_kernels.cu", ["-DLBM_STRICT=1", "-fmad=false"]),
+    ("lbm_api.o", "lbm_api.cu", []),
+    ("lbm2p_api.o", "lbm2p_api.cu", []),
+]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found; cannot build the CUDA extension (there is no CPU fallback)")
+
+
+def _sources():
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    deps.append(os.path.join(HERE, "..", "include", "lbm3d.h"))
+    return [d for d in deps if os.path.isfile(d)]
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(s) > t for s in _sources())
+
+
+def build(force=False, verbose=False):
+    """Compile and link; returns the library path."""
+    if not force and not needs_build():
+        return LIB
+    nvcc = _nvcc()
+    os.makedirs(OBJDIR, exist_ok=True)
+    env = dict(os.environ)
+    # the image exports CC/CXX pointing at a wrapper without libgomp; use the system g++
+    ccbin = ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []
+    objs = []
+    procs = []
+    for obj, src, extra in UNITS:
+        srcp = os.path.join(CSRC, src)
+        if not os.path.exists(srcp):
+            continue
+        objp = os.path.join(OBJDIR, obj)
+        cmd = [nvcc] + ccbin + COMMON + extra + ["-c", srcp, "-o", objp]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env)))
+        objs.append(objp)
+    for cmd, p in procs:
+        out, _ = p.communicate()
+        if verbose and out:
+            sys.stderr.write(out.decode(errors="replace"))
+        if p.returncode != 0:
+            raise RuntimeError("nvcc failed: %s\n%s" % (" ".join(cmd), out.decode(errors="replace")))
+    tmp = LIB + ".tmp"
+    cmd = [nvcc] + ccbin + ARCH + ["-shared", "-o", tmp] + objs
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env)
+    if r.returncode != 0:
+        raise RuntimeError("link failed: %s\n%s" % (" ".join(cmd), r.stdout.decode(errors="replace")))
+    os.replace(tmp, LIB)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,901 @@
+// C-ABI layer of the single-phase solver (include/lbm3d.h): context, geometry
+// preprocessing (link flags / fluid-node compaction + neighbour table), the state
+// machine between the reference's user-visible state (F, rho, v) and the fused
+// pipeline state (post-collision f*), getters/setters, halo staging.
+//
+// Reference: Single_phase/LBM_3D_SinglePhase_Solver.py (line numbers below).
+#include <cub/cub.cuh>
+#include <thrust/iterator/transform_iterator.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "../../include/lbm3d.h"
+#include "lbm_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Face {
+    int type = 0;
+    float rho = 1.0f;
+    float vel[3] = {0.f, 0.f, 0.f};
+};
+
+}  // namespace
+
+struct lbm_ctx {
+    lbm_config cfg{};
+    std::string err;
+    int block = 256;
+    // parameters
+    float S[19]{};
+    float force[3] = {0.f, 0.f, 0.f};
+    Face face[6];
+    float invM[361]{};
+    bool have_geometry = false;
+    bool inited = false;
+    // sizes
+    size_t N = 0;          // nx*ny*nz
+    size_t nf = 0;         // stored nodes (dense: N; sparse: fluid nodes incl. ghost planes)
+    size_t stride = 0;     // population plane stride (elements)
+    uint32_t own_first = 0, own_count = 0;   // node range updated by a step
+    uint32_t plane_first[4] = {0, 0, 0, 0}, plane_count[4] = {0, 0, 0, 0};  // halo planes
+    int xface0 = -1, xface1 = -1;            // local x index of the global x0 / x1 faces
+    // device buffers
+    int8_t *d_solid = nullptr;
+    uint32_t *d_flags = nullptr;   // dense: [N] link words; sparse: [nf] BC words
+    int32_t *d_nbr = nullptr;      // sparse: [18][stride]
+    uint32_t *d_lin = nullptr;     // sparse: [nf]
+    uint32_t *d_rank = nullptr;    // sparse: [N+1] exclusive fluid count (kept for plane lookups)
+    float *d_f[2] = {nullptr, nullptr};
+    float *d_rho = nullptr, *d_v = nullptr, *d_F = nullptr;
+    float *d_vbc = nullptr;
+    uint32_t vbc_off[6]{};
+    float *d_scalar = nullptr;
+    // state machine
+    int cur = 0;
+    bool pipe_valid = false;     // d_f[cur] holds f* of the current step
+    bool macro_valid = true;     // d_rho / d_v current
+    bool F_valid = true;         // d_F current (or implicit w when d_F == nullptr)
+    cudaStream_t stream = nullptr;
+    int64_t launches = 0;
+};
+
+#define CTX_CHECK(ctx)                                                                         \
+    if ((ctx) == nullptr) return LBM_ERR_INVALID;
+#define FAIL(ctx, code, ...)                                                                   \
+    do {                                                                                       \
+        char _b[512];                                                                          \
+        snprintf(_b, sizeof _b, __VA_ARGS__);                                                  \
+        (ctx)->err = _b;                                                                       \
+        return (code);                                                                         \
+    } while (0)
+#define CU(ctx, call)                                                                          \
+    do {                                                                                       \
+        cudaError_t _e = (call);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            char _b[512];                                                                      \
+            snprintf(_b, sizeof _b, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e),    \
+                     __FILE__, __LINE__);                                                      \
+            (ctx)->err = _b;                                                                   \
+            return _e == cudaErrorMemoryAllocation ? LBM_ERR_NOMEM : LBM_ERR_CUDA;             \
+        }                                                                                      \
+    } while (0)
+
+namespace {
+
+// ---- geometry preprocessing ------------------------------------------------------------------
+struct GeoParams {
+    int nx, ny, nz;
+    int halo_x;
+    int xface0, xface1;
+    int bc_type[6];
+};
+
+__constant__ int c_e[19][3] = {{0, 0, 0}, {1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1},
+    {0, 0, -1}, {1, 1, 0}, {-1, -1, 0}, {1, -1, 0}, {-1, 1, 0}, {1, 0, 1}, {-1, 0, -1}, {1, 0, -1},
+    {-1, 0, 1}, {0, 1, 1}, {0, -1, -1}, {0, 1, -1}, {0, -1, 1}};
+
+// periodic_index :247-257 (x wrap disabled when ghost planes supply the neighbours)
+__device__ __forceinline__ bool pull_source(const GeoParams &g, int x, int y, int z, int s, size_t &src) {
+    int xs = x - c_e[s][0], ys = y - c_e[s][1], zs = z - c_e[s][2];
+    if (g.halo_x) {
+        if (xs < 0 || xs > g.nx - 1) return false;
+    } else {
+        if (xs < 0) xs = g.nx - 1;
+        if (xs > g.nx - 1) xs = 0;
+    }
+    if (ys < 0) ys = g.ny - 1;
+    if (ys > g.ny - 1) ys = 0;
+    if (zs < 0) zs = g.nz - 1;
+    if (zs > g.nz - 1) zs = 0;
+    src = ((size_t)xs * g.ny + ys) * g.nz + zs;
+    return true;
+}
+
+// BC bits of a fluid node: winning face (later face overwrites, :272-370) and whether a
+// pressure face reads the zero velocity of a solid inward neighbour (:278, :294 ...).
+__device__ __forceinline__ uint32_t bc_word(const GeoParams &g, const int8_t *solid, int x, int y, int z) {
+    int win = -1;
+    if (g.bc_type[0] && x == g.xface0) win = 0;
+    if (g.bc_type[1] && x == g.xface1) win = 1;
+    if (g.bc_type[2] && y == 0) win = 2;
+    if (g.bc_type[3] && y == g.ny - 1) win = 3;
+    if (g.bc_type[4] && z == 0) win = 4;
+    if (g.bc_type[5] && z == g.nz - 1) win = 5;
+    if (win < 0) return 0u;
+    uint32_t w = (uint32_t)(win + 1) << FL_BC_SHIFT;
+    if (g.bc_type[win] == 1) {
+        int xi = x, yi = y, zi = z;
+        switch (win) {
+            case 0: xi = x + 1; break;
+            case 1: xi = x - 1; break;
+            case 2: yi = 1; break;
+            case 3: yi = g.ny - 2; break;
+            case 4: zi = 1; break;
+            default: zi = g.nz - 2; break;
+        }
+        const bool inside = xi >= 0 && xi < g.nx && yi >= 0 && yi < g.ny && zi >= 0 && zi < g.nz;
+        if (inside && solid[((size_t)xi * g.ny + yi) * g.nz + zi] > 0) w |= FL_PIN_SOLID;
+    }
+    return w;
+}
+
+__global__ void k_build_flags(const GeoParams g, const int8_t *__restrict__ solid,
+                              uint32_t *__restrict__ flags) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t N = (size_t)g.nx * g.ny * g.nz;
+    if (idx >= N) return;
+    const int z = (int)(idx % g.nz);
+    const size_t t = idx / g.nz;
+    const int y = (int)(t % g.ny), x = (int)(t / g.ny);
+    uint32_t fl = 0;
+    if (solid[idx] != 0) {
+        flags[idx] = FL_SOLID;
+        return;
+    }
+    for (int s = 1; s < 19; ++s) {
+        size_t src;
+        if (!pull_source(g, x, y, z, s, src) || solid[src] != 0) fl |= 1u << s;
+    }
+    if (!g.halo_x) {
+        if (x == 0) fl |= FL_AT_X0;
+        if (x == g.nx - 1) fl |= FL_AT_X1;
+    }
+    if (y == 0) fl |= FL_AT_Y0;
+    if (y == g.ny - 1) fl |= FL_AT_Y1;
+    if (z == 0) fl |= FL_AT_Z0;
+    if (z == g.nz - 1) fl |= FL_AT_Z1;
+    fl |= bc_word(g, solid, x, y, z);
+    flags[idx] = fl;
+}
+
+struct IsFluid {
+    __host__ __device__ uint32_t operator()(const int8_t &s) const { return s == 0 ? 1u : 0u; }
+};
+
+__global__ void k_build_sparse(const GeoParams g, const int8_t *__restrict__ solid,
+                               const uint32_t *__restrict__ rank, size_t stride,
+                               uint32_t *__restrict__ lin, uint32_t *__restrict__ bcw,
+                               int32_t *__restrict__ nbr) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t N = (size_t)g.nx * g.ny * g.nz;
+    if (idx >= N || solid[idx] != 0) return;
+    const int z = (int)(idx % g.nz);
+    const size_t t = idx / g.nz;
+    const int y = (int)(t % g.ny), x = (int)(t / g.ny);
+    const uint32_t r = rank[idx];
+    lin[r] = (uint32_t)idx;
+    bcw[r] = bc_word(g, solid, x, y, z);
+    for (int s = 1; s < 19; ++s) {
+        size_t src;
+        int32_t j = -1;
+        if (pull_source(g, x, y, z, s, src) && solid[src] == 0) j = (int32_t)rank[src];
+        nbr[(size_t)(s - 1) * stride + r] = j;
+    }
+}
+
+__global__ void k_fill(float *p, size_t n, float v) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+__global__ void k_fill_weights(float *F, size_t n_nodes) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_nodes * 19) F[i] = d3q19::weight((int)(i % 19));
+}
+
+__global__ void k_binarize(int8_t *s, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) s[i] = s[i] > 0 ? 1 : 0;       // init_geo :175  in_dat[in_dat>0] = 1
+}
+
+// cal_max_v :399-402  (norm evaluated without FMA contraction so every mode agrees)
+__global__ void k_max_v(const float *__restrict__ v, size_t n, float *out) {
+    float best = -1e10f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const float x = v[3 * i], y = v[3 * i + 1], z = v[3 * i + 2];
+        const float nr = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+        best = fmaxf(best, nr);
+    }
+    for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if ((threadIdx.x & 31) == 0 && best >= 0.f) atomicMax((int *)out, __float_as_int(best));
+}
+
+// halo staging: 5 populations of one lattice plane <-> contiguous buffer [5][count]
+struct HaloDirs { int s[5]; };
+__global__ void k_halo_pack(const float *__restrict__ f, size_t stride, uint32_t first, uint32_t count,
+                            HaloDirs d, float *__restrict__ dst) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) dst[(size_t)q * count + i] = f[(size_t)d.s[q] * stride + first + i];
+}
+__global__ void k_halo_unpack(float *__restrict__ f, size_t stride, uint32_t first, uint32_t count,
+                              HaloDirs d, const float *__restrict__ src) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) f[(size_t)d.s[q] * stride + first + i] = src[(size_t)q * count + i];
+}
+
+inline unsigned nblocks(size_t n, int b) { return (unsigned)((n + b - 1) / b); }
+
+void default_relaxation(double niu, int textbook, float S[19]) {
+    // init_simulation :126-131, same double arithmetic as the Python source
+    const double tau_f = textbook ? 3.0 * niu + 0.5 : niu / 3.0 + 0.5;
+    const double s_v = 1.0 / tau_f;
+    const double s_other = 8.0 * (2.0 - s_v) / (8.0 - s_v);
+    const double S64[19] = {0, s_v, s_v, 0, s_other, 0, s_other, 0, s_other, s_v, s_v, s_v, s_v,
+                            s_v, s_v, s_v, s_other, s_other, s_other};
+    for (int i = 0; i < 19; ++i) S[i] = (float)S64[i];
+}
+
+// exact inverse of M (:64-83) as rationals; every non-zero entry rounds to the same f32 as
+// np.linalg.inv's (tests/test_abi_cpu.py); LAPACK's 1e-17 noise entries are exactly 0 here.
+const double kInvM[19][19] = {
+    {1.0/3.0, -1.0/2.0, 1.0/6.0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0},
+    {1.0/18.0, 0, -1.0/18.0, 1.0/6.0, -1.0/6.0, 0, 0, 0, 0, 1.0/12.0, -1.0/12.0, 0, 0, 0, 0, 0, 0, 0, 0},
+    {1.0/18.0, 0, -1.0/18.0, -1.0/6.0, 1.0/6.0, 0, 0, 0, 0, 1.0/12.0, -1.0/12.0, 0, 0, 0, 0, 0, 0, 0, 0},
+    {1.0/18.0, 0, -1.0/18.0, 0, 0, 1.0/6.0, -1.0/6.0, 0, 0, -1.0/24.0, 1.0/24.0, 1.0/8.0, -1.0/8.0, 0, 0, 0, 0, 0, 0},
+    {1.0/18.0, 0, -1.0/18.0, 0, 0, -1.0/6.0, 1.0/6.0, 0, 0, -1.0/24.0, 1.0/24.0, 1.0/8.0, -1.0/8.0, 0, 0, 0, 0, 0, 0},
+    {1.0/18.0, 0, -1.0/18.0, 0, 0, 0, 0, 1.0/6.0, -1.0/6.0, -1.0/24.0, 1.0/24.0, -1.0/8.0, 1.0/8.0, 0, 0, 0, 0, 0, 0},
+    {1.0/18.0, 0, -1.0/18.0, 0, 0, 0, 0, -1.0/6.0, 1.0/6.0, -1.0/24.0, 1.0/24.0, -1.0/8.0, 1.0/8.0, 0, 0, 0, 0, 0, 0},
+    {1.0/36.0, 1.0/24.0, 1.0/72.0, 1.0/12.0, 1.0/24.0, 1.0/12.0, 1.0/24.0, 0, 0, 1.0/48.0, 1.0/48.0, 1.0/16.0, 1.0/16.0, 1.0/4.0, 0, 0, 1.0/8.0, -1.0/8.0, 0},
+    {1.0/36.0, 1.0/24.0, 1.0/72.0, -1.0/12.0, -1.0/24.0, -1.0/12.0, -1.0/24.0, 0, 0, 1.0/48.0, 1.0/48.0, 1.0/16.0, 1.0/16.0, 1.0/4.0, 0, 0, -1.0/8.0, 1.0/8.0, 0},
+    {1.0/36.0, 1.0/24.0, 1.0/72.0, 1.0/12.0, 1.0/24.0, -1.0/12.0, -1.0/24.0, 0, 0, 1.0/48.0, 1.0/48.0, 1.0/16.0, 1.0/16.0, -1.0/4.0, 0, 0, 1.0/8.0, 1.0/8.0, 0},
+    {1.0/36.0, 1.0/24.0, 1.0/72.0, -1.0/12.0, -1.0/24.0, 1.0/12.0, 1.0/24.0, 0, 0, 1.0/48.0, 1.0/48.0, 1.0/16.0, 1.0/16.0, -1.0/4.0, 0, 0, -1.0/8.0, -1.0/8.0, 0},
+    {1.0/36.0, 1.0/24.0, 1.0/72.0, 1.0/12.0, 1.0/24.0, 0, 0, 1.0/12.0, 1.0/24.0, 1.0/48.0, 1.0/48.0, -1.0/16.0, -1.0/16.0, 0, 0, 1.0/4.0, -1.0/8.0, 0, 1.0/8.0},
+    {1.0/36.0, 1.0/24.0, 1.0/72.0, -1.0/12.0, -1.0/24.0, 0, 0, -1.0/12.0, -1.0/24.0, 1.0/48.0, 1.0/48.0, -1.0/16.0, -1.0/16.0, 0, 0, 1.0/4.0, 1.0/8.0, 0, -1.0/8.0},
+    {1.0/36.0, 1.0/24.0, 1.0/72.0, 1.0/12.0, 1.0/24.0, 0, 0, -1.0/12.0, -1.0/24.0, 1.0/48.0, 1.0/48.0, -1.0/16.0, -1.0/16.0, 0, 0, -1.0/4.0, -1.0/8.0, 0, -1.0/8.0},
+    {1.0/36.0, 1.0/24.0, 1.0/72.0, -1.0/12.0, -1.0/24.0, 0, 0, 1.0/12.0, 1.0/24.0, 1.0/48.0, 1.0/48.0, -1.0/16.0, -1.0/16.0, 0, 0, -1.0/4.0, 1.0/8.0, 0, 1.0/8.0},
+    {1.0/36.0, 1.0/24.0, 1.0/72.0, 0, 0, 1.0/12.0, 1.0/24.0, 1.0/12.0, 1.0/24.0, -1.0/24.0, -1.0/24.0, 0, 0, 0, 1.0/4.0, 0, 0, 1.0/8.0, -1.0/8.0},
+    {1.0/36.0, 1.0/24.0, 1.0/72.0, 0, 0, -1.0/12.0, -1.0/24.0, -1.0/12.0, -1.0/24.0, -1.0/24.0, -1.0/24.0, 0, 0, 0, 1.0/4.0, 0, 0, -1.0/8.0, 1.0/8.0},
+    {1.0/36.0, 1.0/24.0, 1.0/72.0, 0, 0, 1.0/12.0, 1.0/24.0, -1.0/12.0, -1.0/24.0, -1.0/24.0, -1.0/24.0, 0, 0, 0, -1.0/4.0, 0, 0, 1.0/8.0, 1.0/8.0},
+    {1.0/36.0, 1.0/24.0, 1.0/72.0, 0, 0, -1.0/12.0, -1.0/24.0, 1.0/12.0, 1.0/24.0, -1.0/24.0, -1.0/24.0, 0, 0, 0, -1.0/4.0, 0, 0, -1.0/8.0, -1.0/8.0}};
+
+void free_device(lbm_ctx *c) {
+    cudaFree(c->d_solid); cudaFree(c->d_flags); cudaFree(c->d_nbr); cudaFree(c->d_lin);
+    cudaFree(c->d_rank); cudaFree(c->d_f[0]); cudaFree(c->d_f[1]); cudaFree(c->d_rho);
+    cudaFree(c->d_v); cudaFree(c->d_F); cudaFree(c->d_vbc); cudaFree(c->d_scalar);
+    c->d_solid = nullptr; c->d_flags = nullptr; c->d_nbr = nullptr; c->d_lin = nullptr;
+    c->d_rank = nullptr; c->d_f[0] = c->d_f[1] = nullptr; c->d_rho = c->d_v = c->d_F = nullptr;
+    c->d_vbc = nullptr; c->d_scalar = nullptr;
+}
+
+void fill_args(const lbm_ctx *c, StepArgs &a) {
+    memset(&a, 0, sizeof a);
+    a.stride = c->stride;
+    a.first = c->own_first;
+    a.count = c->own_count;
+    a.nx = c->cfg.nx; a.ny = c->cfg.ny; a.nz = c->cfg.nz;
+    a.flags = c->d_flags;
+    a.nbr = c->d_nbr;
+    a.lin = c->d_lin;
+    a.rho = c->d_rho; a.v = c->d_v; a.F = nullptr;
+    a.vbc = c->d_vbc;
+    for (int i = 0; i < 6; ++i) a.vbc_off[i] = c->vbc_off[i];
+    a.force = (fabsf(c->force[0]) > 0.f || fabsf(c->force[1]) > 0.f || fabsf(c->force[2]) > 0.f) ? 1 : 0;
+    a.has_bc = 0;
+    for (int i = 0; i < 19; ++i) a.P.S[i] = c->S[i];
+    for (int i = 0; i < 3; ++i) a.P.force[i] = c->force[i];
+    for (int i = 0; i < 6; ++i) {
+        a.P.bc_type[i] = c->face[i].type;
+        a.P.bc_rho[i] = c->face[i].rho;
+        for (int k = 0; k < 3; ++k) a.P.bc_vel[i][k] = c->face[i].vel[k];
+        if (c->face[i].type != 0) a.has_bc = 1;
+    }
+}
+
+int launch(lbm_ctx *c, int mode, const StepArgs &a, cudaStream_t st) {
+    cudaError_t e;
+    if (c->cfg.strict)
+        e = c->cfg.sparse ? lbm_strict::launch_sparse(mode, a, c->block, st)
+                          : lbm_strict::launch_dense(mode, a, c->block, st);
+    else
+        e = c->cfg.sparse ? lbm_fast::launch_sparse(mode, a, c->block, st)
+                          : lbm_fast::launch_dense(mode, a, c->block, st);
+    if (e != cudaSuccess) FAIL(c, LBM_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    if (a.count) c->launches++;
+    return LBM_OK;
+}
+
+// user-visible F array, allocated on first need; solid nodes hold w (:164-169)
+int ensure_F(lbm_ctx *c) {
+    if (c->d_F != nullptr) return LBM_OK;
+    CU(c, cudaMalloc(&c->d_F, c->N * 19 * sizeof(float)));
+    k_fill_weights<<<nblocks(c->N * 19, 256), 256, 0, c->stream>>>(c->d_F, c->N);
+    CU(c, cudaGetLastError());
+    c->launches++;
+    // pristine state: F = w everywhere is already the truth; otherwise it must be extracted
+    return LBM_OK;
+}
+
+// pipeline -> user-visible state (the streaming3 pass of the last step)
+int sync_fields(lbm_ctx *c, bool need_F) {
+    if (!c->inited) FAIL(c, LBM_ERR_STATE, "lbm_init has not been called");
+    CU(c, cudaSetDevice(c->cfg.device));
+    if (need_F) {
+        const bool fresh = c->d_F == nullptr;
+        int r = ensure_F(c);
+        if (r) return r;
+        if (fresh && c->pipe_valid) c->F_valid = false;
+    }
+    const bool want = (!c->macro_valid) || (need_F && !c->F_valid);
+    if (want && c->pipe_valid) {
+        StepArgs a;
+        fill_args(c, a);
+        a.fin = c->d_f[c->cur];
+        a.fout = nullptr;
+        a.F = need_F ? c->d_F : nullptr;
+        int r = launch(c, MODE_EXTRACT, a, c->stream);
+        if (r) return r;
+        c->macro_valid = true;
+        if (need_F) c->F_valid = true;
+    }
+    return LBM_OK;
+}
+
+int copy_out(lbm_ctx *c, void *dst, const void *src, size_t bytes) {
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaMemcpy(dst, src, bytes, cudaMemcpyDefault));
+    return LBM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lbm_abi_version(void) { return LBM3D_ABI_VERSION; }
+
+const char *lbm_last_error(const lbm_ctx *ctx) {
+    return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+int lbm_create(const lbm_config *cfg, lbm_ctx **out) {
+    if (!cfg || !out) { g_create_error = "null argument"; return LBM_ERR_INVALID; }
+    *out = nullptr;
+    if (cfg->nx < 1 || cfg->ny < 1 || cfg->nz < 1) { g_create_error = "extents must be >= 1"; return LBM_ERR_INVALID; }
+    if (cfg->halo_x && cfg->nx < 3) { g_create_error = "halo_x needs nx >= 3 (two ghost planes)"; return LBM_ERR_INVALID; }
+    const size_t N = (size_t)cfg->nx * cfg->ny * cfg->nz;
+    if (N >= ((size_t)1 << 32)) { g_create_error = "lattice per context limited to 2^32 nodes"; return LBM_ERR_INVALID; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device available: ") + cudaGetErrorString(e) +
+                         " (this library has no CPU fallback)";
+        return LBM_ERR_CUDA;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) { g_create_error = "bad device ordinal"; return LBM_ERR_INVALID; }
+    e = cudaSetDevice(cfg->device);
+    if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return LBM_ERR_CUDA; }
+    lbm_ctx *c = new lbm_ctx();
+    c->cfg = *cfg;
+    c->N = N;
+    if (const char *b = getenv("LBM3D_BLOCK")) {
+        int v = atoi(b);
+        if (v >= 32 && v <= 256 && v % 32 == 0) c->block = v;
+    }
+    default_relaxation(0.16667, 0, c->S);        // :18 niu default
+    for (int i = 0; i < 19; ++i)
+        for (int j = 0; j < 19; ++j) c->invM[i * 19 + j] = (float)kInvM[i][j];
+    e = cudaMalloc(&c->d_solid, N);
+    if (e == cudaSuccess) e = cudaMemset(c->d_solid, 0, N);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("cudaMalloc(solid): ") + cudaGetErrorString(e);
+        delete c;
+        return LBM_ERR_NOMEM;
+    }
+    *out = c;
+    return LBM_OK;
+}
+
+int lbm_destroy(lbm_ctx *ctx) {
+    CTX_CHECK(ctx);
+    cudaSetDevice(ctx->cfg.device);
+    cudaDeviceSynchronize();
+    free_device(ctx);
+    delete ctx;
+    return LBM_OK;
+}
+
+int lbm_set_geometry(lbm_ctx *ctx, const int8_t *solid) {
+    CTX_CHECK(ctx);
+    if (!solid) FAIL(ctx, LBM_ERR_INVALID, "null geometry");
+    if (ctx->inited) FAIL(ctx, LBM_ERR_STATE, "geometry must be set before lbm_init");
+    CU(ctx, cudaSetDevice(ctx->cfg.device));
+    CU(ctx, cudaMemcpy(ctx->d_solid, solid, ctx->N, cudaMemcpyDefault));
+    k_binarize<<<nblocks(ctx->N, 256), 256>>>(ctx->d_solid, ctx->N);
+    CU(ctx, cudaGetLastError());
+    ctx->launches++;
+    ctx->have_geometry = true;
+    return LBM_OK;
+}
+
+int lbm_set_bc(lbm_ctx *ctx, int face, int type, float rho, const float vel[3]) {
+    CTX_CHECK(ctx);
+    if (face < 0 || face > 5 || type < 0 || type > 2) FAIL(ctx, LBM_ERR_INVALID, "bad face/type");
+    if (ctx->inited) FAIL(ctx, LBM_ERR_STATE, "boundary conditions are fixed at lbm_init (the reference bakes them into its kernels at first launch)");
+    ctx->face[face].type = type;
+    if (type == 1) ctx->face[face].rho = rho;
+    if (type == 2 && vel) for (int k = 0; k < 3; ++k) ctx->face[face].vel[k] = vel[k];
+    return LBM_OK;
+}
+
+int lbm_set_force(lbm_ctx *ctx, const float force[3]) {
+    CTX_CHECK(ctx);
+    if (!force) FAIL(ctx, LBM_ERR_INVALID, "null force");
+    for (int k = 0; k < 3; ++k) ctx->force[k] = force[k];
+    return LBM_OK;
+}
+
+int lbm_set_viscosity(lbm_ctx *ctx, double niu, int textbook_tau) {
+    CTX_CHECK(ctx);
+    default_relaxation(niu, textbook_tau, ctx->S);
+    return LBM_OK;
+}
+
+int lbm_set_relaxation(lbm_ctx *ctx, const float S[19]) {
+    CTX_CHECK(ctx);
+    if (!S) FAIL(ctx, LBM_ERR_INVALID, "null S");
+    for (int i = 0; i < 19; ++i) ctx->S[i] = S[i];
+    return LBM_OK;
+}
+
+int lbm_set_inverse_matrix(lbm_ctx *ctx, const float invM[361]) {
+    CTX_CHECK(ctx);
+    if (!invM) FAIL(ctx, LBM_ERR_INVALID, "null matrix");
+    memcpy(ctx->invM, invM, sizeof ctx->invM);
+    if (ctx->inited && ctx->cfg.strict) {
+        CU(ctx, cudaSetDevice(ctx->cfg.device));
+        CU(ctx, lbm_strict::set_inverse_matrix(ctx->invM));
+    }
+    return LBM_OK;
+}
+
+int lbm_init(lbm_ctx *c) {
+    CTX_CHECK(c);
+    CU(c, cudaSetDevice(c->cfg.device));
+    const int nx = c->cfg.nx, ny = c->cfg.ny, nz = c->cfg.nz;
+    const size_t N = c->N;
+    const size_t plane = (size_t)ny * nz;
+    // release everything but the geometry (re-init allowed)
+    {
+        int8_t *keep = c->d_solid;
+        c->d_solid = nullptr;
+        free_device(c);
+        c->d_solid = keep;
+    }
+    c->inited = false;
+    GeoParams g;
+    g.nx = nx; g.ny = ny; g.nz = nz;
+    g.halo_x = c->cfg.halo_x ? 1 : 0;
+    // local plane index of the global x faces; with ghost planes the faces are the first /
+    // last OWNED planes of the slabs flagged in cfg.x_face_mask (bit0: holds x0, bit1: holds x1)
+    if (g.halo_x) {
+        c->xface0 = (c->cfg.x_face_mask & 1) ? 1 : -1;
+        c->xface1 = (c->cfg.x_face_mask & 2) ? nx - 2 : -1;
+    } else {
+        c->xface0 = 0;
+        c->xface1 = nx - 1;
+    }
+    g.xface0 = c->xface0; g.xface1 = c->xface1;
+    for (int i = 0; i < 6; ++i) g.bc_type[i] = c->face[i].type;
+
+    CU(c, cudaMalloc(&c->d_scalar, 16));
+    if (!c->cfg.sparse) {
+        c->nf = N;
+        c->stride = (N + 31) / 32 * 32;
+        CU(c, cudaMalloc(&c->d_flags, N * sizeof(uint32_t)));
+        k_build_flags<<<nblocks(N, 256), 256>>>(g, c->d_solid, c->d_flags);
+        CU(c, cudaGetLastError());
+        c->launches++;
+        if (g.halo_x) {
+            c->own_first = (uint32_t)plane;
+            c->own_count = (uint32_t)(plane * (nx - 2));
+            c->plane_first[0] = 0; c->plane_first[1] = (uint32_t)plane;
+            c->plane_first[2] = (uint32_t)(plane * (nx - 2)); c->plane_first[3] = (uint32_t)(plane * (nx - 1));
+            for (int i = 0; i < 4; ++i) c->plane_count[i] = (uint32_t)plane;
+        } else {
+            c->own_first = 0;
+            c->own_count = (uint32_t)N;
+        }
+    } else {
+        // compacted fluid-node list, ascending linear index (replaces the pointer SNode tree :36-44)
+        CU(c, cudaMalloc(&c->d_rank, (N + 1) * sizeof(uint32_t)));
+        auto it = thrust::make_transform_iterator((const int8_t *)c->d_solid, IsFluid());
+        size_t tmp_bytes = 0;
+        void *tmp = nullptr;
+        CU(c, cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, it, c->d_rank, N));
+        CU(c, cudaMalloc(&tmp, tmp_bytes));
+        cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, it, c->d_rank, N);
+        cudaError_t e2 = cudaDeviceSynchronize();
+        cudaFree(tmp);
+        CU(c, e);
+        CU(c, e2);
+        c->launches += 2;
+        uint32_t last_rank = 0;
+        int8_t last_solid = 1;
+        CU(c, cudaMemcpy(&last_rank, c->d_rank + (N - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        CU(c, cudaMemcpy(&last_solid, c->d_solid + (N - 1), 1, cudaMemcpyDeviceToHost));
+        c->nf = (size_t)last_rank + (last_solid == 0 ? 1 : 0);
+        const uint32_t nf32 = (uint32_t)c->nf;
+        CU(c, cudaMemcpy(c->d_rank + N, &nf32, sizeof(uint32_t), cudaMemcpyHostToDevice));
+        c->stride = (c->nf + 31) / 32 * 32;
+        if (c->stride == 0) c->stride = 32;
+        CU(c, cudaMalloc(&c->d_lin, c->stride * sizeof(uint32_t)));
+        CU(c, cudaMalloc(&c->d_flags, c->stride * sizeof(uint32_t)));
+        CU(c, cudaMalloc(&c->d_nbr, c->stride * 18 * sizeof(int32_t)));
+        CU(c, cudaMemset(c->d_nbr, 0xff, c->stride * 18 * sizeof(int32_t)));
+        CU(c, cudaMemset(c->d_flags, 0, c->stride * sizeof(uint32_t)));
+        CU(c, cudaMemset(c->d_lin, 0, c->stride * sizeof(uint32_t)));
+        k_build_sparse<<<nblocks(N, 256), 256>>>(g, c->d_solid, c->d_rank, c->stride, c->d_lin,
+                                                  c->d_flags, c->d_nbr);
+        CU(c, cudaGetLastError());
+        c->launches++;
+        if (g.halo_x) {
+            uint32_t r[4];
+            const size_t at[4] = {plane, plane * 2, plane * (nx - 2), plane * (nx - 1)};
+            for (int i = 0; i < 4; ++i)
+                CU(c, cudaMemcpy(&r[i], c->d_rank + at[i], sizeof(uint32_t), cudaMemcpyDeviceToHost));
+            c->own_first = r[0];
+            c->own_count = r[3] - r[0];
+            c->plane_first[0] = 0; c->plane_count[0] = r[0];
+            c->plane_first[1] = r[0]; c->plane_count[1] = r[1] - r[0];
+            c->plane_first[2] = r[2]; c->plane_count[2] = r[3] - r[2];
+            c->plane_first[3] = r[3]; c->plane_count[3] = nf32 - r[3];
+        } else {
+            c->own_first = 0;
+            c->own_count = nf32;
+        }
+    }
+    // populations (A-B), user-visible macros, pressure-BC velocities
+    const size_t fbytes = c->stride * 19 * sizeof(float);
+    CU(c, cudaMalloc(&c->d_f[0], fbytes));
+    CU(c, cudaMalloc(&c->d_f[1], fbytes));
+    CU(c, cudaMemset(c->d_f[0], 0, fbytes));
+    CU(c, cudaMemset(c->d_f[1], 0, fbytes));
+    CU(c, cudaMalloc(&c->d_rho, N * sizeof(float)));
+    CU(c, cudaMalloc(&c->d_v, N * 3 * sizeof(float)));
+    k_fill<<<nblocks(N, 256), 256>>>(c->d_rho, N, 1.0f);      // init() :165
+    CU(c, cudaGetLastError());
+    c->launches++;
+    CU(c, cudaMemset(c->d_v, 0, N * 3 * sizeof(float)));       // :166
+    const size_t fs[6] = {plane, plane, (size_t)nx * nz, (size_t)nx * nz, (size_t)nx * ny, (size_t)nx * ny};
+    size_t tot = 0;
+    for (int i = 0; i < 6; ++i) { c->vbc_off[i] = (uint32_t)tot; tot += fs[i]; }
+    CU(c, cudaMalloc(&c->d_vbc, tot * 3 * sizeof(float)));
+    CU(c, cudaMemset(c->d_vbc, 0, tot * 3 * sizeof(float)));
+    if (c->cfg.strict) CU(c, lbm_strict::set_inverse_matrix(c->invM));
+    CU(c, cudaDeviceSynchronize());
+    c->cur = 0;
+    c->pipe_valid = false;
+    c->macro_valid = true;
+    c->F_valid = true;
+    c->inited = true;
+    return LBM_OK;
+}
+
+static int ensure_pipeline(lbm_ctx *c, cudaStream_t st) {
+    if (c->pipe_valid) return LBM_OK;
+    // first collision of the user-visible state (:222-241 with the stored rho, v)
+    StepArgs a;
+    fill_args(c, a);
+    a.fin = nullptr;
+    a.fout = c->d_f[c->cur];
+    a.F = c->d_F;      // null = pristine init state (F = w, rho = 1, v = 0)
+    int r = launch(c, MODE_COLLIDE, a, st);
+    if (r) return r;
+    c->pipe_valid = true;
+    return LBM_OK;
+}
+
+int lbm_step(lbm_ctx *c, int nsteps, void *cuda_stream) {
+    CTX_CHECK(c);
+    if (!c->inited) FAIL(c, LBM_ERR_STATE, "lbm_init has not been called");
+    if (nsteps < 0) FAIL(c, LBM_ERR_INVALID, "nsteps < 0");
+    if (nsteps == 0) return LBM_OK;
+    CU(c, cudaSetDevice(c->cfg.device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    c->stream = st;
+    // Reference step n = collide(F_{n-1}) ; stream ; BC ; macro.  The pipeline holds the
+    // post-collision state, so the first step after (re)initialisation is the collision
+    // alone and every later launch is [stream+BC+macro of step k] + [collision of step k+1];
+    // the closing stream+BC+macro runs on demand in sync_fields().
+    if (!c->pipe_valid) {
+        int r = ensure_pipeline(c, st);
+        if (r) return r;
+        nsteps -= 1;
+    } else if (c->cfg.halo_x == 0) {
+        // nothing
+    }
+    StepArgs a;
+    fill_args(c, a);
+    for (int it = 0; it < nsteps; ++it) {
+        a.fin = c->d_f[c->cur];
+        a.fout = c->d_f[c->cur ^ 1];
+        int r = launch(c, MODE_STEP, a, st);
+        if (r) return r;
+        c->cur ^= 1;
+    }
+    c->macro_valid = false;
+    c->F_valid = false;
+    return LBM_OK;
+}
+
+int64_t lbm_launch_count(const lbm_ctx *ctx) { return ctx ? ctx->launches : -1; }
+
+int lbm_synchronize(lbm_ctx *ctx) {
+    CTX_CHECK(ctx);
+    CU(ctx, cudaSetDevice(ctx->cfg.device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return LBM_OK;
+}
+
+int lbm_get_rho(lbm_ctx *c, float *dst) {
+    CTX_CHECK(c);
+    if (!dst) FAIL(c, LBM_ERR_INVALID, "null destination");
+    int r = sync_fields(c, false);
+    if (r) return r;
+    return copy_out(c, dst, c->d_rho, c->N * sizeof(float));
+}
+
+int lbm_get_v(lbm_ctx *c, float *dst) {
+    CTX_CHECK(c);
+    if (!dst) FAIL(c, LBM_ERR_INVALID, "null destination");
+    int r = sync_fields(c, false);
+    if (r) return r;
+    return copy_out(c, dst, c->d_v, c->N * 3 * sizeof(float));
+}
+
+int lbm_get_F(lbm_ctx *c, float *dst) {
+    CTX_CHECK(c);
+    if (!dst) FAIL(c, LBM_ERR_INVALID, "null destination");
+    int r = sync_fields(c, true);
+    if (r) return r;
+    return copy_out(c, dst, c->d_F, c->N * 19 * sizeof(float));
+}
+
+int lbm_get_solid(lbm_ctx *c, int8_t *dst) {
+    CTX_CHECK(c);
+    if (!dst) FAIL(c, LBM_ERR_INVALID, "null destination");
+    CU(c, cudaSetDevice(c->cfg.device));
+    CU(c, cudaMemcpy(dst, c->d_solid, c->N, cudaMemcpyDefault));
+    return LBM_OK;
+}
+
+static int set_field(lbm_ctx *c, const float *src, int which) {
+    if (!src) FAIL(c, LBM_ERR_INVALID, "null source");
+    int r = sync_fields(c, true);     // the other fields must be current before one is replaced
+    if (r) return r;
+    CU(c, cudaStreamSynchronize(c->stream));
+    float *dst = which == 0 ? c->d_rho : (which == 1 ? c->d_v : c->d_F);
+    const size_t n = which == 0 ? c->N : (which == 1 ? c->N * 3 : c->N * 19);
+    CU(c, cudaMemcpy(dst, src, n * sizeof(float), cudaMemcpyDefault));
+    c->pipe_valid = false;            // next step restarts from the user-visible state
+    c->macro_valid = true;
+    c->F_valid = true;
+    return LBM_OK;
+}
+int lbm_set_rho(lbm_ctx *c, const float *src) { CTX_CHECK(c); return set_field(c, src, 0); }
+int lbm_set_v(lbm_ctx *c, const float *src) { CTX_CHECK(c); return set_field(c, src, 1); }
+int lbm_set_F(lbm_ctx *c, const float *src) { CTX_CHECK(c); return set_field(c, src, 2); }
+
+int lbm_get_max_v(lbm_ctx *c, float *out) {
+    CTX_CHECK(c);
+    if (!out) FAIL(c, LBM_ERR_INVALID, "null destination");
+    int r = sync_fields(c, false);
+    if (r) return r;
+    const float seed = -1e10f;        // :395
+    // atomicMax on the int image orders non-negative floats; start below every one of them
+    const int init_bits = 0x80000000;
+    CU(c, cudaMemcpyAsync(c->d_scalar, &init_bits, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    k_max_v<<<148 * 8, 256, 0, c->stream>>>(c->d_v, c->N, c->d_scalar);
+    CU(c, cudaGetLastError());
+    c->launches++;
+    int bits = 0;
+    CU(c, cudaMemcpyAsync(&bits, c->d_scalar, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    float v;
+    memcpy(&v, &bits, sizeof v);
+    *out = bits < 0 ? seed : v;
+    return LBM_OK;
+}
+
+int lbm_get_num_fluid(lbm_ctx *c, int64_t *n) {
+    CTX_CHECK(c);
+    if (!n) FAIL(c, LBM_ERR_INVALID, "null destination");
+    if (!c->inited) FAIL(c, LBM_ERR_STATE, "lbm_init has not been called");
+    if (c->cfg.sparse) { *n = (int64_t)c->nf; return LBM_OK; }
+    // dense: count on demand
+    CU(c, cudaSetDevice(c->cfg.device));
+    auto it = thrust::make_transform_iterator((const int8_t *)c->d_solid, IsFluid());
+    uint32_t *d_out = nullptr;
+    CU(c, cudaMalloc(&d_out, sizeof(uint32_t)));
+    size_t tmp_bytes = 0;
+    void *tmp = nullptr;
+    cub::DeviceReduce::Sum(nullptr, tmp_bytes, it, d_out, c->N);
+    CU(c, cudaMalloc(&tmp, tmp_bytes));
+    cudaError_t e = cub::DeviceReduce::Sum(tmp, tmp_bytes, it, d_out, c->N);
+    uint32_t h = 0;
+    cudaError_t e2 = cudaMemcpy(&h, d_out, sizeof h, cudaMemcpyDeviceToHost);
+    cudaFree(tmp); cudaFree(d_out);
+    CU(c, e); CU(c, e2);
+    *n = h;
+    return LBM_OK;
+}
+
+int lbm_get_fluid_index(lbm_ctx *c, int64_t *dst) {
+    CTX_CHECK(c);
+    if (!dst) FAIL(c, LBM_ERR_INVALID, "null destination");
+    if (!c->inited || !c->cfg.sparse) FAIL(c, LBM_ERR_STATE, "needs an initialised sparse context");
+    CU(c, cudaSetDevice(c->cfg.device));
+    // widen on the host side of the copy: fetch u32, convert
+    std::string buf(c->nf * sizeof(uint32_t), '\0');
+    CU(c, cudaMemcpy(&buf[0], c->d_lin, c->nf * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    const uint32_t *u = reinterpret_cast<const uint32_t *>(buf.data());
+    cudaPointerAttributes at{};
+    const bool dev = cudaPointerGetAttributes(&at, dst) == cudaSuccess && at.type == cudaMemoryTypeDevice;
+    cudaGetLastError();
+    if (!dev) {
+        for (size_t i = 0; i < c->nf; ++i) dst[i] = (int64_t)u[i];
+    } else {
+        std::string w(c->nf * sizeof(int64_t), '\0');
+        int64_t *p = reinterpret_cast<int64_t *>(&w[0]);
+        for (size_t i = 0; i < c->nf; ++i) p[i] = (int64_t)u[i];
+        CU(c, cudaMemcpy(dst, p, c->nf * sizeof(int64_t), cudaMemcpyHostToDevice));
+    }
+    return LBM_OK;
+}
+
+int lbm_get_neighbor_table(lbm_ctx *c, int32_t *dst) {
+    CTX_CHECK(c);
+    if (!dst) FAIL(c, LBM_ERR_INVALID, "null destination");
+    if (!c->inited || !c->cfg.sparse) FAIL(c, LBM_ERR_STATE, "needs an initialised sparse context");
+    CU(c, cudaSetDevice(c->cfg.device));
+    CU(c, cudaMemcpy2D(dst, c->nf * sizeof(int32_t), c->d_nbr, c->stride * sizeof(int32_t),
+                       c->nf * sizeof(int32_t), 18, cudaMemcpyDefault));
+    return LBM_OK;
+}
+
+int lbm_get_link_flags(lbm_ctx *c, uint32_t *dst) {
+    CTX_CHECK(c);
+    if (!dst) FAIL(c, LBM_ERR_INVALID, "null destination");
+    if (!c->inited) FAIL(c, LBM_ERR_STATE, "lbm_init has not been called");
+    CU(c, cudaSetDevice(c->cfg.device));
+    const size_t n = c->cfg.sparse ? c->nf : c->N;
+    CU(c, cudaMemcpy(dst, c->d_flags, n * sizeof(uint32_t), cudaMemcpyDefault));
+    return LBM_OK;
+}
+
+// ---- multi-GPU halo staging ----------------------------------------------------------------
+int64_t lbm_halo_count(lbm_ctx *c, int plane) {
+    if (!c || !c->inited || !c->cfg.halo_x || plane < 0 || plane > 3) return -1;
+    return (int64_t)c->plane_count[plane];
+}
+
+static const HaloDirs kRight = {{1, 7, 9, 11, 13}};   // e_x = +1 (:184-186)
+static const HaloDirs kLeft = {{2, 8, 10, 12, 14}};   // e_x = -1
+
+int lbm_halo_pack(lbm_ctx *c, int side, float *dst, void *cuda_stream) {
+    CTX_CHECK(c);
+    if (!c->inited || !c->cfg.halo_x) FAIL(c, LBM_ERR_STATE, "needs an initialised halo_x context");
+    if (!c->pipe_valid) FAIL(c, LBM_ERR_STATE, "no post-collision state yet (call lbm_step_begin)");
+    if (side < 0 || side > 1 || !dst) FAIL(c, LBM_ERR_INVALID, "bad side/destination");
+    CU(c, cudaSetDevice(c->cfg.device));
+    const int plane = side == 0 ? 1 : 2;
+    const uint32_t cnt = c->plane_count[plane];
+    if (cnt == 0) return LBM_OK;
+    k_halo_pack<<<nblocks(cnt, 256), 256, 0, (cudaStream_t)cuda_stream>>>(
+        c->d_f[c->cur], c->stride, c->plane_first[plane], cnt, side == 0 ? kLeft : kRight, dst);
+    CU(c, cudaGetLastError());
+    c->launches++;
+    return LBM_OK;
+}
+
+int lbm_halo_unpack(lbm_ctx *c, int side, const float *src, void *cuda_stream) {
+    CTX_CHECK(c);
+    if (!c->inited || !c->cfg.halo_x) FAIL(c, LBM_ERR_STATE, "needs an initialised halo_x context");
+    if (side < 0 || side > 1 || !src) FAIL(c, LBM_ERR_INVALID, "bad side/source");
+    CU(c, cudaSetDevice(c->cfg.device));
+    const int plane = side == 0 ? 0 : 3;
+    const uint32_t cnt = c->plane_count[plane];
+    if (cnt == 0) return LBM_OK;
+    // the left ghost receives what the left neighbour sent to its right (e_x = +1) and v.v.
+    k_halo_unpack<<<nblocks(cnt, 256), 256, 0, (cudaStream_t)cuda_stream>>>(
+        c->d_f[c->cur], c->stride, c->plane_first[plane], cnt, side == 0 ? kRight : kLeft, src);
+    CU(c, cudaGetLastError());
+    c->launches++;
+    return LBM_OK;
+}
+
+int lbm_step_begin(lbm_ctx *c, void *cuda_stream) {
+    CTX_CHECK(c);
+    if (!c->inited) FAIL(c, LBM_ERR_STATE, "lbm_init has not been called");
+    CU(c, cudaSetDevice(c->cfg.device));
+    c->stream = (cudaStream_t)cuda_stream;
+    if (c->pipe_valid) return 1;      // nothing to do: a full step is pending
+    int r = ensure_pipeline(c, c->stream);
+    if (r) return r;
+    c->macro_valid = false;
+    c->F_valid = false;
+    return LBM_OK;
+}
+
+int lbm_step_planes(lbm_ctx *c, int x_begin, int x_end, void *cuda_stream) {
+    CTX_CHECK(c);
+    if (!c->inited || !c->pipe_valid) FAIL(c, LBM_ERR_STATE, "pipeline not started");
+    const int lo = c->cfg.halo_x ? 1 : 0, hi = c->cfg.halo_x ? c->cfg.nx - 1 : c->cfg.nx;
+    if (x_begin < lo || x_end > hi || x_begin > x_end) FAIL(c, LBM_ERR_INVALID, "plane range outside the owned slab");
+    CU(c, cudaSetDevice(c->cfg.device));
+    StepArgs a;
+    fill_args(c, a);
+    a.fin = c->d_f[c->cur];
+    a.fout = c->d_f[c->cur ^ 1];
+    const size_t plane = (size_t)c->cfg.ny * c->cfg.nz;
+    if (!c->cfg.sparse) {
+        a.first = (uint32_t)(plane * x_begin);
+        a.count = (uint32_t)(plane * (x_end - x_begin));
+    } else {
+        uint32_t r0, r1;
+        CU(c, cudaMemcpy(&r0, c->d_rank + plane * x_begin, sizeof r0, cudaMemcpyDeviceToHost));
+        CU(c, cudaMemcpy(&r1, c->d_rank + plane * x_end, sizeof r1, cudaMemcpyDeviceToHost));
+        a.first = r0;
+        a.count = r1 - r0;
+    }
+    return launch(c, MODE_STEP, a, (cudaStream_t)cuda_stream);
+}
+
+int lbm_step_flip(lbm_ctx *c) {
+    CTX_CHECK(c);
+    if (!c->inited || !c->pipe_valid) FAIL(c, LBM_ERR_STATE, "pipeline not started");
+    c->cur ^= 1;
+    c->macro_valid = false;
+    c->F_valid = false;
+    return LBM_OK;
+}
+
+int lbm_get_device_ptr(lbm_ctx *c, int which, void **ptr, size_t *bytes) {
+    CTX_CHECK(c);
+    if (!ptr || !bytes) FAIL(c, LBM_ERR_INVALID, "null output");
+    if (!c->inited) FAIL(c, LBM_ERR_STATE, "lbm_init has not been called");
+    switch (which) {
+        case LBM_BUF_F_CUR: *ptr = c->d_f[c->cur]; *bytes = c->stride * 19 * sizeof(float); break;
+        case LBM_BUF_F_NEXT: *ptr = c->d_f[c->cur ^ 1]; *bytes = c->stride * 19 * sizeof(float); break;
+        case LBM_BUF_RHO: *ptr = c->d_rho; *bytes = c->N * sizeof(float); break;
+        case LBM_BUF_V: *ptr = c->d_v; *bytes = c->N * 3 * sizeof(float); break;
+        case LBM_BUF_FLAGS: *ptr = c->d_flags; *bytes = (c->cfg.sparse ? c->nf : c->N) * sizeof(uint32_t); break;
+        default: FAIL(c, LBM_ERR_INVALID, "unknown buffer id");
+    }
+    return LBM_OK;
+}
+
+int64_t lbm_get_stride(lbm_ctx *c) { return c && c->inited ? (int64_t)c->stride : -1; }
+
+}  // extern "C"

@@ -1,0 +1,57 @@
+// Interface between the C-ABI layer (lbm_api.cu) and the kernel translation unit
+// (lbm_kernels.cu, compiled twice: production arithmetic -> namespace lbm_fast,
+// -DLBM_STRICT -fmad=false -> namespace lbm_strict).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "lbm_d3q19.cuh"
+
+// ---- link word of the dense lattice (lbm_get_link_flags) ---------------------------------
+#define FL_LINK_MASK 0x0007FFFEu  /* bits 1..18: pull source of direction s is solid        */
+#define FL_SOLID (1u << 19)       /* node is solid                                           */
+#define FL_BC_SHIFT 20            /* bits 20..22: winning BC face + 1 (0 = not a BC node)    */
+#define FL_BC_MASK 7u
+#define FL_PIN_SOLID (1u << 23)   /* pressure BC: inward neighbour is solid -> v = 0 (:278)  */
+#define FL_AT_X0 (1u << 24)       /* node sits on a face across which periodic_index wraps   */
+#define FL_AT_X1 (1u << 25)
+#define FL_AT_Y0 (1u << 26)
+#define FL_AT_Y1 (1u << 27)
+#define FL_AT_Z0 (1u << 28)
+#define FL_AT_Z1 (1u << 29)
+
+enum { MODE_STEP = 0, MODE_EXTRACT = 1, MODE_COLLIDE = 2 };
+
+struct StepArgs {
+    // populations, SoA: plane s at  base + s*stride  (post-collision state of the pipeline)
+    const float *fin;
+    float *fout;
+    size_t stride;
+    // node range processed by this launch: [first, first+count)
+    uint32_t first, count;
+    int nx, ny, nz;                 // extents of this context's lattice (incl. ghost planes)
+    // dense: link word per node.  sparse: BC word per stored node (bits 20..23), may be null
+    const uint32_t *flags;
+    // sparse only
+    const int32_t *nbr;             // [18][stride] pull table, -1 = bounce
+    const uint32_t *lin;            // [n_fluid] linear index of each stored node
+    // user-visible dense arrays (reference layout), used by MODE_EXTRACT / MODE_COLLIDE
+    float *rho;                     // [N]
+    float *v;                       // [N][3]
+    float *F;                       // [N][19] or null
+    // previous-step velocity of pressure-BC nodes (:279-281 read self.v before streaming3)
+    float *vbc;                     // [sum of face sizes][3]
+    uint32_t vbc_off[6];            // first slot of each face
+    int force;                      // force_flag :137-140
+    int has_bc;                     // any face with type != 0
+    d3q19::LbmParams P;
+};
+
+#define LBM_DECLARE_KERNEL_API(NS)                                                            \
+    namespace NS {                                                                            \
+    cudaError_t launch_dense(int mode, const StepArgs &a, int block, cudaStream_t st);        \
+    cudaError_t launch_sparse(int mode, const StepArgs &a, int block, cudaStream_t st);       \
+    cudaError_t set_inverse_matrix(const float *invM361);                                     \
+    }
+LBM_DECLARE_KERNEL_API(lbm_fast)
+LBM_DECLARE_KERNEL_API(lbm_strict)

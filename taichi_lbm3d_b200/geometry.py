@@ -1,0 +1,96 @@
+"""Geometry input: the reference's text format plus binary formats, and the generators the
+benchmark configurations need.
+
+Reference: ``init_geo`` (Single_phase/LBM_3D_SinglePhase_Solver.py:173-177) reads an ASCII
+file of 0/1 with x fastest (README.md:17-23); ``flow_domain_geo_generation_2D.py:18-27``
+writes the cavity file.  All functions return int8 arrays of shape (nx, ny, nz), C order,
+1 = solid, which is what ``solid.to_numpy()`` exposes in the reference.
+"""
+import os
+
+import numpy as np
+
+
+def load_geometry(filename, nx, ny, nz):
+    """init_geo :173-177.  ``.npy`` (any integer/bool array of shape (nx,ny,nz)) and ``.raw``
+    (uint8, x fastest like the text format) are accepted besides the reference's text."""
+    ext = os.path.splitext(filename)[1].lower()
+    if ext == ".npy":
+        a = np.load(filename)
+        if a.shape != (nx, ny, nz):
+            raise ValueError("%s has shape %s, expected %s" % (filename, a.shape, (nx, ny, nz)))
+        return (a > 0).astype(np.int8)
+    if ext == ".raw":
+        in_dat = np.fromfile(filename, dtype=np.uint8)
+    else:
+        in_dat = _fast_loadtxt(filename)
+    if in_dat.size != nx * ny * nz:
+        raise ValueError("%s holds %d values, expected %d" % (filename, in_dat.size, nx * ny * nz))
+    in_dat = (in_dat > 0).astype(np.int8)                          # :175
+    return np.ascontiguousarray(np.reshape(in_dat, (nx, ny, nz), order='F'))   # :176
+
+
+def _fast_loadtxt(filename):
+    """np.loadtxt(filename) for the 0/1 format, without the per-token Python overhead."""
+    with open(filename, "rb") as fh:
+        raw = fh.read()
+    toks = np.frombuffer(raw, dtype=np.uint8)
+    if toks.size and np.all((toks == 48) | (toks == 49) | (toks == 10) | (toks == 13) | (toks == 32)):
+        return (toks[(toks == 48) | (toks == 49)] - 48).astype(np.float64)
+    return np.loadtxt(filename).reshape(-1)        # general numbers: the reference's own call
+
+
+def save_geometry_text(filename, solid):
+    """flow_domain_geo_generation_2D.py:25-28: Fortran-order flatten, one value per line."""
+    out = np.asarray(solid).reshape(-1, order='F')
+    np.savetxt(filename, out.T, fmt='%d')
+
+
+def cavity(nx, ny, nz):
+    """flow_domain_geo_generation_2D.py:18-23: walls on x=0, y=0, y=-1, z=0, z=-1 (the lid is
+    the open x=nx-1 face, driven by set_bc_vel_x1)."""
+    g = np.zeros((nx, ny, nz), np.int8)
+    g[0, :, :] = 1
+    g[:, 0, :] = 1
+    g[:, -1, :] = 1
+    g[:, :, 0] = 1
+    g[:, :, -1] = 1
+    return g
+
+
+def sphere_pack(nx, ny, nz, solid_fraction=0.80, r_min=8.0, r_max=16.0, seed=512, periodic=True,
+                batch=64):
+    """Seeded overlapping-sphere pack: spheres with radii
+    U[r_min, r_max] are added until the solid fraction reaches ``solid_fraction``."""
+    rng = np.random.default_rng(seed)
+    g = np.zeros((nx, ny, nz), bool)
+    n = np.array([nx, ny, nz])
+    target = solid_fraction * g.size
+    count = 0
+    while count < target:
+        for _ in range(batch):
+            c = rng.random(3) * n
+            r = r_min + (r_max - r_min) * rng.random()
+            lo = np.floor(c - r).astype(int)
+            hi = np.ceil(c + r).astype(int) + 1
+            axes = []
+            for d in range(3):
+                idx = np.arange(lo[d], hi[d])
+                dist = idx - c[d]
+                if periodic:
+                    idx = idx % n[d]
+                else:
+                    keep = (idx >= 0) & (idx < n[d])
+                    idx, dist = idx[keep], dist[keep]
+                axes.append((idx, dist))
+            (ix, dx), (iy, dy), (iz, dz) = axes
+            mask = (dx[:, None, None] ** 2 + dy[None, :, None] ** 2 + dz[None, None, :] ** 2) <= r * r
+            g[np.ix_(ix, iy, iz)] |= mask
+        count = int(g.sum())
+    return g.astype(np.int8)
+
+
+def ftb131_standin():
+    """Synthetic stand-in for the missing img_ftb131.txt: 131^3, seed 131,
+    radii U[4,9], solid fraction >= 0.80, non-periodic in x."""
+    return sphere_pack(131, 131, 131, 0.80, 4.0, 9.0, seed=131, periodic=False)

@@ -1,0 +1,241 @@
+"""GPU parity tests: the CUDA path (through the ctypes/C-ABI binding) against the oracle.
+
+Bars (BASELINE.json north_star): compaction and neighbour tables bit-exact; populations,
+rho and v within relative L-inf 1e-5 after 1000 steps in fp32 (``TOL``).  In verification
+mode (strict=True: oracle evaluation order, no FMA contraction) the CUDA kernels must be
+BIT-IDENTICAL to the oracle, which pins all the plumbing (pull streaming, bounce-back,
+face BCs with their ordering, the pipeline state machine) exactly.
+"""
+import numpy as np
+import pytest
+
+from tests import cases
+from tests.cases import rel_linf
+
+pytestmark = pytest.mark.gpu
+
+TOL = cases.TOL  # relative L-infinity, populations / rho / v (north_star)
+
+
+_V_TOL = {}
+
+
+def _v_tol(case, steps, o32):
+    """see cases.v_abs_tolerance: max(1e-5 max|v|, 2 x the oracle's own fp32 round-off)"""
+    key = (case.name, case.shape, steps)
+    if key not in _V_TOL:
+        o64, _ = _oracle(case, steps, dtype=np.float64)
+        _V_TOL[key] = cases.v_abs_tolerance(o32, o64)
+    return _V_TOL[key]
+
+
+def _oracle(case, steps, **kw):
+    from oracle.cref import RefSinglePhaseC
+    o = case.make_oracle(RefSinglePhaseC, **kw)
+    o0 = None
+    if case.perturb:
+        class _S:       # start state snapshot
+            pass
+        o0 = _S()
+        o0.F, o0.rho, o0.v = o.F.copy(), o.rho.copy(), o.v.copy()
+    o.run(steps)
+    return o, o0
+
+
+def _run_solver(case, steps, sparse, strict, start):
+    lb = case.make_solver(sparse=sparse, strict=strict)
+    if start is not None:
+        case.apply_start(lb, start)
+    lb.run(steps)
+    return lb
+
+
+def _compare(lb, o, exact, case=None, steps=None):
+    fl = o.solid == 0
+    F, rho, v = lb.F.to_numpy(), lb.rho.to_numpy(), lb.v.to_numpy()
+    if exact:
+        assert np.array_equal(F[fl], o.F[fl])
+        assert np.array_equal(rho[fl], o.rho[fl])
+        assert np.array_equal(v[fl], o.v[fl])
+    else:
+        errs = {"F": rel_linf(F[fl], o.F[fl]), "rho": rel_linf(rho[fl], o.rho[fl])}
+        assert max(errs.values()) <= TOL, errs
+        dv = float(np.abs(v[fl].astype(np.float64) - o.v[fl]).max())
+        vtol = TOL * float(np.abs(o.v[fl]).max())
+        if dv > vtol:                    # creeping flow: fall back to the fp64 yardstick
+            vtol = _v_tol(case, steps, o)
+        assert dv <= vtol, ("v", dv, vtol, float(np.abs(o.v[fl]).max()))
+    # solid nodes keep the dense convention rho=1, v=0, F=w (reference :164-169, :390-392)
+    from taichi_lbm3d_b200.constants import W
+    sd = ~fl
+    if sd.any():
+        assert np.all(rho[sd] == 1.0) and np.all(v[sd] == 0.0)
+        assert np.array_equal(F[sd], np.broadcast_to(W, F[sd].shape))
+    return F, rho, v
+
+
+CASES = [cases.case_mixed_bc, cases.case_periodic_force, cases.case_all_faces]
+
+
+@pytest.mark.parametrize("make", CASES)
+@pytest.mark.parametrize("sparse", [False, True])
+@pytest.mark.parametrize("steps", [1, 2, 25])
+def test_strict_bit_identical(cuda, make, sparse, steps):
+    case = make()
+    o, o0 = _oracle(case, steps)
+    lb = _run_solver(case, steps, sparse, True, o0)
+    _compare(lb, o, exact=True)
+
+
+@pytest.mark.parametrize("make", CASES)
+@pytest.mark.parametrize("sparse", [False, True])
+def test_fast_parity_small(cuda, make, sparse):
+    case = make()
+    o, o0 = _oracle(case, 200)
+    lb = _run_solver(case, 200, sparse, False, o0)
+    _compare(lb, o, False, case, 200)
+
+
+def test_step_by_step_equals_run(cuda):
+    """step() x n, with field reads in between, equals run(n) (state machine, :477-481)."""
+    case = cases.case_mixed_bc()
+    o, o0 = _oracle(case, 7)
+    lb = case.make_solver(strict=True)
+    case.apply_start(lb, o0)
+    for i in range(7):
+        lb.step()
+        if i in (2, 3):
+            lb.rho.to_numpy()          # extraction pass must not disturb the pipeline
+            lb.get_max_v()
+        if i == 4:
+            lb.F.to_numpy()
+    _compare(lb, o, exact=True)
+
+
+def test_from_numpy_restart(cuda):
+    """F/rho/v.from_numpy mid-run restarts the pipeline from the user-visible state."""
+    case = cases.case_periodic_force()
+    o, o0 = _oracle(case, 5)
+    lb = case.make_solver(strict=True, sparse=True)
+    case.apply_start(lb, o0)
+    lb.run(3)
+    F, rho, v = lb.F.to_numpy(), lb.rho.to_numpy(), lb.v.to_numpy()
+    lb.F.from_numpy(F)
+    lb.rho.from_numpy(rho)
+    lb.v.from_numpy(v)
+    lb.run(2)
+    _compare(lb, o, exact=True)
+
+
+def test_cavity50_1000_steps(cuda):
+    """reference example_cavity.py shape: 50^3 geo_cavity, lid vz=0.1 on x1, 1000 steps."""
+    case = cases.case_cavity(50)
+    o, _ = _oracle(case, 1000)
+    for sparse in (False, True):
+        lb = _run_solver(case, 1000, sparse, False, None)
+        _, _, v = _compare(lb, o, False, case, 1000)
+        assert abs(lb.get_max_v() - o.get_max_v()) <= 1e-6
+        # the cavity geometry is mirror-symmetric in y and the lid moves along z: so is the flow
+        assert rel_linf(v[:, ::-1, :, 2], v[..., 2]) < 1e-4
+    lbs = _run_solver(case, 1000, False, True, None)
+    _compare(lbs, o, exact=True)
+
+
+def test_poiseuille_reference_example(cuda):
+    """example_poiseuille_flow.py: plates at z=0 and z=15, force fy=1e-4, niu=0.1667."""
+    case = cases.case_poiseuille()
+    steps = 3000
+    o, _ = _oracle(case, steps)
+    lb = _run_solver(case, steps, False, False, None)
+    _compare(lb, o, False, case, steps)
+    lbs = _run_solver(case, steps, True, True, None)
+    _compare(lbs, o, exact=True)
+
+
+def test_porous_pressure_bc_1000_steps(cuda):
+    """config-1 shape (example_porous_medium.py): sphere-pack stand-in, rho 1.0 -> 0.99 in x."""
+    case = cases.case_porous(64)
+    o, _ = _oracle(case, 1000)
+    for sparse in (False, True):
+        lb = _run_solver(case, 1000, sparse, False, None)
+        _compare(lb, o, False, case, 1000)
+    # pressure faces: v stays exactly 0 without a force (SURVEY section 4 KAT)
+    v = lb.v.to_numpy()
+    fl = case.solid == 0
+    assert np.all(v[0][fl[0]] == 0.0) and np.all(v[-1][fl[-1]] == 0.0)
+
+
+def test_sparse_tables_bit_exact(cuda):
+    """fluid-node compaction and 18-neighbour pull table vs a NumPy construction from solid,
+    periodic_index (:247-257) and e (:183-187)."""
+    from taichi_lbm3d_b200.constants import E
+    for shape, frac, seed in [((12, 10, 9), 0.35, 3), ((33, 17, 40), 0.8, 9), ((7, 7, 7), 0.0, 1)]:
+        solid = cases.random_porous(shape, frac, seed)
+        case = cases.Case("t", solid, bc=[(0, "rho", 1.0), (5, "vel", [0, 0, 0.01])])
+        lb = case.make_solver(sparse=True)
+        fluid = solid == 0
+        lin = np.flatnonzero(fluid.reshape(-1))
+        assert lb.num_fluid() == lin.size
+        assert np.array_equal(lb.fluid_index(), lin)
+        rank = np.full(solid.size, -1, np.int64)
+        rank[lin] = np.arange(lin.size)
+        rank3 = rank.reshape(shape)
+        want = np.empty((18, lin.size), np.int32)
+        for s in range(1, 19):
+            src = np.roll(rank3, tuple(int(c) for c in E[s]), axis=(0, 1, 2))   # value at i - e_s
+            want[s - 1] = src[fluid]
+        assert np.array_equal(lb.neighbor_table(), want)
+        # dense link words carry the same information
+        lbd = case.make_solver(sparse=False)
+        fl = lbd.link_flags()
+        for s in range(1, 19):
+            assert np.array_equal(((fl[fluid] >> s) & 1).astype(bool), want[s - 1] < 0)
+        assert np.array_equal((fl >> 19) & 1, solid.astype(np.uint32))
+
+
+def test_rest_state_and_mass(cuda):
+    """rest state is a fixed point to fp32 round-off; closed periodic box conserves mass."""
+    from taichi_lbm3d_b200.constants import W
+    solid = cases.random_porous((20, 18, 16), 0.3, 4)
+    lb = cases.Case("rest", solid).make_solver()
+    lb.run(50)
+    F = lb.F.to_numpy()
+    fl = solid == 0
+    assert np.abs(F[fl] - W).max() < 5e-7
+    assert np.abs(lb.v.to_numpy()).max() < 1e-6
+    case = cases.Case("mass", solid, perturb=1e-3)
+    o, o0 = _oracle(case, 1)
+    lb = case.make_solver(sparse=True)
+    case.apply_start(lb, o0)
+    m0 = lb.F.to_numpy()[fl].astype(np.float64).sum()
+    lb.run(200)
+    m1 = lb.F.to_numpy()[fl].astype(np.float64).sum()
+    assert abs(m1 - m0) / m0 < 5e-6
+
+
+def test_full_size_properties_256(cuda):
+    """BASELINE config 2 at full size (256^3 cavity): properties that need no oracle run --
+    y-mirror symmetry, closed-cavity mass drift, dense == sparse, lid nodes at the BC value."""
+    n = 256
+    case = cases.case_cavity(n)
+    lb = case.make_solver()
+    lb.run(100)
+    rho, v = lb.rho.to_numpy(), lb.v.to_numpy()
+    fl = case.solid == 0
+    assert np.isfinite(rho).all() and np.isfinite(v).all()
+    assert rel_linf(v[:, ::-1, :, 2], v[..., 2]) < 1e-4
+    assert rel_linf(v[:, ::-1, :, 1], -v[..., 1]) < 1e-4
+    lid = fl[n - 1]
+    assert np.abs(v[n - 1][lid] - np.array([0, 0, 0.1], np.float32)).max() < 2e-7
+    lbs = case.make_solver(sparse=True)
+    lbs.run(100)
+    assert rel_linf(lbs.rho.to_numpy(), rho) <= 1e-6
+    assert rel_linf(lbs.v.to_numpy(), v) <= TOL
+    assert lbs.num_fluid() == 255 * 254 * 254
+
+
+def test_launches_are_counted(cuda):
+    lb = cases.case_poiseuille().make_solver()
+    n0 = lb.launch_count
+    lb.run(10)
+    assert lb.launch_count - n0 == 10
