@@ -161,8 +161,11 @@ int lbm_set_inverse_matrix(lbm_ctx *ctx, const float invM[361]);
 /* raw device pointers for zero-copy wrapping (torch.as_tensor via __cuda_array_interface__) */
 enum { LBM_BUF_F_CUR = 0, LBM_BUF_F_NEXT = 1, LBM_BUF_RHO = 2, LBM_BUF_V = 3, LBM_BUF_FLAGS = 4 };
 int lbm_get_device_ptr(lbm_ctx *ctx, int which, void **ptr, size_t *bytes);
-/* elements between consecutive population planes of LBM_BUF_F_* (SoA [19][stride]) */
-int64_t lbm_get_stride(lbm_ctx *ctx);
+/* layout of LBM_BUF_F_*: out[0] = 0 SoA planes [19][stride] | 1 row-blocked [row][19][nzp]
+ * (row = i*ny+j, nzp = nz rounded up to 32) | 2 compact fluid list [19][stride];
+ * out[1] = elements between planes s and s+1; out[2] = elements between z-rows (dense);
+ * out[3] = elements per buffer */
+int lbm_get_layout(lbm_ctx *ctx, int64_t out[4]);
 
 #ifdef __cplusplus
 }

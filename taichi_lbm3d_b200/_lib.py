@@ -71,7 +71,7 @@ SIGNATURES = {
     "lbm_step_planes": (_I, [_VP, _I, _I, _VP]),
     "lbm_step_flip": (_I, [_VP]),
     "lbm_get_device_ptr": (_I, [_VP, _I, _c.POINTER(_VP), _c.POINTER(_c.c_size_t)]),
-    "lbm_get_stride": (_I64, [_VP]),
+    "lbm_get_layout": (_I, [_VP, _c.POINTER(_I64)]),
 }
 
 _lib = None

@@ -43,7 +43,13 @@ struct lbm_ctx {
     size_t N = 0;          // nx*ny*nz
     size_t nf = 0;         // stored nodes (dense: N; sparse: fluid nodes incl. ghost planes)
     size_t stride = 0;     // population plane stride (elements)
-    uint32_t own_first = 0, own_count = 0;   // node range updated by a step
+    uint32_t own_first = 0, own_count = 0;   // sparse: node range updated by a step
+    uint32_t row_first = 0, row_count = 0;   // dense: z-row range updated by a step
+    int layout = 0;        // dense: 0 = SoA planes [19][N]; 1 = row-blocked [row][19][nzp]
+    uint32_t nzp = 0;      // nz rounded up to 32 (row-blocked layout)
+    uint32_t prow = 0;     // elements between consecutive z-rows inside a population plane
+    size_t fsize = 0;      // elements of one population buffer (without guard bands)
+    int spec = 1;          // speculative pull (dense, few solid nodes)
     uint32_t plane_first[4] = {0, 0, 0, 0}, plane_count[4] = {0, 0, 0, 0};  // halo planes
     int xface0 = -1, xface1 = -1;            // local x index of the global x0 / x1 faces
     // device buffers
@@ -52,6 +58,9 @@ struct lbm_ctx {
     int32_t *d_nbr = nullptr;      // sparse: [18][stride]
     uint32_t *d_lin = nullptr;     // sparse: [nf]
     uint32_t *d_rank = nullptr;    // sparse: [N+1] exclusive fluid count (kept for plane lookups)
+    uint8_t *d_cls = nullptr;      // dense: [N] node class (NODE_BULK / NODE_SOLID / NODE_SPECIAL)
+    float *d_fbase[2] = {nullptr, nullptr};   // allocations; d_f = d_fbase + pad
+    size_t pad = 0;                // guard elements before/after the populations (speculative pull)
     float *d_f[2] = {nullptr, nullptr};
     float *d_rho = nullptr, *d_v = nullptr, *d_F = nullptr;
     float *d_vbc = nullptr;
@@ -147,7 +156,7 @@ __device__ __forceinline__ uint32_t bc_word(const GeoParams &g, const int8_t *so
 }
 
 __global__ void k_build_flags(const GeoParams g, const int8_t *__restrict__ solid,
-                              uint32_t *__restrict__ flags) {
+                              uint32_t *__restrict__ flags, uint8_t *__restrict__ cls) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t N = (size_t)g.nx * g.ny * g.nz;
     if (idx >= N) return;
@@ -157,6 +166,13 @@ __global__ void k_build_flags(const GeoParams g, const int8_t *__restrict__ soli
     uint32_t fl = 0;
     if (solid[idx] != 0) {
         flags[idx] = FL_SOLID;
+        // a solid node in the same 32-byte sector (8 nodes of a z-row) as a fluid node stores
+        // too, so the sector is written whole
+        const int z0 = z & ~7;
+        bool any_fluid = false;
+        for (int q = z0; q < z0 + 8 && q < g.nz; ++q)
+            if (solid[idx - z + q] == 0) any_fluid = true;
+        cls[idx] = any_fluid ? NODE_SOLID_WRITE : NODE_SOLID;
         return;
     }
     for (int s = 1; s < 19; ++s) {
@@ -173,6 +189,7 @@ __global__ void k_build_flags(const GeoParams g, const int8_t *__restrict__ soli
     if (z == g.nz - 1) fl |= FL_AT_Z1;
     fl |= bc_word(g, solid, x, y, z);
     flags[idx] = fl;
+    cls[idx] = fl == 0 ? NODE_BULK : NODE_SPECIAL;
 }
 
 struct IsFluid {
@@ -230,19 +247,23 @@ __global__ void k_max_v(const float *__restrict__ v, size_t n, float *out) {
 
 // halo staging: 5 populations of one lattice plane <-> contiguous buffer [5][count]
 struct HaloDirs { int s[5]; };
-__global__ void k_halo_pack(const float *__restrict__ f, size_t stride, uint32_t first, uint32_t count,
-                            HaloDirs d, float *__restrict__ dst) {
+// generic over both storage modes: node i of the plane lives at  plane_s + (row0 + i/nz)*prow + i%nz
+// (dense; SoA has prow = nz) or at  plane_s + first + i  (sparse: nz = 0)
+__global__ void k_halo_pack(StepArgs a, uint32_t row0, uint32_t first, uint32_t count, HaloDirs d,
+                            float *__restrict__ dst) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
+    const uint32_t e = a.nz ? (row0 + i / (uint32_t)a.nz) * a.prow + i % (uint32_t)a.nz : first + i;
 #pragma unroll
-    for (int q = 0; q < 5; ++q) dst[(size_t)q * count + i] = f[(size_t)d.s[q] * stride + first + i];
+    for (int q = 0; q < 5; ++q) dst[(size_t)q * count + i] = a.pown[d.s[q]][e];
 }
-__global__ void k_halo_unpack(float *__restrict__ f, size_t stride, uint32_t first, uint32_t count,
-                              HaloDirs d, const float *__restrict__ src) {
+__global__ void k_halo_unpack(StepArgs a, uint32_t row0, uint32_t first, uint32_t count, HaloDirs d,
+                              const float *__restrict__ src) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
+    const uint32_t e = a.nz ? (row0 + i / (uint32_t)a.nz) * a.prow + i % (uint32_t)a.nz : first + i;
 #pragma unroll
-    for (int q = 0; q < 5; ++q) f[(size_t)d.s[q] * stride + first + i] = src[(size_t)q * count + i];
+    for (int q = 0; q < 5; ++q) a.pout[d.s[q]][e] = src[(size_t)q * count + i];
 }
 
 inline unsigned nblocks(size_t n, int b) { return (unsigned)((n + b - 1) / b); }
@@ -282,7 +303,8 @@ const double kInvM[19][19] = {
 
 void free_device(lbm_ctx *c) {
     cudaFree(c->d_solid); cudaFree(c->d_flags); cudaFree(c->d_nbr); cudaFree(c->d_lin);
-    cudaFree(c->d_rank); cudaFree(c->d_f[0]); cudaFree(c->d_f[1]); cudaFree(c->d_rho);
+    cudaFree(c->d_rank); cudaFree(c->d_fbase[0]); cudaFree(c->d_fbase[1]); cudaFree(c->d_rho);
+    cudaFree(c->d_cls); c->d_cls = nullptr; c->d_fbase[0] = c->d_fbase[1] = nullptr;
     cudaFree(c->d_v); cudaFree(c->d_F); cudaFree(c->d_vbc); cudaFree(c->d_scalar);
     c->d_solid = nullptr; c->d_flags = nullptr; c->d_nbr = nullptr; c->d_lin = nullptr;
     c->d_rank = nullptr; c->d_f[0] = c->d_f[1] = nullptr; c->d_rho = c->d_v = c->d_F = nullptr;
@@ -294,9 +316,14 @@ void fill_args(const lbm_ctx *c, StepArgs &a) {
     a.stride = c->stride;
     a.first = c->own_first;
     a.count = c->own_count;
+    a.row_first = c->row_first;
+    a.row_count = c->row_count;
+    a.prow = c->prow;
+    a.spec = c->spec;
     a.nx = c->cfg.nx; a.ny = c->cfg.ny; a.nz = c->cfg.nz;
     a.flags = c->d_flags;
-    a.nbr = c->d_nbr;
+    a.cls = c->d_cls;
+    for (int s = 0; s < 18; ++s) a.nbr[s] = c->d_nbr ? c->d_nbr + (size_t)s * c->stride : nullptr;
     a.lin = c->d_lin;
     a.rho = c->d_rho; a.v = c->d_v; a.F = nullptr;
     a.vbc = c->d_vbc;
@@ -313,6 +340,20 @@ void fill_args(const lbm_ctx *c, StepArgs &a) {
     }
 }
 
+// plane pointers of the input / output population buffers
+void set_buffers(const lbm_ctx *c, StepArgs &a, const float *fin, float *fout) {
+    static const int e[19][3] = {{0, 0, 0}, {1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1},
+        {0, 0, -1}, {1, 1, 0}, {-1, -1, 0}, {1, -1, 0}, {-1, 1, 0}, {1, 0, 1}, {-1, 0, -1},
+        {1, 0, -1}, {-1, 0, 1}, {0, 1, 1}, {0, -1, -1}, {0, 1, -1}, {0, -1, 1}};
+    const long long sy = c->cfg.sparse ? 0 : (long long)c->prow, sx = (long long)c->cfg.ny * sy;
+    const size_t pstride = (!c->cfg.sparse && c->layout == 1) ? (size_t)c->nzp : c->stride;
+    for (int s = 0; s < 19; ++s) {
+        a.pown[s] = fin ? fin + (size_t)s * pstride : nullptr;
+        a.ppull[s] = fin ? a.pown[s] - (e[s][0] * sx + e[s][1] * sy + e[s][2]) : nullptr;
+        a.pout[s] = fout ? fout + (size_t)s * pstride : nullptr;
+    }
+}
+
 int launch(lbm_ctx *c, int mode, const StepArgs &a, cudaStream_t st) {
     cudaError_t e;
     if (c->cfg.strict)
@@ -322,7 +363,7 @@ int launch(lbm_ctx *c, int mode, const StepArgs &a, cudaStream_t st) {
         e = c->cfg.sparse ? lbm_fast::launch_sparse(mode, a, c->block, st)
                           : lbm_fast::launch_dense(mode, a, c->block, st);
     if (e != cudaSuccess) FAIL(c, LBM_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
-    if (a.count) c->launches++;
+    if (c->cfg.sparse ? a.count : a.row_count) c->launches++;
     return LBM_OK;
 }
 
@@ -351,8 +392,7 @@ int sync_fields(lbm_ctx *c, bool need_F) {
     if (want && c->pipe_valid) {
         StepArgs a;
         fill_args(c, a);
-        a.fin = c->d_f[c->cur];
-        a.fout = nullptr;
+        set_buffers(c, a, c->d_f[c->cur], nullptr);
         a.F = need_F ? c->d_F : nullptr;
         int r = launch(c, MODE_EXTRACT, a, c->stream);
         if (r) return r;
@@ -510,21 +550,55 @@ int lbm_init(lbm_ctx *c) {
 
     CU(c, cudaMalloc(&c->d_scalar, 16));
     if (!c->cfg.sparse) {
-        c->nf = N;
         c->stride = (N + 31) / 32 * 32;
         CU(c, cudaMalloc(&c->d_flags, N * sizeof(uint32_t)));
-        k_build_flags<<<nblocks(N, 256), 256>>>(g, c->d_solid, c->d_flags);
+        CU(c, cudaMalloc(&c->d_cls, N));
+        k_build_flags<<<nblocks(N, 256), 256>>>(g, c->d_solid, c->d_flags, c->d_cls);
         CU(c, cudaGetLastError());
         c->launches++;
+        // population layout: row-blocked [row][19][nzp] keeps the 19 populations of a z-row in
+        // one contiguous 19*nzp*4-byte chunk (measured +4.5% DRAM throughput over SoA planes on
+        // B200, scripts/microbench/streams.cu); SoA when the 32-bit element index would overflow
+        c->nzp = (uint32_t)((nz + 31) / 32 * 32);
+        const size_t rows = (size_t)nx * ny;
+        c->layout = (rows * 19 * c->nzp + 2 * (size_t)(ny + 2) * 19 * c->nzp < ((size_t)1 << 32)) ? 1 : 0;
+        if (const char *l = getenv("LBM3D_LAYOUT")) c->layout = atoi(l) ? 1 : 0;
+        if (c->layout == 1) {
+            c->prow = 19 * c->nzp;
+            c->fsize = rows * c->prow;
+        } else {
+            c->prow = (uint32_t)nz;
+            c->fsize = c->stride * 19;
+        }
+        // speculation pays when few nodes are solid (their speculative loads are wasted)
+        {
+            int64_t nfl = 0;
+            auto it = thrust::make_transform_iterator((const int8_t *)c->d_solid, IsFluid());
+            uint32_t *d_out = nullptr;
+            CU(c, cudaMalloc(&d_out, sizeof(uint32_t)));
+            size_t tmp_bytes = 0;
+            void *tmp = nullptr;
+            cub::DeviceReduce::Sum(nullptr, tmp_bytes, it, d_out, N);
+            CU(c, cudaMalloc(&tmp, tmp_bytes));
+            cudaError_t e = cub::DeviceReduce::Sum(tmp, tmp_bytes, it, d_out, N);
+            uint32_t h = 0;
+            cudaError_t e2 = cudaMemcpy(&h, d_out, sizeof h, cudaMemcpyDeviceToHost);
+            cudaFree(tmp); cudaFree(d_out);
+            CU(c, e); CU(c, e2);
+            nfl = h;
+            c->nf = (size_t)nfl;
+            c->spec = (double)nfl >= 0.75 * (double)N ? 1 : 0;
+            if (const char *sp = getenv("LBM3D_SPEC")) c->spec = atoi(sp) ? 1 : 0;
+        }
         if (g.halo_x) {
-            c->own_first = (uint32_t)plane;
-            c->own_count = (uint32_t)(plane * (nx - 2));
-            c->plane_first[0] = 0; c->plane_first[1] = (uint32_t)plane;
-            c->plane_first[2] = (uint32_t)(plane * (nx - 2)); c->plane_first[3] = (uint32_t)(plane * (nx - 1));
+            c->row_first = (uint32_t)ny;
+            c->row_count = (uint32_t)(ny * (nx - 2));
+            c->plane_first[0] = 0; c->plane_first[1] = (uint32_t)ny;
+            c->plane_first[2] = (uint32_t)(ny * (nx - 2)); c->plane_first[3] = (uint32_t)(ny * (nx - 1));
             for (int i = 0; i < 4; ++i) c->plane_count[i] = (uint32_t)plane;
         } else {
-            c->own_first = 0;
-            c->own_count = (uint32_t)N;
+            c->row_first = 0;
+            c->row_count = (uint32_t)(nx * ny);
         }
     } else {
         // compacted fluid-node list, ascending linear index (replaces the pointer SNode tree :36-44)
@@ -576,11 +650,20 @@ int lbm_init(lbm_ctx *c) {
         }
     }
     // populations (A-B), user-visible macros, pressure-BC velocities
-    const size_t fbytes = c->stride * 19 * sizeof(float);
-    CU(c, cudaMalloc(&c->d_f[0], fbytes));
-    CU(c, cudaMalloc(&c->d_f[1], fbytes));
-    CU(c, cudaMemset(c->d_f[0], 0, fbytes));
-    CU(c, cudaMemset(c->d_f[1], 0, fbytes));
+    // guard band: the dense kernel pulls speculatively from idx -/+ (plane + row + 1)
+    if (c->cfg.sparse) {
+        c->pad = 0;
+        c->fsize = c->stride * 19;
+        c->prow = 0;
+    } else {
+        c->pad = (((size_t)ny + 1) * c->prow + 2 + 31) / 32 * 32;
+    }
+    const size_t fbytes = (c->fsize + 2 * c->pad) * sizeof(float);
+    for (int b = 0; b < 2; ++b) {
+        CU(c, cudaMalloc(&c->d_fbase[b], fbytes));
+        CU(c, cudaMemset(c->d_fbase[b], 0, fbytes));
+        c->d_f[b] = c->d_fbase[b] + c->pad;
+    }
     CU(c, cudaMalloc(&c->d_rho, N * sizeof(float)));
     CU(c, cudaMalloc(&c->d_v, N * 3 * sizeof(float)));
     k_fill<<<nblocks(N, 256), 256>>>(c->d_rho, N, 1.0f);      // init() :165
@@ -607,8 +690,7 @@ static int ensure_pipeline(lbm_ctx *c, cudaStream_t st) {
     // first collision of the user-visible state (:222-241 with the stored rho, v)
     StepArgs a;
     fill_args(c, a);
-    a.fin = nullptr;
-    a.fout = c->d_f[c->cur];
+    set_buffers(c, a, nullptr, c->d_f[c->cur]);
     a.F = c->d_F;      // null = pristine init state (F = w, rho = 1, v = 0)
     int r = launch(c, MODE_COLLIDE, a, st);
     if (r) return r;
@@ -638,8 +720,7 @@ int lbm_step(lbm_ctx *c, int nsteps, void *cuda_stream) {
     StepArgs a;
     fill_args(c, a);
     for (int it = 0; it < nsteps; ++it) {
-        a.fin = c->d_f[c->cur];
-        a.fout = c->d_f[c->cur ^ 1];
+        set_buffers(c, a, c->d_f[c->cur], c->d_f[c->cur ^ 1]);
         int r = launch(c, MODE_STEP, a, st);
         if (r) return r;
         c->cur ^= 1;
@@ -812,8 +893,12 @@ int lbm_halo_pack(lbm_ctx *c, int side, float *dst, void *cuda_stream) {
     const int plane = side == 0 ? 1 : 2;
     const uint32_t cnt = c->plane_count[plane];
     if (cnt == 0) return LBM_OK;
+    StepArgs a;
+    fill_args(c, a);
+    set_buffers(c, a, c->d_f[c->cur], nullptr);
+    if (c->cfg.sparse) a.nz = 0;
     k_halo_pack<<<nblocks(cnt, 256), 256, 0, (cudaStream_t)cuda_stream>>>(
-        c->d_f[c->cur], c->stride, c->plane_first[plane], cnt, side == 0 ? kLeft : kRight, dst);
+        a, c->plane_first[plane], c->plane_first[plane], cnt, side == 0 ? kLeft : kRight, dst);
     CU(c, cudaGetLastError());
     c->launches++;
     return LBM_OK;
@@ -828,8 +913,12 @@ int lbm_halo_unpack(lbm_ctx *c, int side, const float *src, void *cuda_stream) {
     const uint32_t cnt = c->plane_count[plane];
     if (cnt == 0) return LBM_OK;
     // the left ghost receives what the left neighbour sent to its right (e_x = +1) and v.v.
+    StepArgs a;
+    fill_args(c, a);
+    set_buffers(c, a, nullptr, c->d_f[c->cur]);
+    if (c->cfg.sparse) a.nz = 0;
     k_halo_unpack<<<nblocks(cnt, 256), 256, 0, (cudaStream_t)cuda_stream>>>(
-        c->d_f[c->cur], c->stride, c->plane_first[plane], cnt, side == 0 ? kRight : kLeft, src);
+        a, c->plane_first[plane], c->plane_first[plane], cnt, side == 0 ? kRight : kLeft, src);
     CU(c, cudaGetLastError());
     c->launches++;
     return LBM_OK;
@@ -856,12 +945,11 @@ int lbm_step_planes(lbm_ctx *c, int x_begin, int x_end, void *cuda_stream) {
     CU(c, cudaSetDevice(c->cfg.device));
     StepArgs a;
     fill_args(c, a);
-    a.fin = c->d_f[c->cur];
-    a.fout = c->d_f[c->cur ^ 1];
+    set_buffers(c, a, c->d_f[c->cur], c->d_f[c->cur ^ 1]);
     const size_t plane = (size_t)c->cfg.ny * c->cfg.nz;
     if (!c->cfg.sparse) {
-        a.first = (uint32_t)(plane * x_begin);
-        a.count = (uint32_t)(plane * (x_end - x_begin));
+        a.row_first = (uint32_t)(c->cfg.ny * x_begin);
+        a.row_count = (uint32_t)(c->cfg.ny * (x_end - x_begin));
     } else {
         uint32_t r0, r1;
         CU(c, cudaMemcpy(&r0, c->d_rank + plane * x_begin, sizeof r0, cudaMemcpyDeviceToHost));
@@ -886,8 +974,8 @@ int lbm_get_device_ptr(lbm_ctx *c, int which, void **ptr, size_t *bytes) {
     if (!ptr || !bytes) FAIL(c, LBM_ERR_INVALID, "null output");
     if (!c->inited) FAIL(c, LBM_ERR_STATE, "lbm_init has not been called");
     switch (which) {
-        case LBM_BUF_F_CUR: *ptr = c->d_f[c->cur]; *bytes = c->stride * 19 * sizeof(float); break;
-        case LBM_BUF_F_NEXT: *ptr = c->d_f[c->cur ^ 1]; *bytes = c->stride * 19 * sizeof(float); break;
+        case LBM_BUF_F_CUR: *ptr = c->d_f[c->cur]; *bytes = c->fsize * sizeof(float); break;
+        case LBM_BUF_F_NEXT: *ptr = c->d_f[c->cur ^ 1]; *bytes = c->fsize * sizeof(float); break;
         case LBM_BUF_RHO: *ptr = c->d_rho; *bytes = c->N * sizeof(float); break;
         case LBM_BUF_V: *ptr = c->d_v; *bytes = c->N * 3 * sizeof(float); break;
         case LBM_BUF_FLAGS: *ptr = c->d_flags; *bytes = (c->cfg.sparse ? c->nf : c->N) * sizeof(uint32_t); break;
@@ -896,6 +984,16 @@ int lbm_get_device_ptr(lbm_ctx *c, int which, void **ptr, size_t *bytes) {
     return LBM_OK;
 }
 
-int64_t lbm_get_stride(lbm_ctx *c) { return c && c->inited ? (int64_t)c->stride : -1; }
+int lbm_get_layout(lbm_ctx *c, int64_t out[4]) {
+    CTX_CHECK(c);
+    if (!out) FAIL(c, LBM_ERR_INVALID, "null output");
+    if (!c->inited) FAIL(c, LBM_ERR_STATE, "lbm_init has not been called");
+    const bool blocked = !c->cfg.sparse && c->layout == 1;
+    out[0] = c->cfg.sparse ? 2 : c->layout;                      // 0 SoA, 1 row-blocked, 2 compact list
+    out[1] = blocked ? (int64_t)c->nzp : (int64_t)c->stride;     // elements between planes s and s+1
+    out[2] = (int64_t)c->prow;                                   // elements between z-rows (dense)
+    out[3] = (int64_t)c->fsize;                                  // elements per buffer
+    return LBM_OK;
+}
 
 }  // extern "C"

@@ -116,53 +116,111 @@ __device__ __forceinline__ void write_user_fields(const StepArgs &a, uint32_t li
 // ---------------------------------------------------------------------------------------------
 // dense lattice: direct addressing, node = linear index i*ny*nz + j*nz + k (z fastest)
 // ---------------------------------------------------------------------------------------------
-template <bool FORCE, int MODE>
+template <bool FORCE, int MODE, bool SPEC>
 __global__ void __launch_bounds__(256) k_dense(const StepArgs a) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.count) return;
-    const uint32_t idx = a.first + t;
-    const uint32_t fl = a.flags[idx];
-    if (fl & FL_SOLID) return;        // solid nodes keep f = F = w, rho = 1, v = 0 (:164-169, :390-392)
-    const size_t N = a.stride;
+    const uint32_t z = blockIdx.y * blockDim.x + threadIdx.x;
+    const uint32_t r = blockIdx.x * blockDim.y + threadIdx.y;
+    if (z >= (uint32_t)a.nz || r >= a.row_count) return;
+    const uint32_t row = a.row_first + r;
+    const uint32_t idx = row * (uint32_t)a.nz + z;      // node (flags, rho, v, F)
+    const uint32_t pidx = row * a.prow + z;             // element inside a population plane
     float f[19];
+    bool compute = true;
+    float rho = 1.0f, ux = 0.f, uy = 0.f, uz = 0.f;
     if (MODE == MODE_COLLIDE) {
+        const uint32_t fl = a.flags[idx];
+        if (fl & FL_SOLID) return;
         node_collide_only<FORCE>(f, a, fl, idx);
     } else {
-        const float *__restrict__ p = a.fin + idx;
-        const int sx = a.ny * a.nz, sy = a.nz;
-        // offsets to the x-1 / x+1 ... neighbours with the periodic wrap of :247-257
-        const int oxm = (fl & FL_AT_X0) ? (a.nx - 1) * sx : -sx;
-        const int oxp = (fl & FL_AT_X1) ? -(a.nx - 1) * sx : sx;
-        const int oym = (fl & FL_AT_Y0) ? (a.ny - 1) * sy : -sy;
-        const int oyp = (fl & FL_AT_Y1) ? -(a.ny - 1) * sy : sy;
-        const int ozm = (fl & FL_AT_Z0) ? (a.nz - 1) : -1;
-        const int ozp = (fl & FL_AT_Z1) ? -(a.nz - 1) : 1;
-        // pull: F[i][s] = f*[i - e_s][s]; source offset per direction
-#define OFF(ex, ey, ez)                                                                        \
-    ((ex > 0 ? oxm : (ex < 0 ? oxp : 0)) + (ey > 0 ? oym : (ey < 0 ? oyp : 0)) +               \
-     (ez > 0 ? ozm : (ez < 0 ? ozp : 0)))
-        if ((fl & FL_LINK_MASK) == 0) {
-#define X(s, ex, ey, ez, o) f[s] = __ldg(p + (size_t)s * N + OFF(ex, ey, ez));
+        // Speculative pull (SPEC): the class byte and all 19 populations of the common node
+        // (no solid link, no wrap, no BC) are requested together, so a bulk node pays ONE
+        // memory latency.  The buffers carry a guard band of a plane + a row at both ends, so
+        // the speculative addresses of boundary nodes are always mapped; what they fetch is
+        // replaced below.  Without SPEC (mostly-solid lattices) the class is read first.
+        const uint8_t cls = a.cls[idx];
+        if (!SPEC && cls == NODE_SOLID) return;
+        if (SPEC || cls != NODE_SOLID_WRITE) {
+#define X(s, ex, ey, ez, o) f[s] = __ldg(a.ppull[s] + pidx);
             D3Q19_DIRS(X)
 #undef X
         } else {
-            // half-way bounce-back (:267-268): source solid -> own opposite population
+#pragma unroll
+            for (int s = 0; s < 19; ++s) f[s] = 0.f;
+        }
+        // solid nodes keep f = F = w, rho = 1, v = 0 (:164-169, :390-392)
+        if (SPEC && cls == NODE_SOLID) return;
+        compute = cls != NODE_SOLID_WRITE;
+        if (MODE == MODE_EXTRACT && !compute) return;
+        bool pressure = false;
+        uint32_t slot = 0;
+        if (cls == NODE_SPECIAL) {
+            const uint32_t fl = a.flags[idx];
+            const int sx = a.ny * (int)a.prow, sy = (int)a.prow;
+            // offsets to the x-1 / x+1 ... neighbours with the periodic wrap of :247-257
+            const int oxm = (fl & FL_AT_X0) ? (a.nx - 1) * sx : -sx;
+            const int oxp = (fl & FL_AT_X1) ? -(a.nx - 1) * sx : sx;
+            const int oym = (fl & FL_AT_Y0) ? (a.ny - 1) * sy : -sy;
+            const int oyp = (fl & FL_AT_Y1) ? -(a.ny - 1) * sy : sy;
+            const int ozm = (fl & FL_AT_Z0) ? (a.nz - 1) : -1;
+            const int ozp = (fl & FL_AT_Z1) ? -(a.nz - 1) : 1;
+            // Only the directions the speculation got wrong are fetched again: the pull source
+            // is solid -> own opposite population (half-way bounce-back :267-268); the pull
+            // crosses a periodic face -> wrapped source (:247-257).
+#define OFF(ex, ey, ez)                                                                        \
+    ((ex > 0 ? oxm : (ex < 0 ? oxp : 0)) + (ey > 0 ? oym : (ey < 0 ? oyp : 0)) +               \
+     (ez > 0 ? ozm : (ez < 0 ? ozp : 0)))
+#define WRAPS(ex, ey, ez)                                                                      \
+    (fl & ((ex > 0 ? FL_AT_X0 : (ex < 0 ? FL_AT_X1 : 0u)) | (ey > 0 ? FL_AT_Y0 : (ey < 0 ? FL_AT_Y1 : 0u)) | \
+           (ez > 0 ? FL_AT_Z0 : (ez < 0 ? FL_AT_Z1 : 0u))))
 #define X(s, ex, ey, ez, o)                                                                    \
-    f[s] = ((fl >> s) & 1u) ? __ldg(p + (size_t)o * N) : __ldg(p + (size_t)s * N + OFF(ex, ey, ez));
+    if (s > 0) {                                                                               \
+        if ((fl >> s) & 1u) f[s] = __ldg(a.pown[o] + pidx);                                    \
+        else if (WRAPS(ex, ey, ez)) f[s] = __ldg(a.pown[s] + (pidx + OFF(ex, ey, ez)));        \
+    }
             D3Q19_DIRS(X)
 #undef X
-        }
+#undef WRAPS
 #undef OFF
-        float rho, ux, uy, uz;
-        node_update<FORCE, MODE>(f, a, fl, idx, rho, ux, uy, uz);
+            if (a.has_bc) {
+                const uint32_t bc = (fl >> FL_BC_SHIFT) & FL_BC_MASK;
+                if (bc) {
+                    const int face = (int)bc - 1;
+                    const int type = a.P.bc_type[face];
+                    if (type == 1) {                  // :274-281  F = feq(rho_bc, v_prev)
+                        float u0 = 0.f, u1 = 0.f, u2 = 0.f;
+                        slot = vbc_slot(a, face, idx);
+                        if (!(fl & FL_PIN_SOLID)) {
+                            u0 = a.vbc[3 * (size_t)slot + 0];
+                            u1 = a.vbc[3 * (size_t)slot + 1];
+                            u2 = a.vbc[3 * (size_t)slot + 2];
+                        }
+                        feq_all(f, a.P.bc_rho[face], u0, u1, u2);
+                        pressure = true;
+                    } else if (type == 2) {           // :283-288  F = feq(1, bc_vel)
+                        feq_all(f, 1.0f, a.P.bc_vel[face][0], a.P.bc_vel[face][1], a.P.bc_vel[face][2]);
+                    }
+                }
+            }
+        }
+        // one copy of the arithmetic for every fluid lane of the warp
+        if (compute) {
+            macro(f, a.P, FORCE, rho, ux, uy, uz);
+            if (MODE == MODE_STEP) {
+                if (pressure) {
+                    a.vbc[3 * (size_t)slot + 0] = ux;
+                    a.vbc[3 * (size_t)slot + 1] = uy;
+                    a.vbc[3 * (size_t)slot + 2] = uz;
+                }
+                collide(f, a.P, FORCE, rho, ux, uy, uz);
+            }
+        }
         if (MODE == MODE_EXTRACT) {
             write_user_fields<MODE>(a, idx, f, rho, ux, uy, uz);
             return;
         }
     }
-    float *__restrict__ q = a.fout + idx;
 #pragma unroll
-    for (int s = 0; s < 19; ++s) q[(size_t)s * N] = f[s];
+    for (int s = 0; s < 19; ++s) a.pout[s][pidx] = f[s];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -173,19 +231,16 @@ __global__ void __launch_bounds__(256) k_sparse(const StepArgs a) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.count) return;
     const uint32_t i = a.first + t;
-    const size_t N = a.stride;
     const uint32_t fl = a.has_bc ? a.flags[i] : 0u;
     float f[19];
     if (MODE == MODE_COLLIDE) {
         node_collide_only<FORCE>(f, a, fl, a.lin[i]);
     } else {
-        const float *__restrict__ p = a.fin;
-        const int32_t *__restrict__ nb = a.nbr + i;
-        f[0] = __ldg(p + i);
+        f[0] = __ldg(a.pown[0] + i);
 #define X(s, ex, ey, ez, o)                                                                    \
     if (s > 0) {                                                                               \
-        const int32_t j = __ldg(nb + (size_t)(s - 1) * N);                                     \
-        f[s] = j >= 0 ? __ldg(p + (size_t)s * N + j) : __ldg(p + (size_t)o * N + i);           \
+        const int32_t j = __ldg(a.nbr[s > 0 ? s - 1 : 0] + i);                                 \
+        f[s] = j >= 0 ? __ldg(a.pown[s] + (uint32_t)j) : __ldg(a.pown[o] + i);                 \
     }
         D3Q19_DIRS(X)
 #undef X
@@ -197,34 +252,50 @@ __global__ void __launch_bounds__(256) k_sparse(const StepArgs a) {
             return;
         }
     }
-    float *__restrict__ q = a.fout + i;
 #pragma unroll
-    for (int s = 0; s < 19; ++s) q[(size_t)s * N] = f[s];
+    for (int s = 0; s < 19; ++s) a.pout[s][i] = f[s];
 }
 
-#define LAUNCH_CASE(KERN, F, M)                                                                \
-    KERN<F, M><<<grid, block, 0, st>>>(a);                                                     \
-    break;
+template <bool FORCE, int MODE>
+static void launch_dense_t(const StepArgs &a, int block, cudaStream_t st) {
+    // block = (BX along z, BY rows); BX = nz rounded up to a warp, capped at `block`
+    int bx = (a.nz + 31) / 32 * 32;
+    if (bx > block) bx = block;
+    int by = block / bx;
+    if (by < 1) by = 1;
+    dim3 blk(bx, by, 1);
+    dim3 grid((a.row_count + by - 1) / by, (a.nz + bx - 1) / bx, 1);
+    if (a.spec)
+        k_dense<FORCE, MODE, true><<<grid, blk, 0, st>>>(a);
+    else
+        k_dense<FORCE, MODE, false><<<grid, blk, 0, st>>>(a);
+}
+
+template <bool FORCE, int MODE>
+static void launch_sparse_t(const StepArgs &a, int block, cudaStream_t st) {
+    const unsigned grid = (a.count + block - 1) / block;
+    k_sparse<FORCE, MODE><<<grid, block, 0, st>>>(a);
+}
+
+#define DISPATCH(FN)                                                                           \
+    switch ((a.force ? 4 : 0) | mode) {                                                        \
+        case 0: FN<false, MODE_STEP>(a, block, st); break;                                     \
+        case 1: FN<false, MODE_EXTRACT>(a, block, st); break;                                  \
+        case 2: FN<false, MODE_COLLIDE>(a, block, st); break;                                  \
+        case 4: FN<true, MODE_STEP>(a, block, st); break;                                      \
+        case 5: FN<true, MODE_EXTRACT>(a, block, st); break;                                   \
+        case 6: FN<true, MODE_COLLIDE>(a, block, st); break;                                   \
+        default: return cudaErrorInvalidValue;                                                 \
+    }
 
 static cudaError_t launch_any(bool sparse, int mode, const StepArgs &a, int block, cudaStream_t st) {
-    if (a.count == 0) return cudaSuccess;
-    if (block <= 0 || block > 256) block = 256;
-    const unsigned grid = (a.count + block - 1) / block;
-    const int key = (sparse ? 8 : 0) | (a.force ? 4 : 0) | mode;
-    switch (key) {
-        case 0: LAUNCH_CASE(k_dense, false, MODE_STEP)
-        case 1: LAUNCH_CASE(k_dense, false, MODE_EXTRACT)
-        case 2: LAUNCH_CASE(k_dense, false, MODE_COLLIDE)
-        case 4: LAUNCH_CASE(k_dense, true, MODE_STEP)
-        case 5: LAUNCH_CASE(k_dense, true, MODE_EXTRACT)
-        case 6: LAUNCH_CASE(k_dense, true, MODE_COLLIDE)
-        case 8: LAUNCH_CASE(k_sparse, false, MODE_STEP)
-        case 9: LAUNCH_CASE(k_sparse, false, MODE_EXTRACT)
-        case 10: LAUNCH_CASE(k_sparse, false, MODE_COLLIDE)
-        case 12: LAUNCH_CASE(k_sparse, true, MODE_STEP)
-        case 13: LAUNCH_CASE(k_sparse, true, MODE_EXTRACT)
-        case 14: LAUNCH_CASE(k_sparse, true, MODE_COLLIDE)
-        default: return cudaErrorInvalidValue;
+    if (block <= 0 || block > 256 || block % 32) block = 256;
+    if (sparse) {
+        if (a.count == 0) return cudaSuccess;
+        DISPATCH(launch_sparse_t)
+    } else {
+        if (a.row_count == 0) return cudaSuccess;
+        DISPATCH(launch_dense_t)
     }
     return cudaGetLastError();
 }

@@ -21,19 +21,37 @@
 #define FL_AT_Z1 (1u << 29)
 
 enum { MODE_STEP = 0, MODE_EXTRACT = 1, MODE_COLLIDE = 2 };
+// dense node classes: BULK = fluid, no solid link / wrap / BC (the speculative pull is final);
+// SOLID = nothing to do; SPECIAL = fluid that needs its link word; SOLID_WRITE = solid node
+// sharing a 32-byte sector with a fluid node: it stores (dead) values so that the sector is
+// written whole and L2 never has to read-modify-write it
+enum { NODE_BULK = 0, NODE_SOLID = 1, NODE_SPECIAL = 2, NODE_SOLID_WRITE = 3 };
 
 struct StepArgs {
-    // populations, SoA: plane s at  base + s*stride  (post-collision state of the pipeline)
-    const float *fin;
-    float *fout;
+    // populations, SoA, one plane per direction (post-collision state of the pipeline).
+    // Plane base pointers are passed ready-made so that every access is
+    // "uniform 64-bit base + 32-bit node index" (one IMAD.WIDE per load/store):
+    //   pown[s]  plane s of the input buffer          pout[s]  plane s of the output buffer
+    //   ppull[s] = pown[s] - (ex*ny*nz + ey*nz + ez)  pull source of a node without wrap
+    const float *pown[19];
+    const float *ppull[19];
+    float *pout[19];
     size_t stride;
-    // node range processed by this launch: [first, first+count)
+    // sparse: node range processed by this launch: [first, first+count)
     uint32_t first, count;
+    // dense: z-rows [row_first, row_first+row_count) (row = i*ny + j); element of node (row, k)
+    // in a population plane is row*prow + k.  SoA layout: prow = nz, planes `stride` apart;
+    // row-blocked layout [row][19][nzp]: prow = 19*nzp, planes nzp apart.
+    uint32_t row_first, row_count, prow;
+    int spec;                       // 1: speculative pull (few solid nodes)
     int nx, ny, nz;                 // extents of this context's lattice (incl. ghost planes)
     // dense: link word per node.  sparse: BC word per stored node (bits 20..23), may be null
     const uint32_t *flags;
+    // dense: node class byte (NODE_BULK / NODE_SOLID / NODE_SPECIAL); only NODE_SPECIAL nodes
+    // (solid links, periodic wrap, face BC) read their 32-bit link word
+    const uint8_t *cls;
     // sparse only
-    const int32_t *nbr;             // [18][stride] pull table, -1 = bounce
+    const int32_t *nbr[18];         // rows of the [18][stride] pull table, -1 = bounce
     const uint32_t *lin;            // [n_fluid] linear index of each stored node
     // user-visible dense arrays (reference layout), used by MODE_EXTRACT / MODE_COLLIDE
     float *rho;                     // [N]
