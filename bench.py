@@ -160,6 +160,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sparse", action="store_true", help="use the compacted fluid-list storage")
     ap.add_argument("--size", type=int, default=SLAB, help="cube edge / planes per GPU (default 256)")
+    ap.add_argument("--workload", default="cavity", choices=["cavity", "porous"],
+                    help="cavity: BASELINE config 2 (headline); porous: config 3, periodic sphere pack at "
+                         "~20%% porosity, body force fx=1e-6 (use with --sparse)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -178,25 +181,36 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n_gpus = world
 
-    from taichi_lbm3d_b200.geometry import cavity
+    from taichi_lbm3d_b200.geometry import cavity, sphere_pack
     n = args.size
     ny = nz = n
     gnx = n * n_gpus
-    solid = cavity(gnx, ny, nz)
+    porous = args.workload == "porous"
+    if porous:
+        r0 = max(3.0, 8.0 * n / 512.0)
+        solid = sphere_pack(gnx, ny, nz, 0.80, r0, 2 * r0, seed=n, periodic=True)
+    else:
+        solid = cavity(gnx, ny, nz)
     nfl_total = int((solid == 0).sum())
+
+    def configure(lb):
+        if porous:
+            lb.set_force([1e-6, 0.0, 0.0])
+        else:
+            lb.set_bc_vel_x1(LID)
 
     if world == 1:
         from taichi_lbm3d_b200 import LB3D_Solver_Single_Phase
         lb = LB3D_Solver_Single_Phase(gnx, ny, nz, sparse_storage=args.sparse)
         lb.solid.from_numpy(solid)
-        lb.set_bc_vel_x1(LID)
+        configure(lb)
         lb.init_simulation()
         stepper = lb
     else:
         from taichi_lbm3d_b200.multi_gpu import SlabSolver
         lb = SlabSolver(gnx, ny, nz, sparse_storage=args.sparse)
         lb.set_solid(solid)
-        lb.set_bc_vel_x1(LID)
+        configure(lb)
         lb.init_simulation()
         stepper = lb
 
@@ -241,7 +255,7 @@ def main():
         t0 = time.perf_counter()
         lb2 = LB3D_Solver_Single_Phase(gnx, ny, nz, sparse_storage=args.sparse)
         lb2.solid.from_numpy(pinned.numpy())            # host geometry in
-        lb2.set_bc_vel_x1(LID)
+        configure(lb2)
         lb2.init_simulation()                           # H2D + table build
         for _ in range(args.steps):                     # the reference scripts' loop: one call per step
             lb2.step()
@@ -263,15 +277,18 @@ def main():
 
     peak, peak_src = measured_peak()
     achieved = B_PER_LUP * (nfl_total / n_gpus) * args.steps / (ms * 1e-3) / 1e9    # GB/s per GPU
-    workload = "cavity%d_%s" % (n, "sparse" if args.sparse else "dense")
+    workload = "%s%d_%s" % (args.workload, n, "sparse" if args.sparse else "dense")
+    wl_text = ("periodic sphere pack %dx%dx%d at porosity %.3f, body force fx=1e-6 (BASELINE config 3 shape)"
+               % (gnx, ny, nz, nfl_total / float(gnx * ny * nz))) if porous else \
+        ("lid-driven cavity %dx%dx%d, lid vz=0.1 on x1 (BASELINE config 2%s)"
+         % (gnx, ny, nz, "" if n_gpus == 1 else ", x-slabs of %d planes per GPU" % n))
     line = {
         "metric": "mlups", "value": mlups, "unit": "MLUPS", "n_gpus": n_gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": mlups / 900.0 if n_gpus == 1 else None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "lid-driven cavity %dx%dx%d %s, D3Q19 MRT single phase, lid vz=0.1 on x1 "
-                               "(BASELINE config 2%s)" % (gnx, ny, nz, "sparse storage" if args.sparse else "dense",
-                                                          "" if n_gpus == 1 else ", x-slabs of %d planes per GPU" % n),
+        "config": {"workload": "%s; D3Q19 MRT single phase, %s" % (wl_text, "sparse storage (compact fluid list)"
+                                                                    if args.sparse else "dense storage"),
                    "fluid_nodes": nfl_total, "l2_policy": "inputs_exceed_l2 (%.2f GB of populations per GPU vs 126 MB L2)"
                    % (2 * 19 * 4 * n * ny * nz / 1e9),
                    "vs_baseline_note": "900 MLUPS: README.md:5, one A100, grid size unstated",

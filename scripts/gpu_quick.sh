@@ -1,20 +1,20 @@
-# quick GPU check: smoke + gpu tests + bench (dense layouts, sparse)
+# quick GPU check: smoke + gpu tests + bench variants
 (time python __graft_entry__.py smoke) > gpurun_out/smoke.log 2>&1
 (time timeout 1500 python -m pytest tests -m gpu -x -q) > gpurun_out/pytest.log 2>&1
 tail -4 gpurun_out/smoke.log; tail -12 gpurun_out/pytest.log
 run() { name=$1; shift; env "$@" python bench.py --steps 200 --warmup 20 --no-cpu-baseline $EXTRA > gpurun_out/bench_$name.json 2>> gpurun_out/bench.err; }
 : > gpurun_out/bench.err
-EXTRA="" run blocked LBM3D_LAYOUT=1
-EXTRA="" run soa LBM3D_LAYOUT=0
-EXTRA="" run blocked_nospec LBM3D_LAYOUT=1 LBM3D_SPEC=0
-EXTRA="" run blocked_b128 LBM3D_LAYOUT=1 LBM3D_BLOCK=128
-EXTRA="--sparse" run sparse LBM3D_LAYOUT=1
+EXTRA="" run dense A=1
+EXTRA="--sparse" run cav_sparse A=1
+EXTRA="--sparse --workload porous --size 384" run por384_sparse A=1
+EXTRA="--sparse --workload porous --size 384" run por384_sparse_nopf LBM3D_PREFETCH=0
+EXTRA="--sparse --workload porous --size 384" run por384_sparse_full LBM3D_SPARSE_TABLE=full
 python - <<'PY'
 import json,glob
 for f in sorted(glob.glob("gpurun_out/bench_*.json")):
     try:
         d=json.loads(open(f).read().strip().splitlines()[-1])
-        print("%-40s MLUPS %.0f  ms/step %.4f  frac %.4f  e2e %.0f"%(f, d["value"], d["ms_per_step"], d["roofline"]["frac"], d.get("e2e",{}).get("value",0)))
+        print("%-44s MLUPS %.0f  ms/step %.4f  frac %.4f  e2e %.0f  nf %d"%(f, d["value"], d["ms_per_step"], d["roofline"]["frac"], d.get("e2e",{}).get("value",0), d["config"]["fluid_nodes"]))
     except Exception as e: print(f, "ERR", e)
 PY
 tail -3 gpurun_out/bench.err

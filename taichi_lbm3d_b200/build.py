@@ -63,12 +63,13 @@ def build(force=False, verbose=False):
     ccbin = ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []
     objs = []
     procs = []
+    tune = os.environ.get("LBM3D_NVCC_FLAGS", "").split()      # tuning experiments only
     for obj, src, extra in UNITS:
         srcp = os.path.join(CSRC, src)
         if not os.path.exists(srcp):
             continue
         objp = os.path.join(OBJDIR, obj)
-        cmd = [nvcc] + ccbin + COMMON + extra + ["-c", srcp, "-o", objp]
+        cmd = [nvcc] + ccbin + COMMON + extra + tune + ["-c", srcp, "-o", objp]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env)))

@@ -55,7 +55,12 @@ struct lbm_ctx {
     // device buffers
     int8_t *d_solid = nullptr;
     uint32_t *d_flags = nullptr;   // dense: [N] link words; sparse: [nf] BC words
-    int32_t *d_nbr = nullptr;      // sparse: [18][stride]
+    int32_t *d_nbr = nullptr;      // sparse, full table: [18][stride]
+    int32_t *d_rb = nullptr;       // sparse, compressed table: [8][stride] neighbour-row ranks
+    int32_t *d_exc = nullptr;      // sparse, compressed table: [18][exc_stride] explicit sources
+    size_t n_exc = 0, exc_stride = 0;
+    int compressed = 1;
+    uint32_t prefetch_dist = 0;    // sparse: table prefetch distance in nodes (multiple of the block)
     uint32_t *d_lin = nullptr;     // sparse: [nf]
     uint32_t *d_rank = nullptr;    // sparse: [N+1] exclusive fluid count (kept for plane lookups)
     uint8_t *d_cls = nullptr;      // dense: [N] node class (NODE_BULK / NODE_SOLID / NODE_SPECIAL)
@@ -196,10 +201,23 @@ struct IsFluid {
     __host__ __device__ uint32_t operator()(const int8_t &s) const { return s == 0 ? 1u : 0u; }
 };
 
+// true pull sources of a fluid node: j[s-1] = compact index of i - e_s, or -1 (bounce)
+__device__ __forceinline__ void true_sources(const GeoParams &g, const int8_t *solid, const uint32_t *rank,
+                                             int x, int y, int z, int32_t (&j)[18]) {
+    for (int s = 1; s < 19; ++s) {
+        size_t src;
+        j[s - 1] = (pull_source(g, x, y, z, s, src) && solid[src] == 0) ? (int32_t)rank[src] : -1;
+    }
+}
+
+// Pass 1 of the sparse tables: linear index, link word (bounce bits + BC bits), and either
+// the full 18-entry pull table or the compressed one (8 neighbour-row ranks; nodes whose
+// sources do not follow the rank rule are flagged and given a slot in the exception table).
 __global__ void k_build_sparse(const GeoParams g, const int8_t *__restrict__ solid,
                                const uint32_t *__restrict__ rank, size_t stride,
-                               uint32_t *__restrict__ lin, uint32_t *__restrict__ bcw,
-                               int32_t *__restrict__ nbr) {
+                               uint32_t *__restrict__ lin, uint32_t *__restrict__ flags,
+                               int32_t *__restrict__ nbr, int32_t *__restrict__ rb,
+                               uint32_t *__restrict__ exc_count) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t N = (size_t)g.nx * g.ny * g.nz;
     if (idx >= N || solid[idx] != 0) return;
@@ -208,13 +226,74 @@ __global__ void k_build_sparse(const GeoParams g, const int8_t *__restrict__ sol
     const int y = (int)(t % g.ny), x = (int)(t / g.ny);
     const uint32_t r = rank[idx];
     lin[r] = (uint32_t)idx;
-    bcw[r] = bc_word(g, solid, x, y, z);
-    for (int s = 1; s < 19; ++s) {
-        size_t src;
-        int32_t j = -1;
-        if (pull_source(g, x, y, z, s, src) && solid[src] == 0) j = (int32_t)rank[src];
-        nbr[(size_t)(s - 1) * stride + r] = j;
+    int32_t j[18];
+    true_sources(g, solid, rank, x, y, z, j);
+    uint32_t fl = bc_word(g, solid, x, y, z);
+    for (int s = 1; s < 19; ++s)
+        if (j[s - 1] < 0) fl |= 1u << s;
+    if (nbr != nullptr)
+        for (int s = 1; s < 19; ++s) nbr[(size_t)(s - 1) * stride + r] = j[s - 1];
+    if (rb != nullptr) {
+        const int center[8] = {1, 2, 3, 4, 7, 8, 9, 10};     // directions (ex,ey,0) of the 8 rows
+        int32_t rbv[8];
+        for (int k = 0; k < 8; ++k) {
+            size_t src;
+            rbv[k] = pull_source(g, x, y, z, center[k], src) ? (int32_t)rank[src] : 0;
+        }
+        bool ok = true;
+        const bool ghost = g.halo_x && (x == 0 || x == g.nx - 1);   // never updated
+#define X(s, ex, ey, ez, o)                                                                    \
+    if (s > 0 && j[s > 0 ? s - 1 : 0] >= 0 && comp_source<ex, ey, ez>(r, fl, rbv) != j[s > 0 ? s - 1 : 0]) ok = false;
+        D3Q19_DIRS(X)
+#undef X
+        if (!ok && !ghost) {
+            fl |= FL_EXCEPTION;
+            rbv[0] = (int32_t)atomicAdd(exc_count, 1u);
+        }
+        for (int k = 0; k < 8; ++k) rb[(size_t)k * stride + r] = rbv[k];
     }
+    flags[r] = fl;
+}
+
+// Pass 2: explicit sources of the flagged nodes
+__global__ void k_fill_exceptions(const GeoParams g, const int8_t *__restrict__ solid,
+                                  const uint32_t *__restrict__ rank, size_t stride,
+                                  const uint32_t *__restrict__ flags, const int32_t *__restrict__ rb,
+                                  int32_t *__restrict__ exc, size_t exc_stride) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t N = (size_t)g.nx * g.ny * g.nz;
+    if (idx >= N || solid[idx] != 0) return;
+    const uint32_t r = rank[idx];
+    if (!(flags[r] & FL_EXCEPTION)) return;
+    const int z = (int)(idx % g.nz);
+    const size_t t = idx / g.nz;
+    const int y = (int)(t % g.ny), x = (int)(t / g.ny);
+    int32_t j[18];
+    true_sources(g, solid, rank, x, y, z, j);
+    const uint32_t slot = (uint32_t)rb[r];
+    for (int s = 0; s < 18; ++s) exc[(size_t)s * exc_stride + slot] = j[s];
+}
+
+// lbm_get_neighbor_table: expand whichever table the step kernel uses into [18][nf]
+__global__ void k_decode_table(StepArgs a, uint32_t nf, int32_t *__restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nf) return;
+    if (!a.compressed) {
+        for (int s = 0; s < 18; ++s) out[(size_t)s * nf + i] = a.nbr[s][i];
+        return;
+    }
+    const uint32_t fl = a.flags[i];
+    int32_t rb[8];
+    for (int k = 0; k < 8; ++k) rb[k] = a.rb[k][i];
+#define X(s, ex, ey, ez, o)                                                                    \
+    if (s > 0) {                                                                               \
+        int32_t j = -1;                                                                        \
+        if (!((fl >> s) & 1u))                                                                 \
+            j = (fl & FL_EXCEPTION) ? a.exc[s > 0 ? s - 1 : 0][(uint32_t)rb[0]] : comp_source<ex, ey, ez>(i, fl, rb); \
+        out[(size_t)(s > 0 ? s - 1 : 0) * nf + i] = j;                                         \
+    }
+    D3Q19_DIRS(X)
+#undef X
 }
 
 __global__ void k_fill(float *p, size_t n, float v) {
@@ -304,6 +383,7 @@ const double kInvM[19][19] = {
 void free_device(lbm_ctx *c) {
     cudaFree(c->d_solid); cudaFree(c->d_flags); cudaFree(c->d_nbr); cudaFree(c->d_lin);
     cudaFree(c->d_rank); cudaFree(c->d_fbase[0]); cudaFree(c->d_fbase[1]); cudaFree(c->d_rho);
+    cudaFree(c->d_rb); cudaFree(c->d_exc); c->d_rb = nullptr; c->d_exc = nullptr;
     cudaFree(c->d_cls); c->d_cls = nullptr; c->d_fbase[0] = c->d_fbase[1] = nullptr;
     cudaFree(c->d_v); cudaFree(c->d_F); cudaFree(c->d_vbc); cudaFree(c->d_scalar);
     c->d_solid = nullptr; c->d_flags = nullptr; c->d_nbr = nullptr; c->d_lin = nullptr;
@@ -323,7 +403,13 @@ void fill_args(const lbm_ctx *c, StepArgs &a) {
     a.nx = c->cfg.nx; a.ny = c->cfg.ny; a.nz = c->cfg.nz;
     a.flags = c->d_flags;
     a.cls = c->d_cls;
-    for (int s = 0; s < 18; ++s) a.nbr[s] = c->d_nbr ? c->d_nbr + (size_t)s * c->stride : nullptr;
+    for (int s = 0; s < 18; ++s) {
+        a.nbr[s] = c->d_nbr ? c->d_nbr + (size_t)s * c->stride : nullptr;
+        a.exc[s] = c->d_exc ? c->d_exc + (size_t)s * c->exc_stride : nullptr;
+    }
+    for (int k = 0; k < 8; ++k) a.rb[k] = c->d_rb ? c->d_rb + (size_t)k * c->stride : nullptr;
+    a.compressed = c->cfg.sparse ? c->compressed : 0;
+    a.prefetch_dist = c->prefetch_dist;
     a.lin = c->d_lin;
     a.rho = c->d_rho; a.v = c->d_v; a.F = nullptr;
     a.vbc = c->d_vbc;
@@ -621,18 +707,45 @@ int lbm_init(lbm_ctx *c) {
         c->nf = (size_t)last_rank + (last_solid == 0 ? 1 : 0);
         const uint32_t nf32 = (uint32_t)c->nf;
         CU(c, cudaMemcpy(c->d_rank + N, &nf32, sizeof(uint32_t), cudaMemcpyHostToDevice));
-        c->stride = (c->nf + 31) / 32 * 32;
-        if (c->stride == 0) c->stride = 32;
+        // planes padded to the 256-node block: the sparse kernel bulk-copies whole table slices
+        c->stride = (c->nf + 255) / 256 * 256;
+        if (c->stride == 0) c->stride = 256;
         CU(c, cudaMalloc(&c->d_lin, c->stride * sizeof(uint32_t)));
         CU(c, cudaMalloc(&c->d_flags, c->stride * sizeof(uint32_t)));
-        CU(c, cudaMalloc(&c->d_nbr, c->stride * 18 * sizeof(int32_t)));
-        CU(c, cudaMemset(c->d_nbr, 0xff, c->stride * 18 * sizeof(int32_t)));
+        // one wave of resident blocks ahead: 148 SMs x 8 blocks x 256 nodes
+        c->prefetch_dist = 148u * 8u * 256u;
+        if (const char *pd = getenv("LBM3D_PREFETCH")) c->prefetch_dist = (uint32_t)atol(pd) / 256u * 256u;
+        c->compressed = 1;
+        if (const char *tb = getenv("LBM3D_SPARSE_TABLE")) c->compressed = strcmp(tb, "full") == 0 ? 0 : 1;
         CU(c, cudaMemset(c->d_flags, 0, c->stride * sizeof(uint32_t)));
         CU(c, cudaMemset(c->d_lin, 0, c->stride * sizeof(uint32_t)));
+        uint32_t *d_cnt = (uint32_t *)c->d_scalar;
+        CU(c, cudaMemset(d_cnt, 0, sizeof(uint32_t)));
+        if (c->compressed) {
+            CU(c, cudaMalloc(&c->d_rb, c->stride * 8 * sizeof(int32_t)));
+            CU(c, cudaMemset(c->d_rb, 0, c->stride * 8 * sizeof(int32_t)));
+        } else {
+            CU(c, cudaMalloc(&c->d_nbr, c->stride * 18 * sizeof(int32_t)));
+            CU(c, cudaMemset(c->d_nbr, 0xff, c->stride * 18 * sizeof(int32_t)));
+        }
         k_build_sparse<<<nblocks(N, 256), 256>>>(g, c->d_solid, c->d_rank, c->stride, c->d_lin,
-                                                  c->d_flags, c->d_nbr);
+                                                  c->d_flags, c->d_nbr, c->d_rb, d_cnt);
         CU(c, cudaGetLastError());
         c->launches++;
+        if (c->compressed) {
+            uint32_t ne = 0;
+            CU(c, cudaMemcpy(&ne, d_cnt, sizeof ne, cudaMemcpyDeviceToHost));
+            c->n_exc = ne;
+            c->exc_stride = (ne + 31) / 32 * 32 + 32;
+            CU(c, cudaMalloc(&c->d_exc, c->exc_stride * 18 * sizeof(int32_t)));
+            CU(c, cudaMemset(c->d_exc, 0xff, c->exc_stride * 18 * sizeof(int32_t)));
+            if (ne) {
+                k_fill_exceptions<<<nblocks(N, 256), 256>>>(g, c->d_solid, c->d_rank, c->stride, c->d_flags,
+                                                            c->d_rb, c->d_exc, c->exc_stride);
+                CU(c, cudaGetLastError());
+                c->launches++;
+            }
+        }
         if (g.halo_x) {
             uint32_t r[4];
             const size_t at[4] = {plane, plane * 2, plane * (nx - 2), plane * (nx - 1)};
@@ -860,8 +973,16 @@ int lbm_get_neighbor_table(lbm_ctx *c, int32_t *dst) {
     if (!dst) FAIL(c, LBM_ERR_INVALID, "null destination");
     if (!c->inited || !c->cfg.sparse) FAIL(c, LBM_ERR_STATE, "needs an initialised sparse context");
     CU(c, cudaSetDevice(c->cfg.device));
-    CU(c, cudaMemcpy2D(dst, c->nf * sizeof(int32_t), c->d_nbr, c->stride * sizeof(int32_t),
-                       c->nf * sizeof(int32_t), 18, cudaMemcpyDefault));
+    int32_t *tmp = nullptr;
+    CU(c, cudaMalloc(&tmp, (c->nf ? c->nf : 1) * 18 * sizeof(int32_t)));
+    StepArgs a;
+    fill_args(c, a);
+    if (c->nf) k_decode_table<<<nblocks(c->nf, 256), 256>>>(a, (uint32_t)c->nf, tmp);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpy(dst, tmp, c->nf * 18 * sizeof(int32_t), cudaMemcpyDefault);
+    cudaFree(tmp);
+    CU(c, e);
+    c->launches++;
     return LBM_OK;
 }
 

@@ -24,6 +24,20 @@
 namespace LBM_NS {
 using namespace d3q19;
 
+// Loads that must be ISSUED where they are written: volatile asm keeps ptxas from sinking an
+// index load down to its first use, which would chain the table look-ups into one DRAM
+// round trip per neighbour row instead of one for the whole table.
+__device__ __forceinline__ int32_t ld_early_s32(const int32_t *p) {
+    int32_t v;
+    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_early_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
 __device__ __forceinline__ uint32_t vbc_slot(const StepArgs &a, int face, uint32_t lin) {
     const uint32_t z = lin % (uint32_t)a.nz;
     const uint32_t t = lin / (uint32_t)a.nz;
@@ -226,24 +240,137 @@ __global__ void __launch_bounds__(256) k_dense(const StepArgs a) {
 // ---------------------------------------------------------------------------------------------
 // sparse storage: compacted fluid list + 18-neighbour pull table
 // ---------------------------------------------------------------------------------------------
-template <bool FORCE, int MODE>
-__global__ void __launch_bounds__(256) k_sparse(const StepArgs a) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.count) return;
-    const uint32_t i = a.first + t;
-    const uint32_t fl = a.has_bc ? a.flags[i] : 0u;
+#ifndef LBM_SPARSE_MINB
+#define LBM_SPARSE_MINB 8
+#endif
+#define SPARSE_BLOCK 256
+
+// Gathers of the sparse kernel touch partial 128-byte lines (pores are a few nodes wide), but
+// every line is consumed completely within one step by neighbouring warps.  The L2 prefetch-size
+// hint makes a miss bring the whole line (or line pair) from HBM in one burst instead of one
+// 32-byte sector per requesting warp.
+#ifndef LBM_SPARSE_L2HINT
+#define LBM_SPARSE_L2HINT 0
+#endif
+__device__ __forceinline__ float ldg_gather(const float *p) {
+    float v;
+#if LBM_SPARSE_L2HINT == 256
+    asm("ld.global.nc.L2::256B.f32 %0, [%1];" : "=f"(v) : "l"(p));
+#elif LBM_SPARSE_L2HINT == 128
+    asm("ld.global.nc.L2::128B.f32 %0, [%1];" : "=f"(v) : "l"(p));
+#else
+    v = __ldg(p);
+#endif
+    return v;
+}
+
+// ---- TMA bulk copy + mbarrier (sm_90+/sm_100a PTX) ----------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// Sparse step.  A block owns the 256 consecutive stored nodes [B*256, B*256+256) of the
+// compact list (B counted from the start of the arrays so that every bulk copy is 16-byte
+// aligned); threads outside [first, first+count) idle.
+//
+// Phase 1 (COMP): one elected thread pulls the block's slice of the 9 table arrays (8 row
+// ranks + link word, 9 KB) into shared memory with TMA bulk copies on one mbarrier.  Doing
+// this through registers instead lets ptxas sink each index load to its first use and
+// chains up to 9 DRAM round trips; through shared memory it is exactly one, costs no
+// registers, and 9 instructions per block.
+// Phase 2: 19 gathers, then the same BC / macro / collide / store code as the dense kernel.
+template <bool FORCE, int MODE, bool COMP>
+__global__ void __launch_bounds__(SPARSE_BLOCK, LBM_SPARSE_MINB) k_sparse(const StepArgs a) {
+    __shared__ alignas(128) int32_t s_tab[COMP ? 9 : 1][SPARSE_BLOCK];
+    __shared__ uint64_t s_bar;
+    const uint32_t base = (blockIdx.x + a.first / SPARSE_BLOCK) * SPARSE_BLOCK;
+    const uint32_t i = base + threadIdx.x;
+    if (COMP && MODE != MODE_COLLIDE) {
+        if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&s_bar, 9u * SPARSE_BLOCK * 4u);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) bulk_g2s(&s_tab[k][0], a.rb[k] + base, SPARSE_BLOCK * 4u, &s_bar);
+            bulk_g2s(&s_tab[COMP ? 8 : 0][0], a.flags + base, SPARSE_BLOCK * 4u, &s_bar);
+            if (MODE == MODE_STEP && a.prefetch_dist) {
+                // ask L2 for the table slice of the block one wave ahead
+                const uint32_t pb = base + a.prefetch_dist;
+                if (pb + SPARSE_BLOCK <= a.first + a.count) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.rb[k] + pb), "r"(SPARSE_BLOCK * 4u) : "memory");
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.flags + pb), "r"(SPARSE_BLOCK * 4u) : "memory");
+                }
+            }
+        }
+    }
+    const bool active = i >= a.first && i < a.first + a.count;
     float f[19];
+    uint32_t fl = 0;
     if (MODE == MODE_COLLIDE) {
+        if (!active) return;
+        fl = a.flags[i];
         node_collide_only<FORCE>(f, a, fl, a.lin[i]);
     } else {
-        f[0] = __ldg(a.pown[0] + i);
+        if (COMP) {
+            if (active) f[0] = __ldg(a.pown[0] + i);
+            mbar_wait(&s_bar, 0);
+            if (!active) return;
+            fl = (uint32_t)s_tab[COMP ? 8 : 0][threadIdx.x];
+            if (!(fl & FL_EXCEPTION)) {
+                int32_t rb[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) rb[k] = s_tab[COMP ? k : 0][threadIdx.x];
+#define X(s, ex, ey, ez, o)                                                                    \
+    if (s > 0) {                                                                               \
+        const int32_t j = comp_source<ex, ey, ez>(i, fl, rb);                                  \
+        f[s] = ((fl >> s) & 1u) ? ldg_gather(a.pown[o] + i) : ldg_gather(a.pown[s] + (uint32_t)j); \
+    }
+                D3Q19_DIRS(X)
+#undef X
+            } else {
+                const uint32_t slot = (uint32_t)s_tab[0][threadIdx.x];
+#define X(s, ex, ey, ez, o)                                                                    \
+    if (s > 0) {                                                                               \
+        f[s] = ((fl >> s) & 1u) ? __ldg(a.pown[o] + i)                                         \
+                                : __ldg(a.pown[s] + (uint32_t)__ldg(a.exc[s > 0 ? s - 1 : 0] + slot)); \
+    }
+                D3Q19_DIRS(X)
+#undef X
+            }
+        } else {
+            if (!active) return;
+            fl = a.has_bc ? a.flags[i] : 0u;
+            f[0] = __ldg(a.pown[0] + i);
 #define X(s, ex, ey, ez, o)                                                                    \
     if (s > 0) {                                                                               \
         const int32_t j = __ldg(a.nbr[s > 0 ? s - 1 : 0] + i);                                 \
         f[s] = j >= 0 ? __ldg(a.pown[s] + (uint32_t)j) : __ldg(a.pown[o] + i);                 \
     }
-        D3Q19_DIRS(X)
+            D3Q19_DIRS(X)
 #undef X
+        }
         float rho, ux, uy, uz;
         const uint32_t lin = (MODE == MODE_EXTRACT || a.has_bc) ? a.lin[i] : 0u;
         node_update<FORCE, MODE>(f, a, fl, lin, rho, ux, uy, uz);
@@ -273,8 +400,14 @@ static void launch_dense_t(const StepArgs &a, int block, cudaStream_t st) {
 
 template <bool FORCE, int MODE>
 static void launch_sparse_t(const StepArgs &a, int block, cudaStream_t st) {
-    const unsigned grid = (a.count + block - 1) / block;
-    k_sparse<FORCE, MODE><<<grid, block, 0, st>>>(a);
+    (void)block;
+    block = SPARSE_BLOCK;
+    const unsigned b0 = a.first / SPARSE_BLOCK, b1 = (a.first + a.count + SPARSE_BLOCK - 1) / SPARSE_BLOCK;
+    const unsigned grid = b1 - b0;
+    if (a.compressed)
+        k_sparse<FORCE, MODE, true><<<grid, block, 0, st>>>(a);
+    else
+        k_sparse<FORCE, MODE, false><<<grid, block, 0, st>>>(a);
 }
 
 #define DISPATCH(FN)                                                                           \
