@@ -141,13 +141,23 @@ int lbm_get_link_flags(lbm_ctx *ctx, uint32_t *dst_host_or_dev);
  *                       dst holds 5*count floats, [5][count].
  * lbm_halo_unpack(side) side 0: src (sent by the LEFT rank's pack(1)) -> e_x=+1 of plane 0
  *                       side 1: src (sent by the RIGHT rank's pack(0)) -> e_x=-1 of plane 3
- * Both act on the CURRENT post-collision buffer, so the sequence per step is
- *   [lbm_step_begin once] ; repeat { pack, exchange, unpack ; lbm_step(1) }
- * and one more exchange before fields are read.  For overlap, lbm_step_planes updates a
- * range of owned x planes without advancing the buffers; lbm_step_flip advances them. */
+ * `which` = 0 acts on the CURRENT post-collision buffer, 1 on the NEXT one (the output of
+ * lbm_step_planes before lbm_step_flip).  Plain sequence:
+ *   lbm_step_begin ; exchange(0) ; repeat { lbm_step(1) ; exchange(0) }
+ * Overlapped sequence per step: lbm_step_planes(first owned), lbm_step_planes(last owned) ;
+ * exchange(1) on a side stream || lbm_step_planes(interior) ; join ; lbm_step_flip. */
 int64_t lbm_halo_count(lbm_ctx *ctx, int plane);
-int lbm_halo_pack(lbm_ctx *ctx, int side, float *dst_dev, void *cuda_stream);
-int lbm_halo_unpack(lbm_ctx *ctx, int side, const float *src_dev, void *cuda_stream);
+int lbm_halo_pack(lbm_ctx *ctx, int side, int which, float *dst_dev, void *cuda_stream);
+int lbm_halo_unpack(lbm_ctx *ctx, int side, int which, const float *src_dev, void *cuda_stream);
+/* The whole slab loop in native code: NCCL is bound at run time (dlopen of the libnccl.so.2
+ * already loaded by torch).  Rank 0 calls lbm_comm_unique_id (128 bytes), the host side
+ * broadcasts it (torch.distributed), every rank calls lbm_comm_init after lbm_init.
+ * lbm_run_slab = nsteps x { boundary planes ; ncclSend/ncclRecv of the 5+5 face populations
+ * on a side stream || interior planes ; join } when overlap != 0.  world = 1 needs no NCCL
+ * (the ring closes on the slab itself). */
+int lbm_comm_unique_id(void *out128);
+int lbm_comm_init(lbm_ctx *ctx, const void *id128, int world, int rank);
+int lbm_run_slab(lbm_ctx *ctx, int nsteps, int overlap, void *cuda_stream);
 /* first collision of the user-visible state (:222-241) if the pipeline is not running
  * yet; counts as the collision half of the next step.  Returns 1 if already running. */
 int lbm_step_begin(lbm_ctx *ctx, void *cuda_stream);

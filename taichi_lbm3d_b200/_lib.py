@@ -65,8 +65,11 @@ SIGNATURES = {
     "lbm_get_neighbor_table": (_I, [_VP, _VP]),
     "lbm_get_link_flags": (_I, [_VP, _VP]),
     "lbm_halo_count": (_I64, [_VP, _I]),
-    "lbm_halo_pack": (_I, [_VP, _I, _VP, _VP]),
-    "lbm_halo_unpack": (_I, [_VP, _I, _VP, _VP]),
+    "lbm_halo_pack": (_I, [_VP, _I, _I, _VP, _VP]),
+    "lbm_halo_unpack": (_I, [_VP, _I, _I, _VP, _VP]),
+    "lbm_comm_unique_id": (_I, [_VP]),
+    "lbm_comm_init": (_I, [_VP, _VP, _I, _I]),
+    "lbm_run_slab": (_I, [_VP, _I, _I, _VP]),
     "lbm_step_begin": (_I, [_VP, _VP]),
     "lbm_step_planes": (_I, [_VP, _I, _I, _VP]),
     "lbm_step_flip": (_I, [_VP]),

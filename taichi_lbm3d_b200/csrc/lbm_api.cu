@@ -4,6 +4,8 @@
 // pipeline state (post-collision f*), getters/setters, halo staging.
 //
 // Reference: Single_phase/LBM_3D_SinglePhase_Solver.py (line numbers below).
+#include <dlfcn.h>
+
 #include <cub/cub.cuh>
 #include <thrust/iterator/transform_iterator.h>
 #include <cuda_runtime.h>
@@ -12,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "../../include/lbm3d.h"
 #include "lbm_kernels.cuh"
@@ -62,7 +65,8 @@ struct lbm_ctx {
     int compressed = 1;
     uint32_t prefetch_dist = 0;    // sparse: table prefetch distance in nodes (multiple of the block)
     uint32_t *d_lin = nullptr;     // sparse: [nf]
-    uint32_t *d_rank = nullptr;    // sparse: [N+1] exclusive fluid count (kept for plane lookups)
+    uint32_t *d_rank = nullptr;    // sparse: [N+1] exclusive fluid count
+    std::vector<uint32_t> plane_rank;   // sparse: rank at the start of every x plane, [nx+1] (host)
     uint8_t *d_cls = nullptr;      // dense: [N] node class (NODE_BULK / NODE_SOLID / NODE_SPECIAL)
     float *d_fbase[2] = {nullptr, nullptr};   // allocations; d_f = d_fbase + pad
     size_t pad = 0;                // guard elements before/after the populations (speculative pull)
@@ -78,6 +82,12 @@ struct lbm_ctx {
     bool F_valid = true;         // d_F current (or implicit w when d_F == nullptr)
     cudaStream_t stream = nullptr;
     int64_t launches = 0;
+    // multi-GPU slab runner (lbm_comm_init / lbm_run_slab)
+    void *comm = nullptr;            // ncclComm_t
+    int comm_world = 1, comm_rank = 0;
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_boundary = nullptr, ev_comm = nullptr;
+    float *d_send[2] = {nullptr, nullptr}, *d_recv[2] = {nullptr, nullptr};
 };
 
 #define CTX_CHECK(ctx)                                                                         \
@@ -494,6 +504,112 @@ int copy_out(lbm_ctx *c, void *dst, const void *src, size_t bytes) {
     return LBM_OK;
 }
 
+// ---- NCCL, bound at run time from the library torch has already loaded -----------------------
+// (prototypes from nccl.h 2.28: ncclUniqueId is 128 bytes, ncclFloat = 7, ncclSuccess = 0)
+struct NcclId { char internal[128]; };
+struct NcclApi {
+    void *h = nullptr;
+    int (*GetUniqueId)(NcclId *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclId, int) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+NcclApi g_nccl;
+
+bool load_nccl(std::string &err) {
+    if (g_nccl.ok) return true;
+    const char *names[] = {getenv("LBM3D_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+        if (!n) continue;
+        g_nccl.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.h) break;
+    }
+    if (!g_nccl.h) { err = std::string("cannot load NCCL: ") + dlerror(); return false; }
+#define BIND(field, sym)                                                                       \
+    *(void **)(&g_nccl.field) = dlsym(g_nccl.h, sym);                                          \
+    if (!g_nccl.field) { err = std::string("NCCL symbol missing: ") + sym; return false; }
+    BIND(GetUniqueId, "ncclGetUniqueId")
+    BIND(CommInitRank, "ncclCommInitRank")
+    BIND(CommDestroy, "ncclCommDestroy")
+    BIND(Send, "ncclSend")
+    BIND(Recv, "ncclRecv")
+    BIND(GroupStart, "ncclGroupStart")
+    BIND(GroupEnd, "ncclGroupEnd")
+    BIND(GetErrorString, "ncclGetErrorString")
+#undef BIND
+    g_nccl.ok = true;
+    return true;
+}
+
+#define NC(ctx, call)                                                                          \
+    do {                                                                                       \
+        int _r = (call);                                                                       \
+        if (_r != 0) FAIL(ctx, LBM_ERR_CUDA, "%s failed: %s", #call, g_nccl.GetErrorString(_r)); \
+    } while (0)
+
+int halo_pack_impl(lbm_ctx *c, int side, int which, float *dst, cudaStream_t st) {
+    const int plane = side == 0 ? 1 : 2;
+    const uint32_t cnt = c->plane_count[plane];
+    if (cnt == 0) return LBM_OK;
+    static const HaloDirs kR = {{1, 7, 9, 11, 13}}, kL = {{2, 8, 10, 12, 14}};
+    StepArgs a;
+    fill_args(c, a);
+    set_buffers(c, a, c->d_f[which ? c->cur ^ 1 : c->cur], nullptr);
+    if (c->cfg.sparse) a.nz = 0;
+    k_halo_pack<<<nblocks(cnt, 256), 256, 0, st>>>(a, c->plane_first[plane], c->plane_first[plane], cnt,
+                                                     side == 0 ? kL : kR, dst);
+    CU(c, cudaGetLastError());
+    c->launches++;
+    return LBM_OK;
+}
+
+int halo_unpack_impl(lbm_ctx *c, int side, int which, const float *src, cudaStream_t st) {
+    const int plane = side == 0 ? 0 : 3;
+    const uint32_t cnt = c->plane_count[plane];
+    if (cnt == 0) return LBM_OK;
+    static const HaloDirs kR = {{1, 7, 9, 11, 13}}, kL = {{2, 8, 10, 12, 14}};
+    StepArgs a;
+    fill_args(c, a);
+    set_buffers(c, a, nullptr, c->d_f[which ? c->cur ^ 1 : c->cur]);
+    if (c->cfg.sparse) a.nz = 0;
+    // the left ghost receives what the left neighbour sent to its right (e_x = +1) and v.v.
+    k_halo_unpack<<<nblocks(cnt, 256), 256, 0, st>>>(a, c->plane_first[plane], c->plane_first[plane], cnt,
+                                                       side == 0 ? kR : kL, src);
+    CU(c, cudaGetLastError());
+    c->launches++;
+    return LBM_OK;
+}
+
+// one halo exchange of buffer `which` on stream st (see include/lbm3d.h)
+int exchange_impl(lbm_ctx *c, int which, cudaStream_t st) {
+    int r = halo_pack_impl(c, 0, which, c->d_send[0], st);
+    if (r) return r;
+    r = halo_pack_impl(c, 1, which, c->d_send[1], st);
+    if (r) return r;
+    const float *from_left = c->d_send[1], *from_right = c->d_send[0];   // ring of one slab
+    if (c->comm_world > 1) {
+        const int left = (c->comm_rank + c->comm_world - 1) % c->comm_world;
+        const int right = (c->comm_rank + 1) % c->comm_world;
+        NC(c, g_nccl.GroupStart());
+        // posting order matters when left == right (two ranks): pairs match in order
+        NC(c, g_nccl.Send(c->d_send[1], (size_t)5 * c->plane_count[2], 7, right, c->comm, st));
+        NC(c, g_nccl.Send(c->d_send[0], (size_t)5 * c->plane_count[1], 7, left, c->comm, st));
+        NC(c, g_nccl.Recv(c->d_recv[0], (size_t)5 * c->plane_count[0], 7, left, c->comm, st));
+        NC(c, g_nccl.Recv(c->d_recv[1], (size_t)5 * c->plane_count[3], 7, right, c->comm, st));
+        NC(c, g_nccl.GroupEnd());
+        from_left = c->d_recv[0];
+        from_right = c->d_recv[1];
+    }
+    r = halo_unpack_impl(c, 0, which, from_left, st);
+    if (r) return r;
+    return halo_unpack_impl(c, 1, which, from_right, st);
+}
+
 }  // namespace
 
 extern "C" {
@@ -546,6 +662,11 @@ int lbm_destroy(lbm_ctx *ctx) {
     CTX_CHECK(ctx);
     cudaSetDevice(ctx->cfg.device);
     cudaDeviceSynchronize();
+    if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
+    if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
+    if (ctx->ev_boundary) cudaEventDestroy(ctx->ev_boundary);
+    if (ctx->ev_comm) cudaEventDestroy(ctx->ev_comm);
+    for (int i = 0; i < 2; ++i) { cudaFree(ctx->d_send[i]); cudaFree(ctx->d_recv[i]); }
     free_device(ctx);
     delete ctx;
     return LBM_OK;
@@ -746,11 +867,11 @@ int lbm_init(lbm_ctx *c) {
                 c->launches++;
             }
         }
+        c->plane_rank.assign((size_t)nx + 1, 0);
+        CU(c, cudaMemcpy2D(c->plane_rank.data(), sizeof(uint32_t), c->d_rank, plane * sizeof(uint32_t),
+                           sizeof(uint32_t), (size_t)nx + 1, cudaMemcpyDeviceToHost));
         if (g.halo_x) {
-            uint32_t r[4];
-            const size_t at[4] = {plane, plane * 2, plane * (nx - 2), plane * (nx - 1)};
-            for (int i = 0; i < 4; ++i)
-                CU(c, cudaMemcpy(&r[i], c->d_rank + at[i], sizeof(uint32_t), cudaMemcpyDeviceToHost));
+            const uint32_t r[4] = {c->plane_rank[1], c->plane_rank[2], c->plane_rank[nx - 2], c->plane_rank[nx - 1]};
             c->own_first = r[0];
             c->own_count = r[3] - r[0];
             c->plane_first[0] = 0; c->plane_count[0] = r[0];
@@ -1005,43 +1126,114 @@ int64_t lbm_halo_count(lbm_ctx *c, int plane) {
 static const HaloDirs kRight = {{1, 7, 9, 11, 13}};   // e_x = +1 (:184-186)
 static const HaloDirs kLeft = {{2, 8, 10, 12, 14}};   // e_x = -1
 
-int lbm_halo_pack(lbm_ctx *c, int side, float *dst, void *cuda_stream) {
+int lbm_halo_pack(lbm_ctx *c, int side, int which, float *dst, void *cuda_stream) {
     CTX_CHECK(c);
     if (!c->inited || !c->cfg.halo_x) FAIL(c, LBM_ERR_STATE, "needs an initialised halo_x context");
     if (!c->pipe_valid) FAIL(c, LBM_ERR_STATE, "no post-collision state yet (call lbm_step_begin)");
     if (side < 0 || side > 1 || !dst) FAIL(c, LBM_ERR_INVALID, "bad side/destination");
     CU(c, cudaSetDevice(c->cfg.device));
-    const int plane = side == 0 ? 1 : 2;
-    const uint32_t cnt = c->plane_count[plane];
-    if (cnt == 0) return LBM_OK;
-    StepArgs a;
-    fill_args(c, a);
-    set_buffers(c, a, c->d_f[c->cur], nullptr);
-    if (c->cfg.sparse) a.nz = 0;
-    k_halo_pack<<<nblocks(cnt, 256), 256, 0, (cudaStream_t)cuda_stream>>>(
-        a, c->plane_first[plane], c->plane_first[plane], cnt, side == 0 ? kLeft : kRight, dst);
-    CU(c, cudaGetLastError());
-    c->launches++;
-    return LBM_OK;
+    return halo_pack_impl(c, side, which, dst, (cudaStream_t)cuda_stream);
 }
 
-int lbm_halo_unpack(lbm_ctx *c, int side, const float *src, void *cuda_stream) {
+int lbm_halo_unpack(lbm_ctx *c, int side, int which, const float *src, void *cuda_stream) {
     CTX_CHECK(c);
     if (!c->inited || !c->cfg.halo_x) FAIL(c, LBM_ERR_STATE, "needs an initialised halo_x context");
     if (side < 0 || side > 1 || !src) FAIL(c, LBM_ERR_INVALID, "bad side/source");
     CU(c, cudaSetDevice(c->cfg.device));
-    const int plane = side == 0 ? 0 : 3;
-    const uint32_t cnt = c->plane_count[plane];
-    if (cnt == 0) return LBM_OK;
-    // the left ghost receives what the left neighbour sent to its right (e_x = +1) and v.v.
+    return halo_unpack_impl(c, side, which, src, (cudaStream_t)cuda_stream);
+}
+
+int lbm_comm_unique_id(void *out128) {
+    std::string err;
+    if (!out128) return LBM_ERR_INVALID;
+    if (!load_nccl(err)) { g_create_error = err; return LBM_ERR_CUDA; }
+    NcclId id;
+    if (g_nccl.GetUniqueId(&id) != 0) { g_create_error = "ncclGetUniqueId failed"; return LBM_ERR_CUDA; }
+    memcpy(out128, &id, sizeof id);
+    return LBM_OK;
+}
+
+int lbm_comm_init(lbm_ctx *c, const void *id128, int world, int rank) {
+    CTX_CHECK(c);
+    if (!c->inited || !c->cfg.halo_x) FAIL(c, LBM_ERR_STATE, "needs an initialised halo_x context");
+    if (world < 1 || rank < 0 || rank >= world) FAIL(c, LBM_ERR_INVALID, "bad world/rank");
+    CU(c, cudaSetDevice(c->cfg.device));
+    if (world > 1) {
+        if (!id128) FAIL(c, LBM_ERR_INVALID, "null NCCL id");
+        std::string err;
+        if (!load_nccl(err)) FAIL(c, LBM_ERR_CUDA, "%s", err.c_str());
+        NcclId id;
+        memcpy(&id, id128, sizeof id);
+        NC(c, g_nccl.CommInitRank(&c->comm, world, id, rank));
+    }
+    c->comm_world = world;
+    c->comm_rank = rank;
+    if (!c->comm_stream) {
+        // highest priority: while the interior kernel has tens of thousands of blocks queued,
+        // the block scheduler must still pick the few blocks of the pack / NCCL / unpack
+        // kernels first, otherwise the exchange only runs when the interior kernel drains
+        int lo = 0, hi = 0;
+        CU(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU(c, cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, hi));
+    }
+    if (!c->ev_boundary) CU(c, cudaEventCreateWithFlags(&c->ev_boundary, cudaEventDisableTiming));
+    if (!c->ev_comm) CU(c, cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming));
+    const uint32_t sc[2] = {c->plane_count[1], c->plane_count[2]}, rc[2] = {c->plane_count[0], c->plane_count[3]};
+    for (int i = 0; i < 2; ++i) {
+        if (!c->d_send[i]) CU(c, cudaMalloc(&c->d_send[i], (size_t)5 * (sc[i] ? sc[i] : 1) * sizeof(float)));
+        if (!c->d_recv[i]) CU(c, cudaMalloc(&c->d_recv[i], (size_t)5 * (rc[i] ? rc[i] : 1) * sizeof(float)));
+    }
+    return LBM_OK;
+}
+
+// nsteps reference steps of one x-slab with the halo exchange inside (the whole loop runs
+// here so that the per-step host cost is a handful of launches, not a Python round trip)
+int lbm_run_slab(lbm_ctx *c, int nsteps, int overlap, void *cuda_stream) {
+    CTX_CHECK(c);
+    if (!c->inited || !c->cfg.halo_x) FAIL(c, LBM_ERR_STATE, "needs an initialised halo_x context");
+    if (!c->comm_stream) FAIL(c, LBM_ERR_STATE, "lbm_comm_init has not been called");
+    if (nsteps <= 0) return LBM_OK;
+    CU(c, cudaSetDevice(c->cfg.device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    c->stream = st;
+    const int own = c->cfg.nx - 2;
+    if (own < 3) overlap = 0;
+    if (!c->pipe_valid) {
+        int r = ensure_pipeline(c, st);
+        if (r) return r;
+        r = exchange_impl(c, 0, st);
+        if (r) return r;
+        nsteps -= 1;
+    }
     StepArgs a;
-    fill_args(c, a);
-    set_buffers(c, a, nullptr, c->d_f[c->cur]);
-    if (c->cfg.sparse) a.nz = 0;
-    k_halo_unpack<<<nblocks(cnt, 256), 256, 0, (cudaStream_t)cuda_stream>>>(
-        a, c->plane_first[plane], c->plane_first[plane], cnt, side == 0 ? kRight : kLeft, src);
-    CU(c, cudaGetLastError());
-    c->launches++;
+    for (int it = 0; it < nsteps; ++it) {
+        if (!overlap) {
+            fill_args(c, a);
+            set_buffers(c, a, c->d_f[c->cur], c->d_f[c->cur ^ 1]);
+            int r = launch(c, MODE_STEP, a, st);
+            if (r) return r;
+            c->cur ^= 1;
+            r = exchange_impl(c, 0, st);
+            if (r) return r;
+            continue;
+        }
+        // boundary planes -> exchange on the side stream || interior planes -> join
+        int r = lbm_step_planes(c, 1, 2, st);
+        if (r) return r;
+        r = lbm_step_planes(c, own, own + 1, st);
+        if (r) return r;
+        CU(c, cudaEventRecord(c->ev_boundary, st));
+        CU(c, cudaStreamWaitEvent(c->comm_stream, c->ev_boundary, 0));
+        r = exchange_impl(c, 1, c->comm_stream);
+        if (r) return r;
+        CU(c, cudaEventRecord(c->ev_comm, c->comm_stream));
+        r = lbm_step_planes(c, 2, own, st);
+        if (r) return r;
+        CU(c, cudaStreamWaitEvent(st, c->ev_comm, 0));
+        c->cur ^= 1;
+    }
+    c->macro_valid = false;
+    c->F_valid = false;
     return LBM_OK;
 }
 
@@ -1067,16 +1259,12 @@ int lbm_step_planes(lbm_ctx *c, int x_begin, int x_end, void *cuda_stream) {
     StepArgs a;
     fill_args(c, a);
     set_buffers(c, a, c->d_f[c->cur], c->d_f[c->cur ^ 1]);
-    const size_t plane = (size_t)c->cfg.ny * c->cfg.nz;
     if (!c->cfg.sparse) {
         a.row_first = (uint32_t)(c->cfg.ny * x_begin);
         a.row_count = (uint32_t)(c->cfg.ny * (x_end - x_begin));
     } else {
-        uint32_t r0, r1;
-        CU(c, cudaMemcpy(&r0, c->d_rank + plane * x_begin, sizeof r0, cudaMemcpyDeviceToHost));
-        CU(c, cudaMemcpy(&r1, c->d_rank + plane * x_end, sizeof r1, cudaMemcpyDeviceToHost));
-        a.first = r0;
-        a.count = r1 - r0;
+        a.first = c->plane_rank[x_begin];
+        a.count = c->plane_rank[x_end] - a.first;
     }
     return launch(c, MODE_STEP, a, (cudaStream_t)cuda_stream);
 }
