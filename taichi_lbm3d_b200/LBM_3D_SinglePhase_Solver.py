@@ -46,8 +46,10 @@ class _Field:
         self._solver, self._name = solver, name
         self.shape, self.dtype = shape, np.dtype(dtype)
 
-    def to_numpy(self):
-        return self._solver._get_field(self._name)
+    def to_numpy(self, out=None):
+        """Fresh array like the reference's to_numpy(); `out` (addition) receives the copy
+        instead, e.g. a pinned host buffer (torch.empty(..., pin_memory=True).numpy())."""
+        return self._solver._get_field(self._name, out)
 
     def from_numpy(self, arr):
         self._solver._set_field(self._name, arr)
@@ -271,14 +273,20 @@ class LB3D_Solver_Single_Phase:
             raise _lib.LbmError("init_simulation() has not been called")
         return self._ctx
 
-    def _get_field(self, name):
+    def _get_field(self, name, out=None):
         if name == "solid":
+            if out is not None:
+                out[...] = self._solid_host
+                return out
             return self._solid_host.copy()
         if self._ctx is None:
             raise _lib.LbmError("field %s is not available before init_simulation()" % name)
         shape = {"rho": (self.nx, self.ny, self.nz), "v": (self.nx, self.ny, self.nz, 3),
                  "F": (self.nx, self.ny, self.nz, 19), "f": (self.nx, self.ny, self.nz, 19)}[name]
-        out = np.empty(shape, np.float32)
+        if out is None:
+            out = np.empty(shape, np.float32)
+        elif out.shape != shape or out.dtype != np.float32 or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError("out must be a C-contiguous float32 array of shape %s" % (shape,))
         fn = {"rho": self._lib.lbm_get_rho, "v": self._lib.lbm_get_v, "F": self._lib.lbm_get_F,
               "f": self._lib.lbm_get_F}[name]       # after streaming3 f == F (:379)
         self._ck(fn(self._ctx, out.ctypes.data_as(ctypes.c_void_p)), "lbm_get_" + name)
