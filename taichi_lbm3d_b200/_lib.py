@@ -24,7 +24,7 @@ class LbmConfig(ctypes.Structure):
 class Lbm2pConfig(ctypes.Structure):
     """lbm2p_config (include/lbm3d_2phase.h)."""
     _fields_ = [("nx", _c.c_int32), ("ny", _c.c_int32), ("nz", _c.c_int32),
-                ("sparse", _c.c_int32), ("strict", _c.c_int32), ("device", _c.c_int32)]
+                ("strict", _c.c_int32), ("device", _c.c_int32), ("reserved", _c.c_int32)]
 
 
 class LbmError(RuntimeError):
@@ -77,6 +77,33 @@ SIGNATURES = {
     "lbm_get_layout": (_I, [_VP, _c.POINTER(_I64)]),
 }
 
+# every symbol include/lbm3d_2phase.h declares
+SIGNATURES_2P = {
+    "lbm2p_create": (_I, [_c.POINTER(Lbm2pConfig), _c.POINTER(_VP)]),
+    "lbm2p_destroy": (_I, [_VP]),
+    "lbm2p_last_error": (_c.c_char_p, [_VP]),
+    "lbm2p_set_geometry": (_I, [_VP, _VP]),
+    "lbm2p_set_phase": (_I, [_VP, _VP]),
+    "lbm2p_set_fluid": (_I, [_VP, _c.c_double, _c.c_double, _c.c_double, _c.c_double]),
+    "lbm2p_set_force": (_I, [_VP, _FP]),
+    "lbm2p_set_bc": (_I, [_VP, _I, _I, _c.c_float, _FP]),
+    "lbm2p_set_psi_bc": (_I, [_VP, _I, _I, _c.c_float]),
+    "lbm2p_set_inverse_matrix": (_I, [_VP, _FP]),
+    "lbm2p_init": (_I, [_VP]),
+    "lbm2p_step": (_I, [_VP, _I, _VP]),
+    "lbm2p_launch_count": (_I64, [_VP]),
+    "lbm2p_synchronize": (_I, [_VP]),
+    "lbm2p_get_rho": (_I, [_VP, _VP]),
+    "lbm2p_get_v": (_I, [_VP, _VP]),
+    "lbm2p_get_F": (_I, [_VP, _VP]),
+    "lbm2p_get_psi": (_I, [_VP, _VP]),
+    "lbm2p_get_rho_r": (_I, [_VP, _VP]),
+    "lbm2p_get_rho_b": (_I, [_VP, _VP]),
+    "lbm2p_get_solid": (_I, [_VP, _VP]),
+    "lbm2p_set_state": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "lbm2p_get_max_v": (_I, [_VP, _FP]),
+}
+
 _lib = None
 
 
@@ -98,12 +125,20 @@ def load():
                 "taichi_lbm3d_b200: %s is missing and could not be built (%s). Run "
                 "`python -m taichi_lbm3d_b200.build`; there is no CPU fallback." % (path, e))
     lib = ctypes.CDLL(path)
-    for name, (res, args) in SIGNATURES.items():
-        fn = getattr(lib, name)        # AttributeError = ABI mismatch, fail loudly
-        fn.restype = res
-        fn.argtypes = args
+    for table in (SIGNATURES, SIGNATURES_2P):
+        for name, (res, args) in table.items():
+            fn = getattr(lib, name)        # AttributeError = ABI mismatch, fail loudly
+            fn.restype = res
+            fn.argtypes = args
     _lib = lib
     return lib
+
+
+def check2(lib, ctx, status, what):
+    if status < 0:
+        msg = lib.lbm2p_last_error(ctx)
+        raise LbmError("%s failed (%d): %s" % (what, status, msg.decode() if msg else "?"))
+    return status
 
 
 def check(lib, ctx, status, what):

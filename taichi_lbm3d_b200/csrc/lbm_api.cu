@@ -18,6 +18,7 @@
 
 #include "../../include/lbm3d.h"
 #include "lbm_kernels.cuh"
+#include "lbm_geometry.cuh"
 
 namespace {
 
@@ -112,104 +113,6 @@ struct lbm_ctx {
     } while (0)
 
 namespace {
-
-// ---- geometry preprocessing ------------------------------------------------------------------
-struct GeoParams {
-    int nx, ny, nz;
-    int halo_x;
-    int xface0, xface1;
-    int bc_type[6];
-};
-
-__constant__ int c_e[19][3] = {{0, 0, 0}, {1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1},
-    {0, 0, -1}, {1, 1, 0}, {-1, -1, 0}, {1, -1, 0}, {-1, 1, 0}, {1, 0, 1}, {-1, 0, -1}, {1, 0, -1},
-    {-1, 0, 1}, {0, 1, 1}, {0, -1, -1}, {0, 1, -1}, {0, -1, 1}};
-
-// periodic_index :247-257 (x wrap disabled when ghost planes supply the neighbours)
-__device__ __forceinline__ bool pull_source(const GeoParams &g, int x, int y, int z, int s, size_t &src) {
-    int xs = x - c_e[s][0], ys = y - c_e[s][1], zs = z - c_e[s][2];
-    if (g.halo_x) {
-        if (xs < 0 || xs > g.nx - 1) return false;
-    } else {
-        if (xs < 0) xs = g.nx - 1;
-        if (xs > g.nx - 1) xs = 0;
-    }
-    if (ys < 0) ys = g.ny - 1;
-    if (ys > g.ny - 1) ys = 0;
-    if (zs < 0) zs = g.nz - 1;
-    if (zs > g.nz - 1) zs = 0;
-    src = ((size_t)xs * g.ny + ys) * g.nz + zs;
-    return true;
-}
-
-// BC bits of a fluid node: winning face (later face overwrites, :272-370) and whether a
-// pressure face reads the zero velocity of a solid inward neighbour (:278, :294 ...).
-__device__ __forceinline__ uint32_t bc_word(const GeoParams &g, const int8_t *solid, int x, int y, int z) {
-    int win = -1;
-    if (g.bc_type[0] && x == g.xface0) win = 0;
-    if (g.bc_type[1] && x == g.xface1) win = 1;
-    if (g.bc_type[2] && y == 0) win = 2;
-    if (g.bc_type[3] && y == g.ny - 1) win = 3;
-    if (g.bc_type[4] && z == 0) win = 4;
-    if (g.bc_type[5] && z == g.nz - 1) win = 5;
-    if (win < 0) return 0u;
-    uint32_t w = (uint32_t)(win + 1) << FL_BC_SHIFT;
-    if (g.bc_type[win] == 1) {
-        int xi = x, yi = y, zi = z;
-        switch (win) {
-            case 0: xi = x + 1; break;
-            case 1: xi = x - 1; break;
-            case 2: yi = 1; break;
-            case 3: yi = g.ny - 2; break;
-            case 4: zi = 1; break;
-            default: zi = g.nz - 2; break;
-        }
-        const bool inside = xi >= 0 && xi < g.nx && yi >= 0 && yi < g.ny && zi >= 0 && zi < g.nz;
-        if (inside && solid[((size_t)xi * g.ny + yi) * g.nz + zi] > 0) w |= FL_PIN_SOLID;
-    }
-    return w;
-}
-
-__global__ void k_build_flags(const GeoParams g, const int8_t *__restrict__ solid,
-                              uint32_t *__restrict__ flags, uint8_t *__restrict__ cls) {
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t N = (size_t)g.nx * g.ny * g.nz;
-    if (idx >= N) return;
-    const int z = (int)(idx % g.nz);
-    const size_t t = idx / g.nz;
-    const int y = (int)(t % g.ny), x = (int)(t / g.ny);
-    uint32_t fl = 0;
-    if (solid[idx] != 0) {
-        flags[idx] = FL_SOLID;
-        // a solid node in the same 32-byte sector (8 nodes of a z-row) as a fluid node stores
-        // too, so the sector is written whole
-        const int z0 = z & ~7;
-        bool any_fluid = false;
-        for (int q = z0; q < z0 + 8 && q < g.nz; ++q)
-            if (solid[idx - z + q] == 0) any_fluid = true;
-        cls[idx] = any_fluid ? NODE_SOLID_WRITE : NODE_SOLID;
-        return;
-    }
-    for (int s = 1; s < 19; ++s) {
-        size_t src;
-        if (!pull_source(g, x, y, z, s, src) || solid[src] != 0) fl |= 1u << s;
-    }
-    if (!g.halo_x) {
-        if (x == 0) fl |= FL_AT_X0;
-        if (x == g.nx - 1) fl |= FL_AT_X1;
-    }
-    if (y == 0) fl |= FL_AT_Y0;
-    if (y == g.ny - 1) fl |= FL_AT_Y1;
-    if (z == 0) fl |= FL_AT_Z0;
-    if (z == g.nz - 1) fl |= FL_AT_Z1;
-    fl |= bc_word(g, solid, x, y, z);
-    flags[idx] = fl;
-    cls[idx] = fl == 0 ? NODE_BULK : NODE_SPECIAL;
-}
-
-struct IsFluid {
-    __host__ __device__ uint32_t operator()(const int8_t &s) const { return s == 0 ? 1u : 0u; }
-};
 
 // true pull sources of a fluid node: j[s-1] = compact index of i - e_s, or -1 (bounce)
 __device__ __forceinline__ void true_sources(const GeoParams &g, const int8_t *solid, const uint32_t *rank,
@@ -306,34 +209,6 @@ __global__ void k_decode_table(StepArgs a, uint32_t nf, int32_t *__restrict__ ou
 #undef X
 }
 
-__global__ void k_fill(float *p, size_t n, float v) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
-}
-
-__global__ void k_fill_weights(float *F, size_t n_nodes) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_nodes * 19) F[i] = d3q19::weight((int)(i % 19));
-}
-
-__global__ void k_binarize(int8_t *s, size_t n) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) s[i] = s[i] > 0 ? 1 : 0;       // init_geo :175  in_dat[in_dat>0] = 1
-}
-
-// cal_max_v :399-402  (norm evaluated without FMA contraction so every mode agrees)
-__global__ void k_max_v(const float *__restrict__ v, size_t n, float *out) {
-    float best = -1e10f;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (size_t)gridDim.x * blockDim.x) {
-        const float x = v[3 * i], y = v[3 * i + 1], z = v[3 * i + 2];
-        const float nr = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
-        best = fmaxf(best, nr);
-    }
-    for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
-    if ((threadIdx.x & 31) == 0 && best >= 0.f) atomicMax((int *)out, __float_as_int(best));
-}
-
 // halo staging: 5 populations of one lattice plane <-> contiguous buffer [5][count]
 struct HaloDirs { int s[5]; };
 // generic over both storage modes: node i of the plane lives at  plane_s + (row0 + i/nz)*prow + i%nz
@@ -355,7 +230,6 @@ __global__ void k_halo_unpack(StepArgs a, uint32_t row0, uint32_t first, uint32_
     for (int q = 0; q < 5; ++q) a.pout[d.s[q]][e] = src[(size_t)q * count + i];
 }
 
-inline unsigned nblocks(size_t n, int b) { return (unsigned)((n + b - 1) / b); }
 
 void default_relaxation(double niu, int textbook, float S[19]) {
     // init_simulation :126-131, same double arithmetic as the Python source
@@ -366,29 +240,6 @@ void default_relaxation(double niu, int textbook, float S[19]) {
                             s_v, s_v, s_v, s_other, s_other, s_other};
     for (int i = 0; i < 19; ++i) S[i] = (float)S64[i];
 }
-
-// exact inverse of M (:64-83) as rationals; every non-zero entry rounds to the same f32 as
-// np.linalg.inv's (tests/test_abi_cpu.py); LAPACK's 1e-17 noise entries are exactly 0 here.
-const double kInvM[19][19] = {
-    {1.0/3.0, -1.0/2.0, 1.0/6.0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0},
-    {1.0/18.0, 0, -1.0/18.0, 1.0/6.0, -1.0/6.0, 0, 0, 0, 0, 1.0/12.0, -1.0/12.0, 0, 0, 0, 0, 0, 0, 0, 0},
-    {1.0/18.0, 0, -1.0/18.0, -1.0/6.0, 1.0/6.0, 0, 0, 0, 0, 1.0/12.0, -1.0/12.0, 0, 0, 0, 0, 0, 0, 0, 0},
-    {1.0/18.0, 0, -1.0/18.0, 0, 0, 1.0/6.0, -1.0/6.0, 0, 0, -1.0/24.0, 1.0/24.0, 1.0/8.0, -1.0/8.0, 0, 0, 0, 0, 0, 0},
-    {1.0/18.0, 0, -1.0/18.0, 0, 0, -1.0/6.0, 1.0/6.0, 0, 0, -1.0/24.0, 1.0/24.0, 1.0/8.0, -1.0/8.0, 0, 0, 0, 0, 0, 0},
-    {1.0/18.0, 0, -1.0/18.0, 0, 0, 0, 0, 1.0/6.0, -1.0/6.0, -1.0/24.0, 1.0/24.0, -1.0/8.0, 1.0/8.0, 0, 0, 0, 0, 0, 0},
-    {1.0/18.0, 0, -1.0/18.0, 0, 0, 0, 0, -1.0/6.0, 1.0/6.0, -1.0/24.0, 1.0/24.0, -1.0/8.0, 1.0/8.0, 0, 0, 0, 0, 0, 0},
-    {1.0/36.0, 1.0/24.0, 1.0/72.0, 1.0/12.0, 1.0/24.0, 1.0/12.0, 1.0/24.0, 0, 0, 1.0/48.0, 1.0/48.0, 1.0/16.0, 1.0/16.0, 1.0/4.0, 0, 0, 1.0/8.0, -1.0/8.0, 0},
-    {1.0/36.0, 1.0/24.0, 1.0/72.0, -1.0/12.0, -1.0/24.0, -1.0/12.0, -1.0/24.0, 0, 0, 1.0/48.0, 1.0/48.0, 1.0/16.0, 1.0/16.0, 1.0/4.0, 0, 0, -1.0/8.0, 1.0/8.0, 0},
-    {1.0/36.0, 1.0/24.0, 1.0/72.0, 1.0/12.0, 1.0/24.0, -1.0/12.0, -1.0/24.0, 0, 0, 1.0/48.0, 1.0/48.0, 1.0/16.0, 1.0/16.0, -1.0/4.0, 0, 0, 1.0/8.0, 1.0/8.0, 0},
-    {1.0/36.0, 1.0/24.0, 1.0/72.0, -1.0/12.0, -1.0/24.0, 1.0/12.0, 1.0/24.0, 0, 0, 1.0/48.0, 1.0/48.0, 1.0/16.0, 1.0/16.0, -1.0/4.0, 0, 0, -1.0/8.0, -1.0/8.0, 0},
-    {1.0/36.0, 1.0/24.0, 1.0/72.0, 1.0/12.0, 1.0/24.0, 0, 0, 1.0/12.0, 1.0/24.0, 1.0/48.0, 1.0/48.0, -1.0/16.0, -1.0/16.0, 0, 0, 1.0/4.0, -1.0/8.0, 0, 1.0/8.0},
-    {1.0/36.0, 1.0/24.0, 1.0/72.0, -1.0/12.0, -1.0/24.0, 0, 0, -1.0/12.0, -1.0/24.0, 1.0/48.0, 1.0/48.0, -1.0/16.0, -1.0/16.0, 0, 0, 1.0/4.0, 1.0/8.0, 0, -1.0/8.0},
-    {1.0/36.0, 1.0/24.0, 1.0/72.0, 1.0/12.0, 1.0/24.0, 0, 0, -1.0/12.0, -1.0/24.0, 1.0/48.0, 1.0/48.0, -1.0/16.0, -1.0/16.0, 0, 0, -1.0/4.0, -1.0/8.0, 0, -1.0/8.0},
-    {1.0/36.0, 1.0/24.0, 1.0/72.0, -1.0/12.0, -1.0/24.0, 0, 0, 1.0/12.0, 1.0/24.0, 1.0/48.0, 1.0/48.0, -1.0/16.0, -1.0/16.0, 0, 0, -1.0/4.0, 1.0/8.0, 0, 1.0/8.0},
-    {1.0/36.0, 1.0/24.0, 1.0/72.0, 0, 0, 1.0/12.0, 1.0/24.0, 1.0/12.0, 1.0/24.0, -1.0/24.0, -1.0/24.0, 0, 0, 0, 1.0/4.0, 0, 0, 1.0/8.0, -1.0/8.0},
-    {1.0/36.0, 1.0/24.0, 1.0/72.0, 0, 0, -1.0/12.0, -1.0/24.0, -1.0/12.0, -1.0/24.0, -1.0/24.0, -1.0/24.0, 0, 0, 0, 1.0/4.0, 0, 0, -1.0/8.0, 1.0/8.0},
-    {1.0/36.0, 1.0/24.0, 1.0/72.0, 0, 0, 1.0/12.0, 1.0/24.0, -1.0/12.0, -1.0/24.0, -1.0/24.0, -1.0/24.0, 0, 0, 0, -1.0/4.0, 0, 0, 1.0/8.0, 1.0/8.0},
-    {1.0/36.0, 1.0/24.0, 1.0/72.0, 0, 0, -1.0/12.0, -1.0/24.0, 1.0/12.0, 1.0/24.0, -1.0/24.0, -1.0/24.0, 0, 0, 0, -1.0/4.0, 0, 0, -1.0/8.0, -1.0/8.0}};
 
 void free_device(lbm_ctx *c) {
     cudaFree(c->d_solid); cudaFree(c->d_flags); cudaFree(c->d_nbr); cudaFree(c->d_lin);
@@ -754,6 +605,8 @@ int lbm_init(lbm_ctx *c) {
     }
     g.xface0 = c->xface0; g.xface1 = c->xface1;
     for (int i = 0; i < 6; ++i) g.bc_type[i] = c->face[i].type;
+    g.two_phase = 0;
+    for (int i = 0; i < 6; ++i) g.bc_psi_type[i] = 0;
 
     CU(c, cudaMalloc(&c->d_scalar, 16));
     if (!c->cfg.sparse) {

@@ -75,7 +75,7 @@ __device__ __forceinline__ void feq_all(float (&f)[19], float rho, float ux, flo
 // -------------------------------------------------------------------------------------------
 // literal evaluation order (oracle/ref_single_phase.c)
 // -------------------------------------------------------------------------------------------
-__constant__ float c_invM[361];   // inv_M :110, uploaded by the API
+static __constant__ float c_invM[361];   // inv_M :110, uploaded by the API (one copy per TU)
 
 __device__ __forceinline__ void macro(const float (&f)[19], const LbmParams &P, bool force,
                                       float &rho, float &ux, float &uy, float &uz) {

@@ -1,0 +1,187 @@
+// Geometry preprocessing and small utility kernels shared by the single-phase and two-phase
+// C-ABI layers (each translation unit gets its own copy: everything is in an anonymous
+// namespace).  Reference: Single_phase/LBM_3D_SinglePhase_Solver.py (line numbers below).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "lbm_kernels.cuh"
+
+namespace {
+
+// ---- geometry preprocessing ------------------------------------------------------------------
+struct GeoParams {
+    int nx, ny, nz;
+    int halo_x;
+    int xface0, xface1;
+    int bc_type[6];
+    int two_phase;          // also flag nodes whose phase-field stencil touches a solid
+    int bc_psi_type[6];     // two-phase: 0 periodic / 1 constant psi per face (clamped stencil)
+};
+
+__constant__ int c_e[19][3] = {{0, 0, 0}, {1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1},
+    {0, 0, -1}, {1, 1, 0}, {-1, -1, 0}, {1, -1, 0}, {-1, 1, 0}, {1, 0, 1}, {-1, 0, -1}, {1, 0, -1},
+    {-1, 0, 1}, {0, 1, 1}, {0, -1, -1}, {0, 1, -1}, {0, -1, 1}};
+
+// periodic_index :247-257 (x wrap disabled when ghost planes supply the neighbours)
+__device__ __forceinline__ bool pull_source(const GeoParams &g, int x, int y, int z, int s, size_t &src) {
+    int xs = x - c_e[s][0], ys = y - c_e[s][1], zs = z - c_e[s][2];
+    if (g.halo_x) {
+        if (xs < 0 || xs > g.nx - 1) return false;
+    } else {
+        if (xs < 0) xs = g.nx - 1;
+        if (xs > g.nx - 1) xs = 0;
+    }
+    if (ys < 0) ys = g.ny - 1;
+    if (ys > g.ny - 1) ys = 0;
+    if (zs < 0) zs = g.nz - 1;
+    if (zs > g.nz - 1) zs = 0;
+    src = ((size_t)xs * g.ny + ys) * g.nz + zs;
+    return true;
+}
+
+// BC bits of a fluid node: winning face (later face overwrites, :272-370) and whether a
+// pressure face reads the zero velocity of a solid inward neighbour (:278, :294 ...).
+__device__ __forceinline__ uint32_t bc_word(const GeoParams &g, const int8_t *solid, int x, int y, int z) {
+    // single phase: both BC types overwrite all 19 populations, so only the last matching face
+    // counts.  Two-phase: the velocity form (2phase/lbm_solver_3d_2phase.py:500-504) depends on
+    // the current F, so the word records the last PRESSURE face and the kernel then applies
+    // the later velocity faces in order from the at-face bits.
+    int win = -1;
+    const bool only_p = g.two_phase != 0;
+#define BC_MATCH(f) (g.bc_type[f] && (!only_p || g.bc_type[f] == 1))
+    if (BC_MATCH(0) && x == g.xface0) win = 0;
+    if (BC_MATCH(1) && x == g.xface1) win = 1;
+    if (BC_MATCH(2) && y == 0) win = 2;
+    if (BC_MATCH(3) && y == g.ny - 1) win = 3;
+    if (BC_MATCH(4) && z == 0) win = 4;
+    if (BC_MATCH(5) && z == g.nz - 1) win = 5;
+#undef BC_MATCH
+    if (win < 0) return 0u;
+    uint32_t w = (uint32_t)(win + 1) << FL_BC_SHIFT;
+    if (g.bc_type[win] == 1) {
+        int xi = x, yi = y, zi = z;
+        switch (win) {
+            case 0: xi = x + 1; break;
+            case 1: xi = x - 1; break;
+            case 2: yi = 1; break;
+            case 3: yi = g.ny - 2; break;
+            case 4: zi = 1; break;
+            default: zi = g.nz - 2; break;
+        }
+        const bool inside = xi >= 0 && xi < g.nx && yi >= 0 && yi < g.ny && zi >= 0 && zi < g.nz;
+        if (inside && solid[((size_t)xi * g.ny + yi) * g.nz + zi] > 0) w |= FL_PIN_SOLID;
+    }
+    return w;
+}
+
+__global__ void k_build_flags(const GeoParams g, const int8_t *__restrict__ solid,
+                              uint32_t *__restrict__ flags, uint8_t *__restrict__ cls) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t N = (size_t)g.nx * g.ny * g.nz;
+    if (idx >= N) return;
+    const int z = (int)(idx % g.nz);
+    const size_t t = idx / g.nz;
+    const int y = (int)(t % g.ny), x = (int)(t / g.ny);
+    uint32_t fl = 0;
+    if (solid[idx] != 0) {
+        flags[idx] = FL_SOLID;
+        // a solid node in the same 32-byte sector (8 nodes of a z-row) as a fluid node stores
+        // too, so the sector is written whole
+        const int z0 = z & ~7;
+        bool any_fluid = false;
+        for (int q = z0; q < z0 + 8 && q < g.nz; ++q)
+            if (solid[idx - z + q] == 0) any_fluid = true;
+        cls[idx] = any_fluid ? NODE_SOLID_WRITE : NODE_SOLID;
+        return;
+    }
+    for (int s = 1; s < 19; ++s) {
+        size_t src;
+        if (!pull_source(g, x, y, z, s, src) || solid[src] != 0) fl |= 1u << s;
+    }
+    if (!g.halo_x) {
+        if (x == 0) fl |= FL_AT_X0;
+        if (x == g.nx - 1) fl |= FL_AT_X1;
+    }
+    if (y == 0) fl |= FL_AT_Y0;
+    if (y == g.ny - 1) fl |= FL_AT_Y1;
+    if (z == 0) fl |= FL_AT_Z0;
+    if (z == g.nz - 1) fl |= FL_AT_Z1;
+    fl |= bc_word(g, solid, x, y, z);
+    if (g.two_phase) {
+        // Compute_C (2phase/lbm_solver_3d_2phase.py:259-275) looks at i + e_s with
+        // periodic_index_for_psi (:390-428): wrap on periodic psi faces, clamp on constant ones
+        const int n[3] = {g.nx, g.ny, g.nz};
+        bool near = false;
+        for (int s = 1; s < 19; ++s) {
+            int q[3] = {x + c_e[s][0], y + c_e[s][1], z + c_e[s][2]};
+            for (int d = 0; d < 3; ++d) {
+                if (q[d] < 0) q[d] = g.bc_psi_type[2 * d] == 0 ? n[d] - 1 : 0;
+                if (q[d] > n[d] - 1) q[d] = g.bc_psi_type[2 * d + 1] == 0 ? 0 : n[d] - 1;
+            }
+            if (solid[((size_t)q[0] * g.ny + q[1]) * g.nz + q[2]] != 0) near = true;
+        }
+        if (near) fl |= FL_NEAR_SOLID;
+    }
+    flags[idx] = fl;
+    cls[idx] = fl == 0 ? NODE_BULK : NODE_SPECIAL;
+}
+
+struct IsFluid {
+    __host__ __device__ uint32_t operator()(const int8_t &s) const { return s == 0 ? 1u : 0u; }
+};
+
+__global__ void k_fill(float *p, size_t n, float v) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+__global__ void k_fill_weights(float *F, size_t n_nodes) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_nodes * 19) F[i] = d3q19::weight((int)(i % 19));
+}
+
+__global__ void k_binarize(int8_t *s, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) s[i] = s[i] > 0 ? 1 : 0;       // init_geo :175  in_dat[in_dat>0] = 1
+}
+
+// cal_max_v :399-402  (norm evaluated without FMA contraction so every mode agrees)
+__global__ void k_max_v(const float *__restrict__ v, size_t n, float *out) {
+    float best = -1e10f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const float x = v[3 * i], y = v[3 * i + 1], z = v[3 * i + 2];
+        const float nr = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+        best = fmaxf(best, nr);
+    }
+    for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if ((threadIdx.x & 31) == 0 && best >= 0.f) atomicMax((int *)out, __float_as_int(best));
+}
+
+inline unsigned nblocks(size_t n, int b) { return (unsigned)((n + b - 1) / b); }
+
+// exact inverse of M (:64-83) as rationals; every non-zero entry rounds to the same f32 as
+// np.linalg.inv's (tests/test_abi_cpu.py); LAPACK's 1e-17 noise entries are exactly 0 here.
+const double kInvM[19][19] = {
+    {1.0/3.0, -1.0/2.0, 1.0/6.0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0},
+    {1.0/18.0, 0, -1.0/18.0, 1.0/6.0, -1.0/6.0, 0, 0, 0, 0, 1.0/12.0, -1.0/12.0, 0, 0, 0, 0, 0, 0, 0, 0},
+    {1.0/18.0, 0, -1.0/18.0, -1.0/6.0, 1.0/6.0, 0, 0, 0, 0, 1.0/12.0, -1.0/12.0, 0, 0, 0, 0, 0, 0, 0, 0},
+    {1.0/18.0, 0, -1.0/18.0, 0, 0, 1.0/6.0, -1.0/6.0, 0, 0, -1.0/24.0, 1.0/24.0, 1.0/8.0, -1.0/8.0, 0, 0, 0, 0, 0, 0},
+    {1.0/18.0, 0, -1.0/18.0, 0, 0, -1.0/6.0, 1.0/6.0, 0, 0, -1.0/24.0, 1.0/24.0, 1.0/8.0, -1.0/8.0, 0, 0, 0, 0, 0, 0},
+    {1.0/18.0, 0, -1.0/18.0, 0, 0, 0, 0, 1.0/6.0, -1.0/6.0, -1.0/24.0, 1.0/24.0, -1.0/8.0, 1.0/8.0, 0, 0, 0, 0, 0, 0},
+    {1.0/18.0, 0, -1.0/18.0, 0, 0, 0, 0, -1.0/6.0, 1.0/6.0, -1.0/24.0, 1.0/24.0, -1.0/8.0, 1.0/8.0, 0, 0, 0, 0, 0, 0},
+    {1.0/36.0, 1.0/24.0, 1.0/72.0, 1.0/12.0, 1.0/24.0, 1.0/12.0, 1.0/24.0, 0, 0, 1.0/48.0, 1.0/48.0, 1.0/16.0, 1.0/16.0, 1.0/4.0, 0, 0, 1.0/8.0, -1.0/8.0, 0},
+    {1.0/36.0, 1.0/24.0, 1.0/72.0, -1.0/12.0, -1.0/24.0, -1.0/12.0, -1.0/24.0, 0, 0, 1.0/48.0, 1.0/48.0, 1.0/16.0, 1.0/16.0, 1.0/4.0, 0, 0, -1.0/8.0, 1.0/8.0, 0},
+    {1.0/36.0, 1.0/24.0, 1.0/72.0, 1.0/12.0, 1.0/24.0, -1.0/12.0, -1.0/24.0, 0, 0, 1.0/48.0, 1.0/48.0, 1.0/16.0, 1.0/16.0, -1.0/4.0, 0, 0, 1.0/8.0, 1.0/8.0, 0},
+    {1.0/36.0, 1.0/24.0, 1.0/72.0, -1.0/12.0, -1.0/24.0, 1.0/12.0, 1.0/24.0, 0, 0, 1.0/48.0, 1.0/48.0, 1.0/16.0, 1.0/16.0, -1.0/4.0, 0, 0, -1.0/8.0, -1.0/8.0, 0},
+    {1.0/36.0, 1.0/24.0, 1.0/72.0, 1.0/12.0, 1.0/24.0, 0, 0, 1.0/12.0, 1.0/24.0, 1.0/48.0, 1.0/48.0, -1.0/16.0, -1.0/16.0, 0, 0, 1.0/4.0, -1.0/8.0, 0, 1.0/8.0},
+    {1.0/36.0, 1.0/24.0, 1.0/72.0, -1.0/12.0, -1.0/24.0, 0, 0, -1.0/12.0, -1.0/24.0, 1.0/48.0, 1.0/48.0, -1.0/16.0, -1.0/16.0, 0, 0, 1.0/4.0, 1.0/8.0, 0, -1.0/8.0},
+    {1.0/36.0, 1.0/24.0, 1.0/72.0, 1.0/12.0, 1.0/24.0, 0, 0, -1.0/12.0, -1.0/24.0, 1.0/48.0, 1.0/48.0, -1.0/16.0, -1.0/16.0, 0, 0, -1.0/4.0, -1.0/8.0, 0, -1.0/8.0},
+    {1.0/36.0, 1.0/24.0, 1.0/72.0, -1.0/12.0, -1.0/24.0, 0, 0, 1.0/12.0, 1.0/24.0, 1.0/48.0, 1.0/48.0, -1.0/16.0, -1.0/16.0, 0, 0, -1.0/4.0, 1.0/8.0, 0, 1.0/8.0},
+    {1.0/36.0, 1.0/24.0, 1.0/72.0, 0, 0, 1.0/12.0, 1.0/24.0, 1.0/12.0, 1.0/24.0, -1.0/24.0, -1.0/24.0, 0, 0, 0, 1.0/4.0, 0, 0, 1.0/8.0, -1.0/8.0},
+    {1.0/36.0, 1.0/24.0, 1.0/72.0, 0, 0, -1.0/12.0, -1.0/24.0, -1.0/12.0, -1.0/24.0, -1.0/24.0, -1.0/24.0, 0, 0, 0, 1.0/4.0, 0, 0, -1.0/8.0, 1.0/8.0},
+    {1.0/36.0, 1.0/24.0, 1.0/72.0, 0, 0, 1.0/12.0, 1.0/24.0, -1.0/12.0, -1.0/24.0, -1.0/24.0, -1.0/24.0, 0, 0, 0, -1.0/4.0, 0, 0, 1.0/8.0, 1.0/8.0},
+    {1.0/36.0, 1.0/24.0, 1.0/72.0, 0, 0, -1.0/12.0, -1.0/24.0, 1.0/12.0, 1.0/24.0, -1.0/24.0, -1.0/24.0, 0, 0, 0, -1.0/4.0, 0, 0, -1.0/8.0, -1.0/8.0}};
+
+}  // namespace

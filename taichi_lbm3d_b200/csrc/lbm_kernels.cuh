@@ -20,6 +20,7 @@
 #define FL_AT_Z0 (1u << 28)
 #define FL_AT_Z1 (1u << 29)
 
+#define FL_NEAR_SOLID (1u << 30)  /* two-phase: a node of the phase-field stencil is solid         */
 #define FL_EXCEPTION (1u << 31)   /* sparse: pull sources listed explicitly in the exception table */
 
 enum { MODE_STEP = 0, MODE_EXTRACT = 1, MODE_COLLIDE = 2 };
