@@ -44,7 +44,8 @@ struct lbm2p_ctx {
     uint32_t *d_flags = nullptr;
     uint8_t *d_cls = nullptr;
     float *d_fbase[2] = {nullptr, nullptr}, *d_f[2] = {nullptr, nullptr};
-    float *d_recbase = nullptr, *d_rec[8] = {};
+    float4 *d_recA = nullptr, *d_recC = nullptr;
+    float2 *d_recB = nullptr;
     float *d_psibase = nullptr, *d_psi = nullptr;
     float *d_rho_r = nullptr, *d_rho_b = nullptr;
     float *d_rho = nullptr, *d_v = nullptr, *d_F = nullptr;
@@ -122,10 +123,10 @@ __global__ void k2p_bake_psi(const int8_t *__restrict__ solid, float *psi, float
 
 void free2(lbm2p_ctx *c) {
     cudaFree(c->d_flags); cudaFree(c->d_cls); cudaFree(c->d_fbase[0]); cudaFree(c->d_fbase[1]);
-    cudaFree(c->d_recbase); cudaFree(c->d_psibase); cudaFree(c->d_rho_r); cudaFree(c->d_rho_b);
+    cudaFree(c->d_recA); cudaFree(c->d_recB); cudaFree(c->d_recC); cudaFree(c->d_psibase); cudaFree(c->d_rho_r); cudaFree(c->d_rho_b);
     cudaFree(c->d_rho); cudaFree(c->d_v); cudaFree(c->d_F); cudaFree(c->d_vbc); cudaFree(c->d_scalar);
     c->d_flags = nullptr; c->d_cls = nullptr; c->d_fbase[0] = c->d_fbase[1] = nullptr;
-    c->d_recbase = nullptr; c->d_psibase = nullptr; c->d_rho_r = c->d_rho_b = nullptr;
+    c->d_recA = c->d_recC = nullptr; c->d_recB = nullptr; c->d_psibase = nullptr; c->d_rho_r = c->d_rho_b = nullptr;
     c->d_rho = c->d_v = c->d_F = nullptr; c->d_vbc = nullptr; c->d_scalar = nullptr;
 }
 
@@ -162,7 +163,7 @@ void fill2(const lbm2p_ctx *c, Step2Args &A, const float *fin, float *fout) {
         A.bc_psi_type[i] = c->bc_psi_type[i];
         A.bc_psi_val[i] = c->bc_psi_val[i];
     }
-    for (int k = 0; k < 8; ++k) A.rec[k] = c->d_rec[k];
+    A.recA = c->d_recA; A.recB = c->d_recB; A.recC = c->d_recC;
     A.rho_r = c->d_rho_r; A.rho_b = c->d_rho_b; A.psi = c->d_psi;
     A.psi_solid = (float)c->psi_solid;
     A.CapA = (float)c->CapA;
@@ -410,9 +411,12 @@ int lbm2p_init(lbm2p_ctx *c) {
     // node-linear arrays with a guard band of a plane + a row
     c->npad = (plane + nz + 2 + 31) / 32 * 32;
     const size_t nlin = N + 2 * c->npad;
-    CU2(c, cudaMalloc(&c->d_recbase, 8 * nlin * sizeof(float)));
-    CU2(c, cudaMemset(c->d_recbase, 0, 8 * nlin * sizeof(float)));
-    for (int k = 0; k < 8; ++k) c->d_rec[k] = c->d_recbase + (size_t)k * nlin + c->npad;
+    CU2(c, cudaMalloc(&c->d_recA, N * sizeof(float4)));
+    CU2(c, cudaMalloc(&c->d_recB, N * sizeof(float2)));
+    CU2(c, cudaMalloc(&c->d_recC, N * sizeof(float4)));
+    CU2(c, cudaMemset(c->d_recA, 0, N * sizeof(float4)));
+    CU2(c, cudaMemset(c->d_recB, 0, N * sizeof(float2)));
+    CU2(c, cudaMemset(c->d_recC, 0, N * sizeof(float4)));
     CU2(c, cudaMalloc(&c->d_psibase, nlin * sizeof(float)));
     CU2(c, cudaMemset(c->d_psibase, 0, nlin * sizeof(float)));
     c->d_psi = c->d_psibase + c->npad;

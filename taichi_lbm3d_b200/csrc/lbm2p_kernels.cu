@@ -193,38 +193,66 @@ __device__ __forceinline__ void collide2(float (&f)[19], const Step2Args &A, boo
 }
 #endif
 
-// recoloured g_r[S], g_b[S] (:345-363) of a node given its colour record
+// Contribution of one pull source to rho_r, rho_b: the recoloured g_r[s], g_b[s] (:345-363) of
+// the source node, re-evaluated from its colour record, for the direction sg*e_S (sg = -1:
+// the opposite direction LR[S], evaluated on the node's OWN record when the source is solid
+// and its push came back, :370-372).  Negation commutes with rounding, min(a,b,c,d) is
+// symmetric and cs*(-x) = -(cs*x), so both members of a pair (kk, kk+1) reduce to
+//     g_r += cs (e.C)/|C| ,  g_b -= cs (e.C)/|C|     with e the direction being evaluated,
+// bit-identically to the reference's pairwise update.
 template <int S, int EX, int EY, int EZ>
-__device__ __forceinline__ void colour_g(float rr, float rb, float ux, float uy, float uz, float Cx, float Cy,
-                                         float Cz, float &gr, float &gb) {
-    gr = feq<S, EX, EY, EZ>(rr, ux, uy, uz);
-    gb = feq<S, EX, EY, EZ>(rb, ux, uy, uz);
-    if (S > 0) {
-        const float cc = sqrtf(Cx * Cx + Cy * Cy + Cz * Cz);
-        if (cc > 0.f) {
-            // the pair (kk, kk+1), kk odd, shares one cospsi; e_{kk+1} = -e_kk
-            constexpr bool first = (S & 1) != 0;
-            constexpr int KX = first ? EX : -EX, KY = first ? EY : -EY, KZ = first ? EZ : -EZ;
-            constexpr int KK = first ? S : S - 1;
-            const float grk = feq<KK, KX, KY, KZ>(rr, ux, uy, uz);
-            const float grk1 = feq<KK + 1, -KX, -KY, -KZ>(rr, ux, uy, uz);
-            const float gbk = feq<KK, KX, KY, KZ>(rb, ux, uy, uz);
-            const float gbk1 = feq<KK + 1, -KX, -KY, -KZ>(rb, ux, uy, uz);
-            float cs = grk < grk1 ? grk : grk1;
-            cs = cs < gbk ? cs : gbk;
-            cs = cs < gbk1 ? cs : gbk1;
-            const float ef = edotu<KX, KY, KZ>(Cx, Cy, Cz);
-            cs = cs * (ef / cc);
-            if (first) { gr = gr + cs; gb = gb - cs; }
-            else { gr = gr - cs; gb = gb + cs; }
-        }
+__device__ __forceinline__ void colour_add(float sg, const float4 ra, const float2 rq, const float4 *__restrict__ pc,
+                                           float &rr, float &rb) {
+    const float eu = sg * edotu<EX, EY, EZ>(ra.z, ra.w, rq.x);
+    float gr, gb;
+#ifdef LBM_STRICT
+    const float uv = ra.z * ra.z + ra.w * ra.w + rq.x * rq.x;
+    const float T1 = 1.0f + 3.0f * eu + 4.5f * eu * eu - 1.5f * uv;        // feq :161-170
+    gr = weight(S) * ra.x * T1;
+    gb = weight(S) * ra.y * T1;
+    if (S > 0 && rq.y < 0.f) {                   // flagged: |C| > 0
+        const float4 rc = __ldg(pc);
+        const float cc = sqrtf(rc.x * rc.x + rc.y * rc.y + rc.z * rc.z);
+        const float em = -eu;
+        const float T2 = 1.0f + 3.0f * em + 4.5f * em * em - 1.5f * uv;
+        const float gro = weight(S) * ra.x * T2, gbo = weight(S) * ra.y * T2;
+        float cs = gr < gro ? gr : gro;
+        cs = cs < gb ? cs : gb;
+        cs = cs < gbo ? cs : gbo;
+        cs = cs * ((sg * edotu<EX, EY, EZ>(rc.x, rc.y, rc.z)) / cc);
+        gr = gr + cs;
+        gb = gb - cs;
     }
+#else
+    // feq(s) = w rho t with t = q + eu (3 + 4.5 eu); the opposite direction has t - 6 eu
+    const float t = fabsf(rq.y) + eu * (3.0f + 4.5f * eu);
+    gr = ra.x * t;
+    gb = ra.y * t;
+    if (S > 0 && rq.y < 0.f) {                   // interface node; most nodes skip this
+        const float4 rc = __ldg(pc);
+        const float to = t - 6.0f * eu;
+        const float cs = fminf(fminf(gr, ra.x * to), fminf(gb, ra.y * to)) *
+                         (sg * edotu<EX, EY, EZ>(rc.x, rc.y, rc.z) * rc.w);
+        gr = gr + cs;
+        gb = gb - cs;
+    }
+    gr *= weight(S);
+    gb *= weight(S);
+#endif
+    rr = rr + gr;
+    rb = rb + gb;
 }
 
 // ---------------------------------------------------------------------------------------------
 // colour pass
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k2p_colour(const Step2Args A) {
+#ifndef LBM2P_COLOUR_MINB
+#define LBM2P_COLOUR_MINB 8
+#endif
+#ifndef LBM2P_MAIN_MINB
+#define LBM2P_MAIN_MINB 5
+#endif
+__global__ void __launch_bounds__(256, LBM2P_COLOUR_MINB) k2p_colour(const Step2Args A) {
     const StepArgs &a = A.a;
     const uint32_t z = blockIdx.y * blockDim.x + threadIdx.x;
     const uint32_t r = blockIdx.x * blockDim.y + threadIdx.y;
@@ -233,41 +261,43 @@ __global__ void __launch_bounds__(256) k2p_colour(const Step2Args A) {
     const uint32_t idx = row * (uint32_t)a.nz + z;
     const uint8_t cls = a.cls[idx];
     if (cls == NODE_SOLID || cls == NODE_SOLID_WRITE) return;
-    const uint32_t fl = cls == NODE_SPECIAL ? a.flags[idx] : 0u;
     const int sx = a.ny * a.nz, sy = a.nz;
-    // node-linear offsets to x-1 / x+1 ... with the periodic wrap of periodic_index :377-387
-    const int oxm = (fl & FL_AT_X0) ? (a.nx - 1) * sx : -sx;
-    const int oxp = (fl & FL_AT_X1) ? -(a.nx - 1) * sx : sx;
-    const int oym = (fl & FL_AT_Y0) ? (a.ny - 1) * sy : -sy;
-    const int oyp = (fl & FL_AT_Y1) ? -(a.ny - 1) * sy : sy;
-    const int ozm = (fl & FL_AT_Z0) ? (a.nz - 1) : -1;
-    const int ozp = (fl & FL_AT_Z1) ? -(a.nz - 1) : 1;
-    float own[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) own[c] = A.rec[c][idx];
+    const float4 *__restrict__ pA = A.recA + idx;
+    const float2 *__restrict__ pB = A.recB + idx;
+    const float4 *__restrict__ pC = A.recC + idx;
     float rr = 0.f, rb = 0.f;        // accumulators start at 0 (:596)
+    uint32_t fl = 0;
+    if (cls == NODE_BULK) {
+        // no solid link, no wrap: sources at uniform offsets
+#define X(s, ex, ey, ez, o)                                                                    \
+    {                                                                                          \
+        const int off = -((ex) * sx + (ey) * sy + (ez));                                       \
+        colour_add<s, ex, ey, ez>(1.0f, __ldg(pA + off), __ldg(pB + off), pC + off, rr, rb);   \
+    }
+        D3Q19_DIRS(X)
+#undef X
+    } else {
+        fl = a.flags[idx];
+        // node-linear offsets to x-1 / x+1 ... with the periodic wrap of periodic_index :377-387
+        const int oxm = (fl & FL_AT_X0) ? (a.nx - 1) * sx : -sx;
+        const int oxp = (fl & FL_AT_X1) ? -(a.nx - 1) * sx : sx;
+        const int oym = (fl & FL_AT_Y0) ? (a.ny - 1) * sy : -sy;
+        const int oyp = (fl & FL_AT_Y1) ? -(a.ny - 1) * sy : sy;
+        const int ozm = (fl & FL_AT_Z0) ? (a.nz - 1) : -1;
+        const int ozp = (fl & FL_AT_Z1) ? -(a.nz - 1) : 1;
 #define OFF(ex, ey, ez)                                                                        \
     ((ex > 0 ? oxm : (ex < 0 ? oxp : 0)) + (ey > 0 ? oym : (ey < 0 ? oyp : 0)) +               \
      (ez > 0 ? ozm : (ez < 0 ? ozp : 0)))
 #define X(s, ex, ey, ez, o)                                                                    \
     {                                                                                          \
-        float gr, gb;                                                                          \
-        if ((fl >> s) & 1u) {                                                                  \
-            /* source solid: the node's own push of direction LR[s] came back (:370-372) */    \
-            colour_g<o, -(ex), -(ey), -(ez)>(own[0], own[1], own[2], own[3], own[4], own[5], own[6], own[7], gr, gb); \
-        } else if (s == 0) {                                                                   \
-            colour_g<s, ex, ey, ez>(own[0], own[1], own[2], own[3], own[4], own[5], own[6], own[7], gr, gb); \
-        } else {                                                                               \
-            const uint32_t j = idx + OFF(ex, ey, ez);                                          \
-            colour_g<s, ex, ey, ez>(A.rec[0][j], A.rec[1][j], A.rec[2][j], A.rec[3][j], A.rec[4][j], \
-                                    A.rec[5][j], A.rec[6][j], A.rec[7][j], gr, gb);            \
-        }                                                                                      \
-        rr = rr + gr;                                                                          \
-        rb = rb + gb;                                                                          \
+        const bool bounce = (fl >> s) & 1u;                                                    \
+        const int off = (s == 0 || bounce) ? 0 : OFF(ex, ey, ez);                              \
+        colour_add<s, ex, ey, ez>(bounce ? -1.0f : 1.0f, __ldg(pA + off), __ldg(pB + off), pC + off, rr, rb); \
     }
-    D3Q19_DIRS(X)
+        D3Q19_DIRS(X)
 #undef X
 #undef OFF
+    }
     float psi = rr - rb / (rr + rb);         // :605, precedence as written
     // Boundary_condition_psi :445-486, faces in order, the last matching face wins
     int win = -1;
@@ -293,7 +323,7 @@ __global__ void __launch_bounds__(256) k2p_colour(const Step2Args A) {
 // main pass
 // ---------------------------------------------------------------------------------------------
 template <bool FORCE, int MODE, bool SPEC>
-__global__ void __launch_bounds__(256) k2p_main(const Step2Args A) {
+__global__ void __launch_bounds__(256, LBM2P_MAIN_MINB) k2p_main(const Step2Args A) {
     const StepArgs &a = A.a;
     const uint32_t z = blockIdx.y * blockDim.x + threadIdx.x;
     const uint32_t r = blockIdx.x * blockDim.y + threadIdx.y;
@@ -447,14 +477,13 @@ __global__ void __launch_bounds__(256) k2p_main(const Step2Args A) {
         if ((fl & FL_NEAR_SOLID) && fabsf(rr - rb) > 0.9f) { Cx = 0.f; Cy = 0.f; Cz = 0.f; }   // :271-273
         const float psi = ps[0];
         collide2(f, A, FORCE, rho, ux, uy, uz, psi, Cx, Cy, Cz);
-        A.rec[0][idx] = rr;
-        A.rec[1][idx] = rb;
-        A.rec[2][idx] = ux;
-        A.rec[3][idx] = uy;
-        A.rec[4][idx] = uz;
-        A.rec[5][idx] = Cx;
-        A.rec[6][idx] = Cy;
-        A.rec[7][idx] = Cz;
+        // colour record of this collision (see lbm2p_kernels.cuh)
+        const float c2 = Cx * Cx + Cy * Cy + Cz * Cz;
+        const float ccn = sqrtf(c2);
+        const float q = 1.0f - 1.5f * (ux * ux + uy * uy + uz * uz);
+        A.recA[idx] = make_float4(rr, rb, ux, uy);
+        A.recB[idx] = make_float2(uz, ccn > 0.f ? -q : q);
+        if (ccn > 0.f) A.recC[idx] = make_float4(Cx, Cy, Cz, 1.0f / ccn);
     }
 #pragma unroll
     for (int s = 0; s < 19; ++s) a.pout[s][pidx] = f[s];

@@ -8,9 +8,13 @@ enum { COLOUR_SPEC_NONE = 0 };
 struct Step2Args {
     StepArgs a;               // populations, link words, node classes, rows, flow BCs, force
     // colour record published by the collision of step n, read by the colour pass:
-    //   0 rho_r, 1 rho_b, 2..4 v, 5..7 C   -- the values the collision used (2phase/
-    //   lbm_solver_3d_2phase.py:345-363), node-linear [8][N] with a guard band
-    float *rec[8];
+    //   recA = (rho_r, rho_b, vx, vy), recB = (vz, +-q) with q = 1 - 1.5 v.v, negative when C != 0
+    //   (interface node), recC = (Cx, Cy, Cz, 1/|C|) written and read for interface nodes only --
+    //   the values the collision used (2phase/lbm_solver_3d_2phase.py:345-363).  24 B per node
+    //   (+16 B at the interface) instead of the 152 B of stored g_r, g_b.
+    float4 *recA;
+    float2 *recB;
+    float4 *recC;
     // node-linear [N] state of the current step (also what to_numpy() shows):
     float *rho_r, *rho_b;     // :593-594
     float *psi;               // :605; solid nodes hold psi_solid so Compute_C needs no solid test

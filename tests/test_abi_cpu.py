@@ -26,6 +26,11 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, fn), "missing export %s" % fn
         assert fn in _lib.SIGNATURES, "ctypes binding lacks %s" % fn
     assert lib.lbm_abi_version() == 1
+    declared2 = _header_functions("lbm3d_2phase.h")
+    assert len(declared2) >= 20
+    for fn in declared2:
+        assert hasattr(lib, fn), "missing export %s" % fn
+        assert fn in _lib.SIGNATURES_2P, "ctypes binding lacks %s" % fn
 
 
 def test_no_cpu_fallback():
@@ -43,6 +48,11 @@ def test_no_cpu_fallback():
         lb.init_simulation()
     with pytest.raises(_lib.LbmError):
         lb.step()
+    from taichi_lbm3d_b200 import LB3D_Solver_Two_Phase
+    cfg2 = _lib.Lbm2pConfig(nx=4, ny=4, nz=4, strict=0, device=0, reserved=0)
+    assert lib.lbm2p_create(ctypes.byref(cfg2), ctypes.byref(ctx)) == -2
+    with pytest.raises(_lib.LbmError):
+        LB3D_Solver_Two_Phase(4, 4, 4).init_simulation()
 
 
 def test_product_never_imports_the_oracle():
@@ -140,3 +150,31 @@ def test_vtr_roundtrip(tmp_path):
     assert np.array_equal(data["Solid"], solid) and np.array_equal(data["rho"], rho)
     for k in range(3):
         assert np.array_equal(data["velocity"][k], v[..., k])
+
+
+def test_two_phase_class_keeps_script_globals():
+    """attribute names and defaults of 2phase/lbm_solver_3d_2phase.py:16-39"""
+    from taichi_lbm3d_b200 import LB3D_Solver_Two_Phase
+    lb = LB3D_Solver_Two_Phase(6, 5, 4)
+    assert (lb.fx, lb.fy, lb.fz) == (5.0e-5, -2e-5, 0.0) and lb.niu_l == 0.1 and lb.niu_g == 0.1
+    assert lb.psi_solid == 0.7 and lb.CapA == 0.005 and lb.rho_bcxr == 0.995
+    assert (lb.bc_psi_x_left, lb.psi_x_left) == (1, -1.0) and lb.bc_psi_z_right == 0
+    lb.set_bc_psi(3, 1.0)
+    assert lb.bc_psi_y_right == 1 and lb.psi_y_right == 1.0
+    lb.set_bc_rho(1, 0.99)
+    assert lb.bc_x_right == 1 and lb.rho_bcxr == 0.99
+    psi = np.where(np.arange(6)[:, None, None] < 2, -1.0, 1.0) * np.ones((6, 5, 4))
+    lb.psi.from_numpy(psi)
+    assert np.array_equal(lb.psi.to_numpy(), psi.astype(np.float32))
+
+
+def test_two_phase_init_geo(tmp_path):
+    from taichi_lbm3d_b200 import LB3D_Solver_Two_Phase, geometry
+    rng = np.random.default_rng(2)
+    g = (rng.random((5, 4, 3)) < 0.3).astype(np.int8)
+    ph = np.where(rng.random((5, 4, 3)) < 0.5, -1.0, 1.0)
+    geometry.save_geometry_text(str(tmp_path / "g.dat"), g)
+    np.savetxt(str(tmp_path / "p.dat"), ph.reshape(-1, order='F'))
+    lb = LB3D_Solver_Two_Phase(5, 4, 3)
+    s, p = lb.init_geo(str(tmp_path / "g.dat"), str(tmp_path / "p.dat"))     # script :194-202
+    assert np.array_equal(s, g) and np.array_equal(p, ph.astype(np.float32))
