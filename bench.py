@@ -160,6 +160,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sparse", action="store_true", help="use the compacted fluid-list storage")
     ap.add_argument("--size", type=int, default=SLAB, help="cube edge / planes per GPU (default 256)")
+    ap.add_argument("--domain", type=int, default=0,
+                    help="fixed GLOBAL cube edge split into x-slabs over the ranks (strong scaling, BASELINE "
+                         "config 5: --domain 1024); default 0 = weak scaling with --size planes per GPU")
     ap.add_argument("--workload", default="cavity", choices=["cavity", "porous"],
                     help="cavity: BASELINE config 2 (headline); porous: config 3, periodic sphere pack at "
                          "~20%% porosity, body force fx=1e-6 (use with --sparse)")
@@ -185,6 +188,12 @@ def main():
     n = args.size
     ny = nz = n
     gnx = n * n_gpus
+    if args.domain:
+        gnx = ny = nz = args.domain
+        n = (gnx + n_gpus - 1) // n_gpus
+    if os.environ.get("LBM3D_BENCH_SHAPE") and n_gpus == 1:      # tuning experiments: "nx,ny,nz"
+        gnx, ny, nz = (int(t) for t in os.environ["LBM3D_BENCH_SHAPE"].split(","))
+        n = gnx
     porous = args.workload == "porous"
     if porous:
         r0 = max(3.0, 8.0 * n / 512.0)
@@ -251,7 +260,7 @@ def main():
         del lb, stepper
         torch.cuda.empty_cache()
         pinned = torch.from_numpy(solid).pin_memory()
-        rho_pin = torch.empty((gnx, ny, nz), dtype=torch.float32, pin_memory=True)
+        rho_pin = torch.empty((gnx, ny, nz), dtype=torch.float32, pin_memory=True)  # noqa
         v_pin = torch.empty((gnx, ny, nz, 3), dtype=torch.float32, pin_memory=True)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -287,12 +296,12 @@ def main():
     line = {
         "metric": "mlups", "value": mlups, "unit": "MLUPS", "n_gpus": n_gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": mlups / 900.0 if n_gpus == 1 else None,
+        "scaling": "strong" if args.domain else "weak", "vs_baseline": mlups / 900.0 if n_gpus == 1 else None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%s; D3Q19 MRT single phase, %s" % (wl_text, "sparse storage (compact fluid list)"
                                                                     if args.sparse else "dense storage"),
                    "fluid_nodes": nfl_total, "l2_policy": "inputs_exceed_l2 (%.2f GB of populations per GPU vs 126 MB L2)"
-                   % (2 * 19 * 4 * n * ny * nz / 1e9),
+                   % (2 * 19 * 4 * float(n) * ny * nz / 1e9),
                    "vs_baseline_note": "900 MLUPS: README.md:5, one A100, grid size unstated",
                    "parallelism": "x-slabs x%d" % n_gpus, "max_v": max_v},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

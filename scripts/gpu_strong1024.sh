@@ -1,0 +1,8 @@
+# BASELINE config 5: 1024^3 cavity split into x-slabs (strong scaling points that fit)
+for n in 8 4; do
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2953$n bench.py --gpus $n --domain 1024 --steps 100 --warmup 10 > gpurun_out/strong1024_$n.json 2>> gpurun_out/strong.err
+  tail -1 gpurun_out/strong1024_$n.json | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('N=%d 1024^3: %.0f MLUPS  %.3f ms/step  per-GPU frac %.4f'%(d['n_gpus'], d['value'], d['ms_per_step'], d['roofline']['frac']))"
+done
+grep -v "OMP_NUM\|\*\*\*" gpurun_out/strong.err | tail -5

@@ -239,6 +239,22 @@ class LB3D_Solver_Single_Phase:
                                        np.ascontiguousarray(v[0:self.nx, 0:self.ny, 0:self.nz, 1]),
                                        np.ascontiguousarray(v[0:self.nx, 0:self.ny, 0:self.nz, 2]))})
 
+    # ---- checkpoint / restart (the reference cannot resume: its VTK dumps lack populations) ----
+    def save_checkpoint(self, path):
+        """state of the run (F, rho, v) + geometry as a compressed .npz"""
+        np.savez_compressed(path, nx=self.nx, ny=self.ny, nz=self.nz, solid=self._solid_host,
+                            F=self.F.to_numpy(), rho=self.rho.to_numpy(), v=self.v.to_numpy())
+
+    def load_checkpoint(self, path):
+        """restore F, rho, v saved by save_checkpoint (after init_simulation(), same geometry)"""
+        d = np.load(path)
+        if (int(d["nx"]), int(d["ny"]), int(d["nz"])) != (self.nx, self.ny, self.nz) or \
+                not np.array_equal(d["solid"], self._solid_host):
+            raise ValueError("checkpoint was written for a different lattice")
+        self.F.from_numpy(d["F"])
+        self.rho.from_numpy(d["rho"])
+        self.v.from_numpy(d["v"])
+
     # ---- sparse-storage tables (bit-exact compaction checks) ---------------------------------
     def num_fluid(self):
         n = ctypes.c_int64()

@@ -254,8 +254,10 @@ __device__ __forceinline__ void colour_add(float sg, const float4 ra, const floa
 #endif
 __global__ void __launch_bounds__(256, LBM2P_COLOUR_MINB) k2p_colour(const Step2Args A) {
     const StepArgs &a = A.a;
-    const uint32_t z = blockIdx.y * blockDim.x + threadIdx.x;
-    const uint32_t r = blockIdx.x * blockDim.y + threadIdx.y;
+    // blockIdx.x walks the z-chunks of a row (fastest), (blockIdx.z, blockIdx.y) the row groups:
+    // blocks that run together then cover whole z-rows, i.e. contiguous 19*nzp*4-byte chunks
+    const uint32_t z = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t r = (blockIdx.z * gridDim.y + blockIdx.y) * blockDim.y + threadIdx.y;
     if (z >= (uint32_t)a.nz || r >= a.row_count) return;
     const uint32_t row = a.row_first + r;
     const uint32_t idx = row * (uint32_t)a.nz + z;
@@ -325,8 +327,10 @@ __global__ void __launch_bounds__(256, LBM2P_COLOUR_MINB) k2p_colour(const Step2
 template <bool FORCE, int MODE, bool SPEC>
 __global__ void __launch_bounds__(256, LBM2P_MAIN_MINB) k2p_main(const Step2Args A) {
     const StepArgs &a = A.a;
-    const uint32_t z = blockIdx.y * blockDim.x + threadIdx.x;
-    const uint32_t r = blockIdx.x * blockDim.y + threadIdx.y;
+    // blockIdx.x walks the z-chunks of a row (fastest), (blockIdx.z, blockIdx.y) the row groups:
+    // blocks that run together then cover whole z-rows, i.e. contiguous 19*nzp*4-byte chunks
+    const uint32_t z = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t r = (blockIdx.z * gridDim.y + blockIdx.y) * blockDim.y + threadIdx.y;
     if (z >= (uint32_t)a.nz || r >= a.row_count) return;
     const uint32_t row = a.row_first + r;
     const uint32_t idx = row * (uint32_t)a.nz + z;
@@ -499,12 +503,16 @@ static void launch_main_t(const Step2Args &A, dim3 grid, dim3 blk, cudaStream_t 
 
 static void geometry(const StepArgs &a, int block, dim3 &grid, dim3 &blk) {
     if (block <= 0 || block > 256 || block % 32) block = 256;
-    int bx = (a.nz + 31) / 32 * 32;
+    // split a z-row into the fewest chunks of at most `block` threads, of equal (warp-rounded) size
+    const int nchunk = (a.nz + block - 1) / block;
+    int bx = ((a.nz + nchunk - 1) / nchunk + 31) / 32 * 32;
     if (bx > block) bx = block;
     int by = block / bx;
     if (by < 1) by = 1;
     blk = dim3(bx, by, 1);
-    grid = dim3((a.row_count + by - 1) / by, (a.nz + bx - 1) / bx, 1);
+    const unsigned rg = (a.row_count + by - 1) / by;
+    const unsigned gy = rg < 32768u ? rg : 32768u;
+    grid = dim3((a.nz + bx - 1) / bx, gy, (rg + gy - 1) / gy);
 }
 
 cudaError_t launch_main(int mode, const Step2Args &A, int block, cudaStream_t st) {

@@ -3,8 +3,6 @@
 #pragma once
 #include "lbm_kernels.cuh"
 
-enum { COLOUR_SPEC_NONE = 0 };
-
 struct Step2Args {
     StepArgs a;               // populations, link words, node classes, rows, flow BCs, force
     // colour record published by the collision of step n, read by the colour pass:

@@ -801,8 +801,6 @@ int lbm_step(lbm_ctx *c, int nsteps, void *cuda_stream) {
         int r = ensure_pipeline(c, st);
         if (r) return r;
         nsteps -= 1;
-    } else if (c->cfg.halo_x == 0) {
-        // nothing
     }
     StepArgs a;
     fill_args(c, a);
@@ -975,9 +973,6 @@ int64_t lbm_halo_count(lbm_ctx *c, int plane) {
     if (!c || !c->inited || !c->cfg.halo_x || plane < 0 || plane > 3) return -1;
     return (int64_t)c->plane_count[plane];
 }
-
-static const HaloDirs kRight = {{1, 7, 9, 11, 13}};   // e_x = +1 (:184-186)
-static const HaloDirs kLeft = {{2, 8, 10, 12, 14}};   // e_x = -1
 
 int lbm_halo_pack(lbm_ctx *c, int side, int which, float *dst, void *cuda_stream) {
     CTX_CHECK(c);

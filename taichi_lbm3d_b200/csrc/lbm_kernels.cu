@@ -132,8 +132,10 @@ __device__ __forceinline__ void write_user_fields(const StepArgs &a, uint32_t li
 // ---------------------------------------------------------------------------------------------
 template <bool FORCE, int MODE, bool SPEC>
 __global__ void __launch_bounds__(256) k_dense(const StepArgs a) {
-    const uint32_t z = blockIdx.y * blockDim.x + threadIdx.x;
-    const uint32_t r = blockIdx.x * blockDim.y + threadIdx.y;
+    // blockIdx.x walks the z-chunks of a row (fastest), (blockIdx.z, blockIdx.y) the row groups:
+    // blocks that run together then cover whole z-rows, i.e. contiguous 19*nzp*4-byte chunks
+    const uint32_t z = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t r = (blockIdx.z * gridDim.y + blockIdx.y) * blockDim.y + threadIdx.y;
     if (z >= (uint32_t)a.nz || r >= a.row_count) return;
     const uint32_t row = a.row_first + r;
     const uint32_t idx = row * (uint32_t)a.nz + z;      // node (flags, rho, v, F)
@@ -386,12 +388,16 @@ __global__ void __launch_bounds__(SPARSE_BLOCK, LBM_SPARSE_MINB) k_sparse(const 
 template <bool FORCE, int MODE>
 static void launch_dense_t(const StepArgs &a, int block, cudaStream_t st) {
     // block = (BX along z, BY rows); BX = nz rounded up to a warp, capped at `block`
-    int bx = (a.nz + 31) / 32 * 32;
+    // split a z-row into the fewest chunks of at most `block` threads, of equal (warp-rounded) size
+    const int nchunk = (a.nz + block - 1) / block;
+    int bx = ((a.nz + nchunk - 1) / nchunk + 31) / 32 * 32;
     if (bx > block) bx = block;
     int by = block / bx;
     if (by < 1) by = 1;
     dim3 blk(bx, by, 1);
-    dim3 grid((a.row_count + by - 1) / by, (a.nz + bx - 1) / bx, 1);
+    const unsigned rg = (a.row_count + by - 1) / by;
+    const unsigned gy = rg < 32768u ? rg : 32768u;
+    dim3 grid((a.nz + bx - 1) / bx, gy, (rg + gy - 1) / gy);
     if (a.spec)
         k_dense<FORCE, MODE, true><<<grid, blk, 0, st>>>(a);
     else

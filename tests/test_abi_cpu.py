@@ -178,3 +178,19 @@ def test_two_phase_init_geo(tmp_path):
     lb = LB3D_Solver_Two_Phase(5, 4, 3)
     s, p = lb.init_geo(str(tmp_path / "g.dat"), str(tmp_path / "p.dat"))     # script :194-202
     assert np.array_equal(s, g) and np.array_equal(p, ph.astype(np.float32))
+
+
+def test_create_rejects_bad_and_oversized_lattices():
+    """argument errors are reported before any device work (no GPU needed)"""
+    import ctypes
+    from taichi_lbm3d_b200 import _lib
+    lib = _lib.load()
+    ctx = ctypes.c_void_p()
+    for nx, ny, nz, halo in ((0, 4, 4, 0), (4, -1, 4, 0), (2048, 2048, 2048, 0), (2, 4, 4, 1)):
+        cfg = _lib.LbmConfig(nx=nx, ny=ny, nz=nz, sparse=0, strict=0, halo_x=halo, device=0, x_face_mask=0)
+        assert lib.lbm_create(ctypes.byref(cfg), ctypes.byref(ctx)) == -1        # LBM_ERR_INVALID
+        assert lib.lbm_last_error(None)
+    assert lib.lbm_create(None, ctypes.byref(ctx)) == -1
+    # NULL contexts are refused, not dereferenced
+    assert lib.lbm_step(None, 1, None) == -1 and lib.lbm_init(None) == -1 and lib.lbm_launch_count(None) == -1
+    assert lib.lbm2p_step(None, 1, None) == -1

@@ -239,3 +239,74 @@ def test_launches_are_counted(cuda):
     n0 = lb.launch_count
     lb.run(10)
     assert lb.launch_count - n0 == 10
+
+
+def test_config1_ftb131_standin_1000_steps(cuda):
+    """BASELINE config 1 as example_porous_medium.py runs it: 131^3, rho(x0)=1.0, rho(x1)=0.99,
+    default viscosity, no force, dense storage -- on the seeded stand-in for the missing
+    img_ftb131.txt; populations, rho, v after 1000 steps against the oracle."""
+    from taichi_lbm3d_b200.geometry import ftb131_standin
+    case = cases.Case("cfg1_ftb131", ftb131_standin(), bc=[(1, "rho", 0.99), (0, "rho", 1.0)])
+    o, _ = _oracle(case, 1000)
+    lb = _run_solver(case, 1000, False, False, None)
+    _compare(lb, o, False, case, 1000)
+    lbs = _run_solver(case, 1000, True, False, None)          # same case on the sparse storage
+    _compare(lbs, o, False, case, 1000)
+    assert abs(lb.get_max_v() - o.get_max_v()) <= 1e-6
+
+
+def test_checkpoint_roundtrip(cuda, tmp_path):
+    case = cases.case_mixed_bc()
+    o, o0 = _oracle(case, 8)
+    lb = case.make_solver(strict=True)
+    case.apply_start(lb, o0)
+    lb.run(5)
+    path = str(tmp_path / "ckpt.npz")
+    lb.save_checkpoint(path)
+    lb2 = case.make_solver(strict=True, sparse=True)           # restart on the other storage mode
+    lb2.load_checkpoint(path)
+    lb2.run(3)
+    _compare(lb2, o, exact=True)
+
+
+EDGE_SHAPES = [(1, 4, 5), (2, 2, 2), (3, 1, 40), (5, 3, 33), (4, 6, 1)]
+
+
+@pytest.mark.parametrize("shape", EDGE_SHAPES)
+@pytest.mark.parametrize("sparse", [False, True])
+def test_degenerate_extents(cuda, shape, sparse):
+    """extents of 1 or 2 make periodic_index wrap a node onto itself or onto the same neighbour
+    twice (:247-257); rows shorter / longer than a warp; all against the oracle, bit for bit"""
+    solid = cases.random_porous(shape, 0.25, 5)
+    solid.flat[0] = 0
+    case = cases.Case("edge", solid, force=[1e-5, -2e-5, 3e-5], perturb=1e-3)
+    o, o0 = _oracle(case, 6)
+    lb = case.make_solver(sparse=sparse, strict=True)
+    case.apply_start(lb, o0)
+    lb.run(6)
+    _compare(lb, o, exact=True)
+
+
+@pytest.mark.parametrize("sparse", [False, True])
+def test_all_solid_and_single_fluid_node(cuda, sparse):
+    """empty fluid set, and one fluid node enclosed by solid (every link bounces back)"""
+    from taichi_lbm3d_b200.constants import W
+    solid = np.ones((4, 5, 6), np.int8)
+    lb = cases.Case("solid", solid).make_solver(sparse=sparse)
+    lb.run(3)
+    assert lb.num_fluid() == 0
+    assert np.all(lb.rho.to_numpy() == 1.0) and np.all(lb.v.to_numpy() == 0.0)
+    assert lb.get_max_v() == 0.0
+    solid[2, 2, 3] = 0
+    case = cases.Case("one", solid, force=[1e-4, 0.0, 0.0], perturb=1e-3)
+    o, o0 = _oracle(case, 5)
+    lb = case.make_solver(sparse=sparse, strict=True)
+    case.apply_start(lb, o0)
+    lb.run(5)
+    _compare(lb, o, exact=True)
+    assert lb.num_fluid() == 1
+    if sparse:
+        assert np.all(lb.neighbor_table() == -1)
+    # mass of the enclosed node is conserved up to the reference's Guo mass sink (moment 0)
+    assert abs(lb.F.to_numpy()[2, 2, 3].sum() - o.F[2, 2, 3].sum()) == 0.0
+    assert np.array_equal(lb.F.to_numpy()[0, 0, 0], W)

@@ -98,3 +98,24 @@ def test_drainage_131_properties(cuda):
     assert np.isfinite(p[fl]).all() and np.isfinite(lb.F.to_numpy()[fl]).all()
     assert p[fl].min() > -1.2 and p[fl].max() < 1.2
     assert abs((rr + rb)[fl].mean() - 1.0) < 1e-3
+
+
+def test_config4_131_against_oracle(cuda):
+    """BASELINE config 4 at full size (131^3 stand-in, README parameters niu_l=0.05, niu_g=0.2,
+    CapA=0.005, psi_solid=0.7, constant psi=-1 on x0, force (5e-5,-2e-5,0)): 40 steps against
+    the C oracle, production arithmetic 1e-5, verification arithmetic bit-identical."""
+    from taichi_lbm3d_b200.geometry import ftb131_standin
+    solid = ftb131_standin()
+    psi = np.ones(solid.shape, np.float32)
+    psi[:13] = -1.0
+    case = cases2p.Case2P("cfg4", solid, psi, niu_l=0.05, niu_g=0.2, CapA=0.005, psi_solid=0.7)
+    o = _oracle(case, 40)
+    fl = solid == 0
+    lb = case.make_solver(strict=True)
+    lb.run(40)
+    for n in FIELDS:
+        assert np.array_equal(getattr(lb, n).to_numpy()[fl], getattr(o, n)[fl]), n
+    lbf = case.make_solver()
+    lbf.run(40)
+    for n in ("F", "rho", "psi", "rho_r", "rho_b"):
+        assert rel_linf(getattr(lbf, n).to_numpy()[fl], getattr(o, n)[fl]) <= TOL, n
