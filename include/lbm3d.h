@@ -52,7 +52,12 @@ typedef struct {
     int32_t nx, ny, nz;   /* lattice extents of this context (ctor :11) */
     int32_t sparse;       /* 0: direct-addressed dense lattice (:31-35);
                              1: compacted fluid-node list + 18-neighbour table, replaces the
-                                pointer/dense SNode tree (:36-44) */
+                                pointer/dense SNode tree (:36-44); two population buffers (A-B);
+                             2: the same list stepped IN PLACE on one buffer (AA pattern): odd
+                                steps pull through the table and store back into the pulled
+                                locations, even steps are purely local -- half the memory and
+                                the table is read every other step.  Falls back to 1 with
+                                halo_x (slab exchange needs both buffers) */
     int32_t strict;       /* 0: factored MRT transform, FMA allowed (production);
                              1: oracle evaluation order, no FMA contraction -> bit-identical
                                 to oracle/ref_single_phase.c (verification mode) */

@@ -165,7 +165,10 @@ class LB3D_Solver_Single_Phase:
         if not torch.cuda.is_available():
             raise _lib.LbmError("taichi_lbm3d_b200 needs a CUDA device (no CPU fallback)")
         dev = torch.cuda.current_device() if self.device is None else torch.device(self.device).index or 0
-        return _lib.LbmConfig(nx=self.nx, ny=self.ny, nz=self.nz, sparse=int(bool(self.sparse_storage)),
+        import os
+        # sparse storage steps in place (AA pattern, one population buffer) unless LBM3D_AA=0
+        mode = 0 if not self.sparse_storage else (1 if os.environ.get("LBM3D_AA", "1") == "0" else 2)
+        return _lib.LbmConfig(nx=self.nx, ny=self.ny, nz=self.nz, sparse=mode,
                               strict=int(self.strict), halo_x=0, device=int(dev), x_face_mask=0)
 
     def init_simulation(self):

@@ -18,6 +18,8 @@
 // The pull needs psi of step n at all neighbours before C can be formed, hence two kernels.
 // Algorithmic bytes per node-step: 152 (populations) + 16 (rho_r, rho_b r/w) +
 // 8 (psi r/w) = 176; this implementation moves 176 + 64 (record write + read) = 240.
+#include <cstdlib>
+
 #include "lbm2p_kernels.cuh"
 
 #ifdef LBM_STRICT
@@ -501,12 +503,16 @@ static void launch_main_t(const Step2Args &A, dim3 grid, dim3 blk, cudaStream_t 
         k2p_main<FORCE, MODE, false><<<grid, blk, 0, st>>>(A);
 }
 
-static void geometry(const StepArgs &a, int block, dim3 &grid, dim3 &blk) {
+// `zmax`: longest z extent of a block.  The main pass streams, so a block is one whole z-row
+// (contiguous chunk).  The colour pass gathers 19 neighbour records per node: a block of a
+// few y-rows x 64 z shares most of them through L1 (half the L2->L1 traffic of a one-row block).
+static void geometry(const StepArgs &a, int block, dim3 &grid, dim3 &blk, int zmax = 256) {
     if (block <= 0 || block > 256 || block % 32) block = 256;
-    // split a z-row into the fewest chunks of at most `block` threads, of equal (warp-rounded) size
-    const int nchunk = (a.nz + block - 1) / block;
+    if (zmax > block) zmax = block;
+    // split a z-row into the fewest chunks of at most `zmax` threads, of equal (warp-rounded) size
+    const int nchunk = (a.nz + zmax - 1) / zmax;
     int bx = ((a.nz + nchunk - 1) / nchunk + 31) / 32 * 32;
-    if (bx > block) bx = block;
+    if (bx > zmax) bx = zmax;
     int by = block / bx;
     if (by < 1) by = 1;
     blk = dim3(bx, by, 1);
@@ -534,7 +540,13 @@ cudaError_t launch_main(int mode, const Step2Args &A, int block, cudaStream_t st
 cudaError_t launch_colour(const Step2Args &A, int block, cudaStream_t st) {
     if (A.a.row_count == 0) return cudaSuccess;
     dim3 grid, blk;
-    geometry(A.a, block, grid, blk);
+    static int zmax = 0;
+    if (zmax == 0) {
+        const char *e = getenv("LBM3D_COLOUR_BX");       // tuning knob
+        zmax = e ? atoi(e) : 32;
+        if (zmax < 32 || zmax > 256 || zmax % 32) zmax = 32;
+    }
+    geometry(A.a, block, grid, blk, zmax);
     k2p_colour<<<grid, blk, 0, st>>>(A);
     return cudaGetLastError();
 }

@@ -77,6 +77,8 @@ struct lbm_ctx {
     uint32_t vbc_off[6]{};
     float *d_scalar = nullptr;
     // state machine
+    bool aa = false;             // sparse in-place (AA-pattern) stepping on one buffer
+    int parity = 0;              // aa: 0 = natural layout, 1 = arrival layout (see lbm_kernels.cuh)
     int cur = 0;
     bool pipe_valid = false;     // d_f[cur] holds f* of the current step
     bool macro_valid = true;     // d_rho / d_v current
@@ -271,6 +273,7 @@ void fill_args(const lbm_ctx *c, StepArgs &a) {
     for (int k = 0; k < 8; ++k) a.rb[k] = c->d_rb ? c->d_rb + (size_t)k * c->stride : nullptr;
     a.compressed = c->cfg.sparse ? c->compressed : 0;
     a.prefetch_dist = c->prefetch_dist;
+    a.aa = AA_OFF;
     a.lin = c->d_lin;
     a.rho = c->d_rho; a.v = c->d_v; a.F = nullptr;
     a.vbc = c->d_vbc;
@@ -341,6 +344,7 @@ int sync_fields(lbm_ctx *c, bool need_F) {
         fill_args(c, a);
         set_buffers(c, a, c->d_f[c->cur], nullptr);
         a.F = need_F ? c->d_F : nullptr;
+        if (c->aa && c->parity) a.aa = AA_EVEN;      // arrival layout: the streamed state is local
         int r = launch(c, MODE_EXTRACT, a, c->stream);
         if (r) return r;
         c->macro_valid = true;
@@ -746,11 +750,14 @@ int lbm_init(lbm_ctx *c) {
         c->pad = (((size_t)ny + 1) * c->prow + 2 + 31) / 32 * 32;
     }
     const size_t fbytes = (c->fsize + 2 * c->pad) * sizeof(float);
-    for (int b = 0; b < 2; ++b) {
+    c->aa = c->cfg.sparse == 2 && c->compressed && !c->cfg.halo_x;
+    c->parity = 0;
+    for (int b = 0; b < (c->aa ? 1 : 2); ++b) {
         CU(c, cudaMalloc(&c->d_fbase[b], fbytes));
         CU(c, cudaMemset(c->d_fbase[b], 0, fbytes));
         c->d_f[b] = c->d_fbase[b] + c->pad;
     }
+    if (c->aa) c->d_f[1] = c->d_f[0];
     CU(c, cudaMalloc(&c->d_rho, N * sizeof(float)));
     CU(c, cudaMalloc(&c->d_v, N * 3 * sizeof(float)));
     k_fill<<<nblocks(N, 256), 256>>>(c->d_rho, N, 1.0f);      // init() :165
@@ -782,6 +789,7 @@ static int ensure_pipeline(lbm_ctx *c, cudaStream_t st) {
     int r = launch(c, MODE_COLLIDE, a, st);
     if (r) return r;
     c->pipe_valid = true;
+    c->parity = 0;               // the collision writes the natural layout
     return LBM_OK;
 }
 
@@ -806,9 +814,11 @@ int lbm_step(lbm_ctx *c, int nsteps, void *cuda_stream) {
     fill_args(c, a);
     for (int it = 0; it < nsteps; ++it) {
         set_buffers(c, a, c->d_f[c->cur], c->d_f[c->cur ^ 1]);
+        if (c->aa) a.aa = c->parity ? AA_EVEN : AA_ODD;
         int r = launch(c, MODE_STEP, a, st);
         if (r) return r;
-        c->cur ^= 1;
+        if (c->aa) c->parity ^= 1;
+        else c->cur ^= 1;
     }
     c->macro_valid = false;
     c->F_valid = false;
@@ -1101,6 +1111,7 @@ int lbm_step_begin(lbm_ctx *c, void *cuda_stream) {
 int lbm_step_planes(lbm_ctx *c, int x_begin, int x_end, void *cuda_stream) {
     CTX_CHECK(c);
     if (!c->inited || !c->pipe_valid) FAIL(c, LBM_ERR_STATE, "pipeline not started");
+    if (c->aa) FAIL(c, LBM_ERR_STATE, "plane-wise stepping needs two buffers (create the context with sparse = 1)");
     const int lo = c->cfg.halo_x ? 1 : 0, hi = c->cfg.halo_x ? c->cfg.nx - 1 : c->cfg.nx;
     if (x_begin < lo || x_end > hi || x_begin > x_end) FAIL(c, LBM_ERR_INVALID, "plane range outside the owned slab");
     CU(c, cudaSetDevice(c->cfg.device));
@@ -1120,6 +1131,7 @@ int lbm_step_planes(lbm_ctx *c, int x_begin, int x_end, void *cuda_stream) {
 int lbm_step_flip(lbm_ctx *c) {
     CTX_CHECK(c);
     if (!c->inited || !c->pipe_valid) FAIL(c, LBM_ERR_STATE, "pipeline not started");
+    if (c->aa) FAIL(c, LBM_ERR_STATE, "plane-wise stepping needs two buffers (create the context with sparse = 1)");
     c->cur ^= 1;
     c->macro_valid = false;
     c->F_valid = false;

@@ -301,20 +301,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 // chains up to 9 DRAM round trips; through shared memory it is exactly one, costs no
 // registers, and 9 instructions per block.
 // Phase 2: 19 gathers, then the same BC / macro / collide / store code as the dense kernel.
-template <bool FORCE, int MODE, bool COMP>
+template <bool FORCE, int MODE, bool COMP, int AA>
 __global__ void __launch_bounds__(SPARSE_BLOCK, LBM_SPARSE_MINB) k_sparse(const StepArgs a) {
-    __shared__ alignas(128) int32_t s_tab[COMP ? 9 : 1][SPARSE_BLOCK];
+    constexpr bool TABLE = COMP && MODE != MODE_COLLIDE && AA != AA_EVEN;   // phase 1 needed
+    __shared__ alignas(128) int32_t s_tab[TABLE ? 9 : 1][SPARSE_BLOCK];
     __shared__ uint64_t s_bar;
     const uint32_t base = (blockIdx.x + a.first / SPARSE_BLOCK) * SPARSE_BLOCK;
     const uint32_t i = base + threadIdx.x;
-    if (COMP && MODE != MODE_COLLIDE) {
+    if (TABLE) {
         if (threadIdx.x == 0) mbar_init(&s_bar, 1);
         __syncthreads();
         if (threadIdx.x == 0) {
             mbar_expect_tx(&s_bar, 9u * SPARSE_BLOCK * 4u);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) bulk_g2s(&s_tab[k][0], a.rb[k] + base, SPARSE_BLOCK * 4u, &s_bar);
-            bulk_g2s(&s_tab[COMP ? 8 : 0][0], a.flags + base, SPARSE_BLOCK * 4u, &s_bar);
+            for (int k = 0; k < 8; ++k) bulk_g2s(&s_tab[TABLE ? k : 0][0], a.rb[k] + base, SPARSE_BLOCK * 4u, &s_bar);
+            bulk_g2s(&s_tab[TABLE ? 8 : 0][0], a.flags + base, SPARSE_BLOCK * 4u, &s_bar);
             if (MODE == MODE_STEP && a.prefetch_dist) {
                 // ask L2 for the table slice of the block one wave ahead
                 const uint32_t pb = base + a.prefetch_dist;
@@ -335,15 +336,22 @@ __global__ void __launch_bounds__(SPARSE_BLOCK, LBM_SPARSE_MINB) k_sparse(const 
         fl = a.flags[i];
         node_collide_only<FORCE>(f, a, fl, a.lin[i]);
     } else {
-        if (COMP) {
+        if (AA == AA_EVEN) {
+            // arrival layout: everything this node needs sits in its own 19 slots
+            if (!active) return;
+            fl = a.has_bc ? a.flags[i] : 0u;
+#define X(s, ex, ey, ez, o) f[s] = __ldg(a.pown[o] + i);
+            D3Q19_DIRS(X)
+#undef X
+        } else if (COMP) {
             if (active) f[0] = __ldg(a.pown[0] + i);
             mbar_wait(&s_bar, 0);
             if (!active) return;
-            fl = (uint32_t)s_tab[COMP ? 8 : 0][threadIdx.x];
+            fl = (uint32_t)s_tab[TABLE ? 8 : 0][threadIdx.x];
             if (!(fl & FL_EXCEPTION)) {
                 int32_t rb[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) rb[k] = s_tab[COMP ? k : 0][threadIdx.x];
+                for (int k = 0; k < 8; ++k) rb[k] = s_tab[TABLE ? k : 0][threadIdx.x];
 #define X(s, ex, ey, ez, o)                                                                    \
     if (s > 0) {                                                                               \
         const int32_t j = comp_source<ex, ey, ez>(i, fl, rb);                                  \
@@ -381,6 +389,34 @@ __global__ void __launch_bounds__(SPARSE_BLOCK, LBM_SPARSE_MINB) k_sparse(const 
             return;
         }
     }
+    if (AA == AA_ODD && MODE == MODE_STEP && COMP) {
+        // in place: f*_{LR[s]}(i) goes back to the location direction s was pulled from (each
+        // location is read and written by exactly this one thread, loads above, stores here)
+        a.pout[0][i] = f[0];
+        if (!(fl & FL_EXCEPTION)) {
+            int32_t rb[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) rb[k] = s_tab[TABLE ? k : 0][threadIdx.x];
+#define X(s, ex, ey, ez, o)                                                                    \
+    if (s > 0) {                                                                               \
+        const int32_t j = comp_source<ex, ey, ez>(i, fl, rb);                                  \
+        if ((fl >> s) & 1u) a.pout[o][i] = f[o];                                               \
+        else a.pout[s][(uint32_t)j] = f[o];                                                    \
+    }
+            D3Q19_DIRS(X)
+#undef X
+        } else {
+            const uint32_t slot = (uint32_t)s_tab[0][threadIdx.x];
+#define X(s, ex, ey, ez, o)                                                                    \
+    if (s > 0) {                                                                               \
+        if ((fl >> s) & 1u) a.pout[o][i] = f[o];                                               \
+        else a.pout[s][(uint32_t)__ldg(a.exc[s > 0 ? s - 1 : 0] + slot)] = f[o];               \
+    }
+            D3Q19_DIRS(X)
+#undef X
+        }
+        return;
+    }
 #pragma unroll
     for (int s = 0; s < 19; ++s) a.pout[s][i] = f[s];
 }
@@ -410,10 +446,14 @@ static void launch_sparse_t(const StepArgs &a, int block, cudaStream_t st) {
     block = SPARSE_BLOCK;
     const unsigned b0 = a.first / SPARSE_BLOCK, b1 = (a.first + a.count + SPARSE_BLOCK - 1) / SPARSE_BLOCK;
     const unsigned grid = b1 - b0;
-    if (a.compressed)
-        k_sparse<FORCE, MODE, true><<<grid, block, 0, st>>>(a);
+    if (!a.compressed)
+        k_sparse<FORCE, MODE, false, AA_OFF><<<grid, block, 0, st>>>(a);
+    else if (a.aa == AA_ODD)
+        k_sparse<FORCE, MODE, true, AA_ODD><<<grid, block, 0, st>>>(a);
+    else if (a.aa == AA_EVEN)
+        k_sparse<FORCE, MODE, true, AA_EVEN><<<grid, block, 0, st>>>(a);
     else
-        k_sparse<FORCE, MODE, false><<<grid, block, 0, st>>>(a);
+        k_sparse<FORCE, MODE, true, AA_OFF><<<grid, block, 0, st>>>(a);
 }
 
 #define DISPATCH(FN)                                                                           \

@@ -24,6 +24,7 @@
 #define FL_EXCEPTION (1u << 31)   /* sparse: pull sources listed explicitly in the exception table */
 
 enum { MODE_STEP = 0, MODE_EXTRACT = 1, MODE_COLLIDE = 2 };
+enum { AA_OFF = 0, AA_ODD = 1, AA_EVEN = 2 };
 // dense node classes: BULK = fluid, no solid link / wrap / BC (the speculative pull is final);
 // SOLID = nothing to do; SPECIAL = fluid that needs its link word; SOLID_WRITE = solid node
 // sharing a 32-byte sector with a fluid node: it stores (dead) values so that the sector is
@@ -66,6 +67,14 @@ struct StepArgs {
     const int32_t *exc[18];
     int compressed;
     uint32_t prefetch_dist;         // nodes ahead whose table lines are pulled into L2 (0 = off)
+    // sparse in-place (AA-pattern) stepping on ONE buffer (pown == pout planes):
+    //   AA_OFF   two buffers, pull from pown, store to pout
+    //   AA_ODD   buffer in natural layout (slot s of node i = f*_s(i)): pull like AA_OFF, then
+    //            store f*_{LR[s]} back into the very location direction s was pulled from, which
+    //            leaves every slot holding the population that ARRIVES there next step
+    //   AA_EVEN  buffer in arrival layout: F_q(i) = slot LR[q] of node i, purely local, no
+    //            table; stores f*_q into slot q (natural layout again)
+    int aa;
     const uint32_t *lin;            // [n_fluid] linear index of each stored node
     // user-visible dense arrays (reference layout), used by MODE_EXTRACT / MODE_COLLIDE
     float *rho;                     // [N]
