@@ -254,16 +254,20 @@ def main():
     max_v = stepper.get_max_v()
 
     # ---- end to end through the public API with host buffers ---------------------------------
-    e2e = None
+    # the whole user-level job: host geometry in (pinned), init_simulation (table / flag build),
+    # K x step(), rho, v and max_v back into pinned host buffers; wall clock between barriers,
+    # max over ranks
+    del lb, stepper
+    torch.cuda.empty_cache()
+    from taichi_lbm3d_b200 import LB3D_Solver_Single_Phase
+    from taichi_lbm3d_b200.multi_gpu import SlabPartition, SlabSolver
+    own = SlabPartition(gnx, world, rank).own
+    pinned = torch.from_numpy(solid).pin_memory()
+    rho_pin = torch.empty((own, ny, nz), dtype=torch.float32, pin_memory=True)
+    v_pin = torch.empty((own, ny, nz, 3), dtype=torch.float32, pin_memory=True)
+    barrier()
+    t0 = time.perf_counter()
     if world == 1:
-        from taichi_lbm3d_b200 import LB3D_Solver_Single_Phase
-        del lb, stepper
-        torch.cuda.empty_cache()
-        pinned = torch.from_numpy(solid).pin_memory()
-        rho_pin = torch.empty((gnx, ny, nz), dtype=torch.float32, pin_memory=True)  # noqa
-        v_pin = torch.empty((gnx, ny, nz, 3), dtype=torch.float32, pin_memory=True)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
         lb2 = LB3D_Solver_Single_Phase(gnx, ny, nz, sparse_storage=args.sparse)
         lb2.solid.from_numpy(pinned.numpy())            # host geometry in
         configure(lb2)
@@ -272,14 +276,32 @@ def main():
             lb2.step()
         rho_h = lb2.rho.to_numpy(out=rho_pin.numpy())   # D2H results into pinned host buffers
         v_h = lb2.v.to_numpy(out=v_pin.numpy())
-        mv = lb2.get_max_v()
-        dt = time.perf_counter() - t0
-        e2e = {"value": nfl_total * args.steps / dt / 1e6, "unit": "MLUPS",
-               "h2d_bytes_per_step": solid.nbytes / args.steps,
-               "d2h_bytes_per_step": (rho_h.nbytes + v_h.nbytes + 4) / args.steps,
-               "job": "geometry upload + init_simulation + %d x step() + rho, v, max_v to host" % args.steps,
-               "seconds": dt, "max_v": mv}
-        del lb2
+        h2d = solid.nbytes
+    else:
+        lb2 = SlabSolver(gnx, ny, nz, sparse_storage=args.sparse)
+        lb2.set_solid(pinned.numpy())
+        configure(lb2)
+        lb2.init_simulation()
+        for _ in range(args.steps):
+            lb2.step()
+        rho_pin.numpy()[...] = lb2.local_field("rho")
+        v_pin.numpy()[...] = lb2.local_field("v")
+        rho_h, v_h = rho_pin.numpy(), v_pin.numpy()
+        h2d = (own + 2) * ny * nz
+    mv = lb2.get_max_v()
+    barrier()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    e2e = {"value": nfl_total * args.steps / dt / 1e6, "unit": "MLUPS",
+           "h2d_bytes_per_step": h2d * n_gpus / args.steps,
+           "d2h_bytes_per_step": (rho_h.nbytes + v_h.nbytes + 4) * n_gpus / args.steps,
+           "job": "geometry upload + init_simulation + %d x step() + rho, v, max_v to host%s"
+                  % (args.steps, "" if world == 1 else " (every rank its slab)"),
+           "seconds": dt, "max_v": mv}
+    del lb2
 
     if rank != 0:
         if world > 1:
@@ -315,7 +337,10 @@ def main():
     if not args.no_cpu_baseline and n_gpus == 1:
         try:
             cores = os.cpu_count() or 1
-            nb, sb = 128, 5
+            # bounded sample: about 12 s of host time on a 128^3 cavity, sized from a 64^3 probe
+            cal, _, _ = cpu_reference_run(64, 2, 1)
+            nb = 128
+            sb = int(max(5, min(400, 12.0 * cal * 1e6 / nb ** 3)))
             v, dtc, nflc = cpu_reference_run(nb, sb, 1)
             line["cpu_baseline"] = {"value": v, "unit": "MLUPS", "cores": cores, "kind": "port",
                                     "sample": "%d steps of a %d^3 cavity (same BCs), C/OpenMP restatement of the "

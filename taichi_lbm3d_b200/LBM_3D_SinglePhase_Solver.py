@@ -7,7 +7,7 @@ the fused sm_100a CUDA step behind the C ABI of ``include/lbm3d.h``.  The case s
 the reference run after dropping their two Taichi lines (``import taichi`` / ``ti.init``).
 
 Additions that the reference does not have: ``run(n)`` (n steps, one launch each, no
-Python in between), ``tau_mode`` (the textbook relaxation time the other copies of the
+Python in between), ``in_place`` (sparse storage on ONE population buffer, AA pattern), ``tau_mode`` (the textbook relaxation time the other copies of the
 solver use), ``strict`` (oracle-order arithmetic for verification), ``to_torch`` on fields.
 
 There is no CPU path: constructing the solver is cheap, ``init_simulation`` needs a GPU.
@@ -64,10 +64,14 @@ class _Field:
 
 
 class LB3D_Solver_Single_Phase:
-    def __init__(self, nx, ny, nz, sparse_storage=False, strict=False, tau_mode="class", device=None):
+    def __init__(self, nx, ny, nz, sparse_storage=False, strict=False, tau_mode="class", device=None,
+                 in_place=None):
         # reference :13-28
         self.enable_projection = True
         self.sparse_storage = sparse_storage
+        # sparse storage only: step IN PLACE on one population buffer (AA pattern: half the
+        # memory, 82 % instead of 87 % of the HBM roofline on B200); default from LBM3D_AA
+        self.in_place = in_place
         self.nx, self.ny, self.nz = nx, ny, nz
         self.fx, self.fy, self.fz = 0.0e-6, 0.0, 0.0
         self.niu = 0.16667
@@ -166,8 +170,8 @@ class LB3D_Solver_Single_Phase:
             raise _lib.LbmError("taichi_lbm3d_b200 needs a CUDA device (no CPU fallback)")
         dev = torch.cuda.current_device() if self.device is None else torch.device(self.device).index or 0
         import os
-        # sparse storage steps in place (AA pattern, one population buffer) unless LBM3D_AA=0
-        mode = 0 if not self.sparse_storage else (1 if os.environ.get("LBM3D_AA", "1") == "0" else 2)
+        in_place = os.environ.get("LBM3D_AA", "0") == "1" if self.in_place is None else bool(self.in_place)
+        mode = 0 if not self.sparse_storage else (2 if in_place else 1)
         return _lib.LbmConfig(nx=self.nx, ny=self.ny, nz=self.nz, sparse=mode,
                               strict=int(self.strict), halo_x=0, device=int(dev), x_face_mask=0)
 

@@ -116,7 +116,9 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
+    # LBM3D_LIB: a differently tuned build of the same sources (python -m taichi_lbm3d_b200.build
+    # --tag NAME --flags "-D..."), for A/B timing on the GPU box
+    path = os.environ.get("LBM3D_LIB") or _build.LIB
     if not os.path.exists(path):
         try:
             _build.build()

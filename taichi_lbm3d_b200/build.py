@@ -52,8 +52,19 @@ def needs_build():
     return any(os.path.getmtime(s) > t for s in _sources())
 
 
-def build(force=False, verbose=False):
-    """Compile and link; returns the library path."""
+def build(force=False, verbose=False, tag=None, flags=None):
+    """Compile and link; returns the library path.  `tag` / `flags` build a tuning variant
+    lib/liblbm3d_b200.<tag>.so with extra nvcc flags (selected at run time with LBM3D_LIB)."""
+    global OBJDIR, LIB
+    if tag:
+        saved = OBJDIR, LIB
+        OBJDIR, LIB = os.path.join(LIBDIR, "obj_" + tag), os.path.join(LIBDIR, "liblbm3d_b200.%s.so" % tag)
+        os.environ["LBM3D_NVCC_FLAGS"] = flags or ""
+        try:
+            return build(force=True, verbose=verbose)
+        finally:
+            OBJDIR, LIB = saved
+            os.environ.pop("LBM3D_NVCC_FLAGS", None)
     if not force and not needs_build():
         return LIB
     nvcc = _nvcc()
@@ -90,4 +101,6 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    _tag = sys.argv[sys.argv.index("--tag") + 1] if "--tag" in sys.argv else None
+    _flags = sys.argv[sys.argv.index("--flags") + 1] if "--flags" in sys.argv else None
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, tag=_tag, flags=_flags))

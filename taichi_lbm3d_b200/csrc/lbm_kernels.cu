@@ -13,6 +13,8 @@
 //                 from_numpy): reads F, rho, v exactly as the reference's colission does
 //
 // Compiled twice (see lbm_kernels.cuh): namespace lbm_fast / lbm_strict.
+#include <cstdlib>
+
 #include "lbm_kernels.cuh"
 
 #ifdef LBM_STRICT
@@ -245,6 +247,9 @@ __global__ void __launch_bounds__(256) k_dense(const StepArgs a) {
 #ifndef LBM_SPARSE_MINB
 #define LBM_SPARSE_MINB 8
 #endif
+#ifndef LBM_SPARSE_MINB_ODD
+#define LBM_SPARSE_MINB_ODD 6
+#endif
 #define SPARSE_BLOCK 256
 
 // Gathers of the sparse kernel touch partial 128-byte lines (pores are a few nodes wide), but
@@ -295,42 +300,44 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 // compact list (B counted from the start of the arrays so that every bulk copy is 16-byte
 // aligned); threads outside [first, first+count) idle.
 //
-// Phase 1 (COMP): one elected thread pulls the block's slice of the 9 table arrays (8 row
-// ranks + link word, 9 KB) into shared memory with TMA bulk copies on one mbarrier.  Doing
-// this through registers instead lets ptxas sink each index load to its first use and
-// chains up to 9 DRAM round trips; through shared memory it is exactly one, costs no
-// registers, and 9 instructions per block.
+// Phase 1 (COMP): one elected thread pulls the block's slice of the pull table (8 arrays of
+// 16-bit row-rank offsets, the link words, the block's rank bases: 5.2 KB) into shared memory
+// with TMA bulk copies on one mbarrier.  Doing this through registers instead lets ptxas sink
+// each index load to its first use and chains up to 9 DRAM round trips; through shared memory
+// it is exactly one, costs no registers, and 10 instructions per block.
 // Phase 2: 19 gathers, then the same BC / macro / collide / store code as the dense kernel.
+// A direction whose pull source is solid reads the node's own opposite population instead
+// (half-way bounce-back); the node INDEX is selected, so either way it is one load (and, in
+// place, one store) per direction and warp.
+struct SparseTable {
+    alignas(128) uint16_t rb[8][SPARSE_BLOCK];
+    alignas(16) uint32_t fl[SPARSE_BLOCK];
+    alignas(16) int32_t blk[16];
+};
+constexpr uint32_t kTableBytes = 8u * SPARSE_BLOCK * 2u + SPARSE_BLOCK * 4u + 64u;
+
+// issue the bulk copies of table block `blk` into `tab`, completing on `bar`
+__device__ __forceinline__ void table_fetch(const StepArgs &a, uint32_t blk, SparseTable &tab, uint64_t *bar) {
+    const uint32_t base = blk * SPARSE_BLOCK;
+    mbar_expect_tx(bar, kTableBytes);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) bulk_g2s(&tab.rb[k][0], a.rb16[k] + base, SPARSE_BLOCK * 2u, bar);
+    bulk_g2s(&tab.fl[0], a.flags + base, SPARSE_BLOCK * 4u, bar);
+    bulk_g2s(&tab.blk[0], a.blk + (size_t)blk * 16, 64u, bar);
+}
+
+// one stored node: pull (through the table slice in shared memory once `bar` flips to
+// `parity`), BC, macro, collide, store
 template <bool FORCE, int MODE, bool COMP, int AA>
-__global__ void __launch_bounds__(SPARSE_BLOCK, LBM_SPARSE_MINB) k_sparse(const StepArgs a) {
-    constexpr bool TABLE = COMP && MODE != MODE_COLLIDE && AA != AA_EVEN;   // phase 1 needed
-    __shared__ alignas(128) int32_t s_tab[TABLE ? 9 : 1][SPARSE_BLOCK];
-    __shared__ uint64_t s_bar;
-    const uint32_t base = (blockIdx.x + a.first / SPARSE_BLOCK) * SPARSE_BLOCK;
-    const uint32_t i = base + threadIdx.x;
-    if (TABLE) {
-        if (threadIdx.x == 0) mbar_init(&s_bar, 1);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            mbar_expect_tx(&s_bar, 9u * SPARSE_BLOCK * 4u);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) bulk_g2s(&s_tab[TABLE ? k : 0][0], a.rb[k] + base, SPARSE_BLOCK * 4u, &s_bar);
-            bulk_g2s(&s_tab[TABLE ? 8 : 0][0], a.flags + base, SPARSE_BLOCK * 4u, &s_bar);
-            if (MODE == MODE_STEP && a.prefetch_dist) {
-                // ask L2 for the table slice of the block one wave ahead
-                const uint32_t pb = base + a.prefetch_dist;
-                if (pb + SPARSE_BLOCK <= a.first + a.count) {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.rb[k] + pb), "r"(SPARSE_BLOCK * 4u) : "memory");
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.flags + pb), "r"(SPARSE_BLOCK * 4u) : "memory");
-                }
-            }
-        }
-    }
+__device__ __forceinline__ void sparse_node(const StepArgs &a, const SparseTable &s_tab, uint64_t *s_bar,
+                                            uint32_t parity, uint32_t i) {
     const bool active = i >= a.first && i < a.first + a.count;
     float f[19];
     uint32_t fl = 0;
+    // half-way bounce-back (:267-268): a direction whose pull source is solid takes the node's
+    // own opposite population, which sits `stride` elements above or below in the next plane;
+    // as ONE signed node index per direction (the context guarantees 2 * stride < 2^31)
+    const int32_t ip = (int32_t)i + (int32_t)a.stride, im = (int32_t)i - (int32_t)a.stride;
     if (MODE == MODE_COLLIDE) {
         if (!active) return;
         fl = a.flags[i];
@@ -344,31 +351,27 @@ __global__ void __launch_bounds__(SPARSE_BLOCK, LBM_SPARSE_MINB) k_sparse(const 
             D3Q19_DIRS(X)
 #undef X
         } else if (COMP) {
-            if (active) f[0] = __ldg(a.pown[0] + i);
-            mbar_wait(&s_bar, 0);
+            mbar_wait(s_bar, parity);
             if (!active) return;
-            fl = (uint32_t)s_tab[TABLE ? 8 : 0][threadIdx.x];
+            fl = s_tab.fl[threadIdx.x];
             if (!(fl & FL_EXCEPTION)) {
                 int32_t rb[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) rb[k] = s_tab[TABLE ? k : 0][threadIdx.x];
+                for (int k = 0; k < 8; ++k) rb[k] = s_tab.blk[k] + (int32_t)s_tab.rb[k][threadIdx.x];
 #define X(s, ex, ey, ez, o)                                                                    \
-    if (s > 0) {                                                                               \
-        const int32_t j = comp_source<ex, ey, ez>(i, fl, rb);                                  \
-        f[s] = ((fl >> s) & 1u) ? ldg_gather(a.pown[o] + i) : ldg_gather(a.pown[s] + (uint32_t)j); \
-    }
+    if (s > 0) f[s] = ldg_gather(a.pown[s] + (((fl >> s) & 1u) ? ((o) > (s) ? ip : im) : comp_source<ex, ey, ez>(i, fl, rb)));
                 D3Q19_DIRS(X)
 #undef X
             } else {
-                const uint32_t slot = (uint32_t)s_tab[0][threadIdx.x];
+                const uint32_t slot = (uint32_t)s_tab.blk[8] + s_tab.rb[0][threadIdx.x];
 #define X(s, ex, ey, ez, o)                                                                    \
-    if (s > 0) {                                                                               \
-        f[s] = ((fl >> s) & 1u) ? __ldg(a.pown[o] + i)                                         \
-                                : __ldg(a.pown[s] + (uint32_t)__ldg(a.exc[s > 0 ? s - 1 : 0] + slot)); \
-    }
+    if (s > 0) f[s] = __ldg(a.pown[s] + (((fl >> s) & 1u) ? ((o) > (s) ? ip : im) : __ldg(a.exc[s > 0 ? s - 1 : 0] + slot)));
                 D3Q19_DIRS(X)
 #undef X
             }
+            // the rest population last: requested first, ptxas parks it in local memory at once,
+            // which waits for it to arrive before any gather is issued
+            f[0] = __ldg(a.pown[0] + i);
         } else {
             if (!active) return;
             fl = a.has_bc ? a.flags[i] : 0u;
@@ -396,22 +399,15 @@ __global__ void __launch_bounds__(SPARSE_BLOCK, LBM_SPARSE_MINB) k_sparse(const 
         if (!(fl & FL_EXCEPTION)) {
             int32_t rb[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) rb[k] = s_tab[TABLE ? k : 0][threadIdx.x];
+            for (int k = 0; k < 8; ++k) rb[k] = s_tab.blk[k] + (int32_t)s_tab.rb[k][threadIdx.x];
 #define X(s, ex, ey, ez, o)                                                                    \
-    if (s > 0) {                                                                               \
-        const int32_t j = comp_source<ex, ey, ez>(i, fl, rb);                                  \
-        if ((fl >> s) & 1u) a.pout[o][i] = f[o];                                               \
-        else a.pout[s][(uint32_t)j] = f[o];                                                    \
-    }
+    if (s > 0) a.pout[s][((fl >> s) & 1u) ? ((o) > (s) ? ip : im) : comp_source<ex, ey, ez>(i, fl, rb)] = f[o];
             D3Q19_DIRS(X)
 #undef X
         } else {
-            const uint32_t slot = (uint32_t)s_tab[0][threadIdx.x];
+            const uint32_t slot = (uint32_t)s_tab.blk[8] + s_tab.rb[0][threadIdx.x];
 #define X(s, ex, ey, ez, o)                                                                    \
-    if (s > 0) {                                                                               \
-        if ((fl >> s) & 1u) a.pout[o][i] = f[o];                                               \
-        else a.pout[s][(uint32_t)__ldg(a.exc[s > 0 ? s - 1 : 0] + slot)] = f[o];               \
-    }
+    if (s > 0) a.pout[s][((fl >> s) & 1u) ? ((o) > (s) ? ip : im) : __ldg(a.exc[s > 0 ? s - 1 : 0] + slot)] = f[o];
             D3Q19_DIRS(X)
 #undef X
         }
@@ -419,6 +415,35 @@ __global__ void __launch_bounds__(SPARSE_BLOCK, LBM_SPARSE_MINB) k_sparse(const 
     }
 #pragma unroll
     for (int s = 0; s < 19; ++s) a.pout[s][i] = f[s];
+}
+
+// occupancy: 8 blocks (32 registers) per SM, except the in-place odd step, which keeps the 19
+// pull locations live across the collision and is faster unspilled at 6 blocks (40 registers)
+template <bool FORCE, int MODE, bool COMP, int AA>
+__global__ void __launch_bounds__(SPARSE_BLOCK, (AA == AA_ODD && MODE == MODE_STEP) ? LBM_SPARSE_MINB_ODD : LBM_SPARSE_MINB)
+k_sparse(const StepArgs a) {
+    constexpr bool TABLE = COMP && MODE != MODE_COLLIDE && AA != AA_EVEN;   // phase 1 needed
+    __shared__ SparseTable s_tab;
+    __shared__ uint64_t s_bar;
+    const uint32_t blk = blockIdx.x + a.first / SPARSE_BLOCK;
+    if (TABLE) {
+        if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            table_fetch(a, blk, s_tab, &s_bar);
+            if (MODE == MODE_STEP && a.prefetch_dist) {
+                // ask L2 for the table slice of the block one wave ahead
+                const uint32_t pb = blk * SPARSE_BLOCK + a.prefetch_dist;
+                if (pb + SPARSE_BLOCK <= a.first + a.count) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.rb16[k] + pb), "r"(SPARSE_BLOCK * 2u) : "memory");
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.flags + pb), "r"(SPARSE_BLOCK * 4u) : "memory");
+                }
+            }
+        }
+    }
+    sparse_node<FORCE, MODE, COMP, AA>(a, s_tab, &s_bar, 0u, blk * SPARSE_BLOCK + threadIdx.x);
 }
 
 template <bool FORCE, int MODE>

@@ -78,7 +78,7 @@ CASES = [cases.case_mixed_bc, cases.case_periodic_force, cases.case_all_faces]
 
 
 @pytest.mark.parametrize("make", CASES)
-@pytest.mark.parametrize("sparse", [False, True])
+@pytest.mark.parametrize("sparse", [False, True, "aa"])
 @pytest.mark.parametrize("steps", [1, 2, 25])
 def test_strict_bit_identical(cuda, make, sparse, steps):
     case = make()
@@ -88,7 +88,7 @@ def test_strict_bit_identical(cuda, make, sparse, steps):
 
 
 @pytest.mark.parametrize("make", CASES)
-@pytest.mark.parametrize("sparse", [False, True])
+@pytest.mark.parametrize("sparse", [False, True, "aa"])
 def test_fast_parity_small(cuda, make, sparse):
     case = make()
     o, o0 = _oracle(case, 200)
@@ -169,7 +169,10 @@ def test_sparse_tables_bit_exact(cuda):
     """fluid-node compaction and 18-neighbour pull table vs a NumPy construction from solid,
     periodic_index (:247-257) and e (:183-187)."""
     from taichi_lbm3d_b200.constants import E
-    for shape, frac, seed in [((12, 10, 9), 0.35, 3), ((33, 17, 40), 0.8, 9), ((7, 7, 7), 0.0, 1)]:
+    # the last lattice holds > 65535 fluid nodes per x plane pair: the periodic x wrap makes the
+    # neighbour-row ranks of some 256-node table blocks span more than 16 bits (exception path)
+    for shape, frac, seed in [((12, 10, 9), 0.35, 3), ((33, 17, 40), 0.8, 9), ((7, 7, 7), 0.0, 1),
+                              ((40, 48, 48), 0.1, 5)]:
         solid = cases.random_porous(shape, frac, seed)
         case = cases.Case("t", solid, bc=[(0, "rho", 1.0), (5, "vel", [0, 0, 0.01])])
         lb = case.make_solver(sparse=True)
@@ -191,6 +194,17 @@ def test_sparse_tables_bit_exact(cuda):
         for s in range(1, 19):
             assert np.array_equal(((fl[fluid] >> s) & 1).astype(bool), want[s - 1] < 0)
         assert np.array_equal((fl >> 19) & 1, solid.astype(np.uint32))
+
+
+@pytest.mark.parametrize("sparse", [True, "aa"])
+def test_wide_table_blocks_bit_identical(cuda, sparse):
+    """periodic lattice large enough that table blocks straddling the x wrap overflow the
+    16-bit rank offsets (all their nodes become exceptions): still bit-identical to the oracle"""
+    solid = cases.random_porous((40, 48, 48), 0.1, 5)
+    case = cases.Case("wide", solid, force=[1e-5, 2e-6, -3e-6], perturb=1e-3)
+    o, o0 = _oracle(case, 3)
+    lb = _run_solver(case, 3, sparse, True, o0)
+    _compare(lb, o, exact=True)
 
 
 def test_rest_state_and_mass(cuda):
@@ -232,6 +246,9 @@ def test_full_size_properties_256(cuda):
     assert rel_linf(lbs.rho.to_numpy(), rho) <= 1e-6
     assert rel_linf(lbs.v.to_numpy(), v) <= TOL
     assert lbs.num_fluid() == 255 * 254 * 254
+    lba = case.make_solver(sparse="aa")                  # in place == two buffers, bit for bit
+    lba.run(100)
+    assert np.array_equal(lba.v.to_numpy(), lbs.v.to_numpy())
 
 
 def test_launches_are_counted(cuda):
@@ -273,7 +290,7 @@ EDGE_SHAPES = [(1, 4, 5), (2, 2, 2), (3, 1, 40), (5, 3, 33), (4, 6, 1)]
 
 
 @pytest.mark.parametrize("shape", EDGE_SHAPES)
-@pytest.mark.parametrize("sparse", [False, True])
+@pytest.mark.parametrize("sparse", [False, True, "aa"])
 def test_degenerate_extents(cuda, shape, sparse):
     """extents of 1 or 2 make periodic_index wrap a node onto itself or onto the same neighbour
     twice (:247-257); rows shorter / longer than a warp; all against the oracle, bit for bit"""
@@ -287,7 +304,7 @@ def test_degenerate_extents(cuda, shape, sparse):
     _compare(lb, o, exact=True)
 
 
-@pytest.mark.parametrize("sparse", [False, True])
+@pytest.mark.parametrize("sparse", [False, True, "aa"])
 def test_all_solid_and_single_fluid_node(cuda, sparse):
     """empty fluid set, and one fluid node enclosed by solid (every link bounces back)"""
     from taichi_lbm3d_b200.constants import W
