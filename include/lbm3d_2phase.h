@@ -24,11 +24,16 @@ extern "C" {
 
 typedef struct lbm2p_ctx lbm2p_ctx;
 
+/* lbm2p_config.reserved: x-slab flags (multi-GPU, new work: the reference is single-device) */
+#define LBM2P_HALO_X 1     /* planes x=0 and x=nx-1 are ghost planes owned by the slab neighbours */
+#define LBM2P_HOLDS_X0 2   /* this slab's first owned plane is the global x0 face */
+#define LBM2P_HOLDS_X1 4   /* this slab's last owned plane is the global x1 face */
+
 typedef struct {
     int32_t nx, ny, nz;   /* :17 */
     int32_t strict;       /* 1: oracle evaluation order, no FMA contraction (verification) */
     int32_t device;
-    int32_t reserved;
+    int32_t reserved;     /* 0, or LBM2P_HALO_X | LBM2P_HOLDS_X0 | LBM2P_HOLDS_X1 */
 } lbm2p_config;
 
 int lbm2p_create(const lbm2p_config *cfg, lbm2p_ctx **out);
@@ -68,6 +73,28 @@ int lbm2p_get_solid(lbm2p_ctx *ctx, int8_t *dst);
 int lbm2p_set_state(lbm2p_ctx *ctx, const float *F, const float *rho, const float *v, const float *psi,
                     const float *rho_r, const float *rho_b);
 int lbm2p_get_max_v(lbm2p_ctx *ctx, float *out);
+
+/* ---- multi-GPU x-slabs (contexts created with LBM2P_HALO_X) -------------------------------
+ * The collision of a node needs psi of its 18 neighbours and the colour pass the records of its
+ * 18 pull sources, so a step has TWO exchanges across every cut:
+ *   stage 0 (after the main pass):   the 5 populations of f* that cross the cut + the colour
+ *                                    records (rho_r, rho_b, v, q, C) of the boundary plane,
+ *                                    15 floats per face node
+ *   stage 1 (after the colour pass): psi of the boundary plane, 1 float per face node
+ * lbm2p_run_slab drives colour ; exchange(1) ; main ; exchange(0) with ncclSend/ncclRecv.  The
+ * pack / unpack / stage entry points let another transport (torch.distributed, or several
+ * emulated ranks in one process) run the same schedule:
+ *   stage(0) ; exchange(0) ; repeat { stage(1) ; exchange(1) ; stage(2) ; exchange(0) }
+ * side 0 = towards x-1 (packs local plane 1, fills ghost plane 0), side 1 = towards x+1. */
+int64_t lbm2p_halo_floats(lbm2p_ctx *ctx, int stage);
+int lbm2p_halo_pack(lbm2p_ctx *ctx, int stage, int side, float *dst_dev, void *cuda_stream);
+int lbm2p_halo_unpack(lbm2p_ctx *ctx, int stage, int side, const float *src_dev, void *cuda_stream);
+/* stage 0: first collision of the user-visible state (returns 1 if already done), 1: colour
+ * pass, 2: main pass */
+int lbm2p_slab_stage(lbm2p_ctx *ctx, int stage, void *cuda_stream);
+int lbm2p_comm_unique_id(void *out128);
+int lbm2p_comm_init(lbm2p_ctx *ctx, const void *id128, int world, int rank);
+int lbm2p_run_slab(lbm2p_ctx *ctx, int nsteps, void *cuda_stream);
 
 #ifdef __cplusplus
 }

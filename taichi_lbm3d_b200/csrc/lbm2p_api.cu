@@ -1,5 +1,6 @@
 // C-ABI layer of the two-phase colour-gradient solver (include/lbm3d_2phase.h).
-// Reference: 2phase/lbm_solver_3d_2phase.py (line numbers below).  Dense storage, one GPU.
+// Reference: 2phase/lbm_solver_3d_2phase.py (line numbers below).  Dense storage; one GPU or an
+// x-slab of a multi-GPU run (ghost planes + two halo exchanges per step, see lbm2p_run_slab).
 #include <cub/cub.cuh>
 #include <cuda_runtime.h>
 #include <thrust/iterator/transform_iterator.h>
@@ -12,6 +13,7 @@
 #include "../../include/lbm3d_2phase.h"
 #include "lbm2p_kernels.cuh"
 #include "lbm_geometry.cuh"
+#include "lbm_nccl.cuh"
 
 namespace {
 thread_local std::string g2_create_error;
@@ -59,6 +61,14 @@ struct lbm2p_ctx {
     bool macro_valid = true, F_valid = true;
     cudaStream_t stream = nullptr;
     int64_t launches = 0;
+    // x-slab (cfg.reserved bit0): planes 0 and nx-1 are ghost planes
+    bool halo = false;
+    int xface0 = 0, xface1 = 0;            // local x of the global x faces (-1: not in this slab)
+    uint32_t row_first = 0, row_count = 0;  // z-rows updated by a step
+    void *comm = nullptr;                  // ncclComm_t
+    int comm_world = 1, comm_rank = 0;
+    bool comm_ready = false;
+    float *d_send[2] = {nullptr, nullptr}, *d_recv[2] = {nullptr, nullptr};
 };
 
 #define CTX2(ctx)                                                                              \
@@ -143,8 +153,9 @@ void fill2(const lbm2p_ctx *c, Step2Args &A, const float *fin, float *fout) {
         a.pout[s] = fout ? fout + (size_t)s * c->nzp : nullptr;
     }
     a.stride = 0;
-    a.row_first = 0;
-    a.row_count = (uint32_t)(c->cfg.nx * c->cfg.ny);
+    a.row_first = c->row_first;
+    a.row_count = c->row_count;
+    a.halo_x = c->halo ? 1 : 0;
     a.prow = c->prow;
     a.spec = c->spec;
     a.nx = c->cfg.nx; a.ny = c->cfg.ny; a.nz = c->cfg.nz;
@@ -267,6 +278,8 @@ int lbm2p_create(const lbm2p_config *cfg, lbm2p_ctx **out) {
     lbm2p_ctx *c = new lbm2p_ctx();
     c->cfg = *cfg;
     c->N = N;
+    c->halo = (cfg->reserved & LBM2P_HALO_X) != 0;
+    if (c->halo && cfg->nx < 3) { g2_create_error = "an x-slab needs nx >= 3 (two ghost planes)"; delete c; return -1; }
     if (const char *b = getenv("LBM3D_BLOCK")) {
         int v = atoi(b);
         if (v >= 32 && v <= 256 && v % 32 == 0) c->block = v;
@@ -291,6 +304,8 @@ int lbm2p_destroy(lbm2p_ctx *c) {
     CTX2(c);
     cudaSetDevice(c->cfg.device);
     cudaDeviceSynchronize();
+    if (c->comm && g_nccl.ok) g_nccl.CommDestroy(c->comm);
+    for (int i = 0; i < 2; ++i) { cudaFree(c->d_send[i]); cudaFree(c->d_recv[i]); }
     free2(c);
     cudaFree(c->d_solid);
     cudaFree(c->d_psi0);
@@ -371,8 +386,19 @@ int lbm2p_init(lbm2p_ctx *c) {
     c->inited = false;
     GeoParams g;
     g.nx = nx; g.ny = ny; g.nz = nz;
-    g.halo_x = 0;
-    g.xface0 = 0; g.xface1 = nx - 1;
+    g.halo_x = c->halo ? 1 : 0;
+    if (c->halo) {
+        // the global x faces are the first / last OWNED planes of the slabs that hold them
+        c->xface0 = (c->cfg.reserved & LBM2P_HOLDS_X0) ? 1 : -1;
+        c->xface1 = (c->cfg.reserved & LBM2P_HOLDS_X1) ? nx - 2 : -1;
+        c->row_first = (uint32_t)ny;
+        c->row_count = (uint32_t)(ny * (nx - 2));
+    } else {
+        c->xface0 = 0; c->xface1 = nx - 1;
+        c->row_first = 0;
+        c->row_count = (uint32_t)(nx * ny);
+    }
+    g.xface0 = c->xface0; g.xface1 = c->xface1;
     for (int i = 0; i < 6; ++i) { g.bc_type[i] = c->face[i].type; g.bc_psi_type[i] = c->bc_psi_type[i]; }
     g.two_phase = 1;
     CU2(c, cudaMalloc(&c->d_scalar, 16));
@@ -447,6 +473,7 @@ int lbm2p_init(lbm2p_ctx *c) {
 int lbm2p_step(lbm2p_ctx *c, int nsteps, void *cuda_stream) {
     CTX2(c);
     if (!c->inited) FAIL2(c, -4, "lbm2p_init has not been called");
+    if (c->halo) FAIL2(c, -4, "an x-slab context is stepped with lbm2p_run_slab (halo exchange inside)");
     if (nsteps < 0) FAIL2(c, -1, "nsteps < 0");
     if (nsteps == 0) return 0;
     CU2(c, cudaSetDevice(c->cfg.device));
@@ -476,6 +503,216 @@ int lbm2p_step(lbm2p_ctx *c, int nsteps, void *cuda_stream) {
     }
     c->macro_valid = false;
     c->F_valid = false;
+    return 0;
+}
+
+// ---- multi-GPU x-slabs -----------------------------------------------------------------------
+// A slab context (cfg.reserved & LBM2P_HALO_X) owns planes 1..nx-2; planes 0 and nx-1 mirror
+// the neighbours' boundary planes.  Two exchanges per step (include/lbm3d_2phase.h):
+//   stage 0, after the main pass:   5 face-crossing populations of f* + the colour records
+//   stage 1, after the colour pass: psi
+namespace {
+
+size_t halo_floats(const lbm2p_ctx *c, int stage) {
+    const size_t P = (size_t)c->cfg.ny * c->cfg.nz;
+    return stage == 0 ? 15 * P : P;
+}
+
+int pack2(lbm2p_ctx *c, int stage, int side, float *dst, cudaStream_t st) {
+    const size_t P = (size_t)c->cfg.ny * c->cfg.nz;
+    const int x = side == 0 ? 1 : c->cfg.nx - 2;               // boundary plane that is sent
+    const size_t off = (size_t)x * P;
+    if (stage == 1) {
+        CU2(c, cudaMemcpyAsync(dst, c->d_psi + off, P * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
+    static const HaloDirs kR = {{1, 7, 9, 11, 13}}, kL = {{2, 8, 10, 12, 14}};
+    Step2Args A;
+    fill2(c, A, c->d_f[c->cur], nullptr);
+    k_halo_pack<<<nblocks(P, 256), 256, 0, st>>>(A.a, (uint32_t)(x * c->cfg.ny), 0u, (uint32_t)P, side == 0 ? kL : kR, dst);
+    CU2(c, cudaGetLastError());
+    c->launches++;
+    CU2(c, cudaMemcpyAsync(dst + 5 * P, c->d_recA + off, P * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+    CU2(c, cudaMemcpyAsync(dst + 9 * P, c->d_recB + off, P * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+    CU2(c, cudaMemcpyAsync(dst + 11 * P, c->d_recC + off, P * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+int unpack2(lbm2p_ctx *c, int stage, int side, const float *src, cudaStream_t st) {
+    const size_t P = (size_t)c->cfg.ny * c->cfg.nz;
+    const int x = side == 0 ? 0 : c->cfg.nx - 1;               // ghost plane that is filled
+    const size_t off = (size_t)x * P;
+    if (stage == 1) {
+        CU2(c, cudaMemcpyAsync(c->d_psi + off, src, P * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
+    static const HaloDirs kR = {{1, 7, 9, 11, 13}}, kL = {{2, 8, 10, 12, 14}};
+    Step2Args A;
+    fill2(c, A, nullptr, c->d_f[c->cur]);
+    // the left ghost receives what the left neighbour sent to its right (e_x = +1) and v.v.
+    k_halo_unpack<<<nblocks(P, 256), 256, 0, st>>>(A.a, (uint32_t)(x * c->cfg.ny), 0u, (uint32_t)P, side == 0 ? kR : kL, src);
+    CU2(c, cudaGetLastError());
+    c->launches++;
+    CU2(c, cudaMemcpyAsync(c->d_recA + off, src + 5 * P, P * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+    CU2(c, cudaMemcpyAsync(c->d_recB + off, src + 9 * P, P * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+    CU2(c, cudaMemcpyAsync(c->d_recC + off, src + 11 * P, P * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+#define NC2(ctx, call)                                                                         \
+    do {                                                                                       \
+        int _r = (call);                                                                       \
+        if (_r != 0) FAIL2(ctx, -2, "%s failed: %s", #call, g_nccl.GetErrorString(_r));        \
+    } while (0)
+
+int exchange2(lbm2p_ctx *c, int stage, cudaStream_t st) {
+    int r = pack2(c, stage, 0, c->d_send[0], st);
+    if (r) return r;
+    r = pack2(c, stage, 1, c->d_send[1], st);
+    if (r) return r;
+    const float *from_left = c->d_send[1], *from_right = c->d_send[0];     // ring of one slab
+    if (c->comm_world > 1) {
+        const int left = (c->comm_rank + c->comm_world - 1) % c->comm_world;
+        const int right = (c->comm_rank + 1) % c->comm_world;
+        const size_t n = halo_floats(c, stage);
+        NC2(c, g_nccl.GroupStart());
+        // posting order matters when left == right (two ranks): pairs match in order
+        NC2(c, g_nccl.Send(c->d_send[1], n, 7, right, c->comm, st));
+        NC2(c, g_nccl.Send(c->d_send[0], n, 7, left, c->comm, st));
+        NC2(c, g_nccl.Recv(c->d_recv[0], n, 7, left, c->comm, st));
+        NC2(c, g_nccl.Recv(c->d_recv[1], n, 7, right, c->comm, st));
+        NC2(c, g_nccl.GroupEnd());
+        from_left = c->d_recv[0];
+        from_right = c->d_recv[1];
+    }
+    r = unpack2(c, stage, 0, from_left, st);
+    if (r) return r;
+    return unpack2(c, stage, 1, from_right, st);
+}
+
+// one stage of the slab step: 0 first collision (if the pipeline is empty), 1 colour, 2 main
+int stage2(lbm2p_ctx *c, int stage, cudaStream_t st) {
+    Step2Args A;
+    if (stage == 0) {
+        if (c->pipe_valid) return 1;
+        fill2(c, A, nullptr, c->d_f[c->cur]);
+        A.a.F = c->d_F;
+        int r = launch_main2(c, MODE_COLLIDE, A, st);
+        if (r) return r;
+        c->pipe_valid = true;
+        c->colour_valid = false;
+    } else if (stage == 1) {
+        if (!c->pipe_valid) FAIL2(c, -4, "pipeline not started");
+        if (c->colour_valid) return 1;
+        fill2(c, A, c->d_f[c->cur], nullptr);
+        int r = launch_colour2(c, A, st);
+        if (r) return r;
+        c->colour_valid = true;
+    } else {
+        if (!c->pipe_valid || !c->colour_valid) FAIL2(c, -4, "the colour pass of this step has not run");
+        fill2(c, A, c->d_f[c->cur], c->d_f[c->cur ^ 1]);
+        int r = launch_main2(c, MODE_STEP, A, st);
+        if (r) return r;
+        c->cur ^= 1;
+        c->colour_valid = false;
+    }
+    c->macro_valid = false;
+    c->F_valid = false;
+    return 0;
+}
+
+}  // namespace
+
+int64_t lbm2p_halo_floats(lbm2p_ctx *c, int stage) {
+    if (!c || !c->inited || !c->halo || stage < 0 || stage > 1) return -1;
+    return (int64_t)halo_floats(c, stage);
+}
+
+int lbm2p_halo_pack(lbm2p_ctx *c, int stage, int side, float *dst, void *cuda_stream) {
+    CTX2(c);
+    if (!c->inited || !c->halo) FAIL2(c, -4, "needs an initialised x-slab context");
+    if (!c->pipe_valid) FAIL2(c, -4, "no post-collision state yet (run stage 0 first)");
+    if (stage < 0 || stage > 1 || side < 0 || side > 1 || !dst) FAIL2(c, -1, "bad stage/side/destination");
+    CU2(c, cudaSetDevice(c->cfg.device));
+    return pack2(c, stage, side, dst, (cudaStream_t)cuda_stream);
+}
+
+int lbm2p_halo_unpack(lbm2p_ctx *c, int stage, int side, const float *src, void *cuda_stream) {
+    CTX2(c);
+    if (!c->inited || !c->halo) FAIL2(c, -4, "needs an initialised x-slab context");
+    if (stage < 0 || stage > 1 || side < 0 || side > 1 || !src) FAIL2(c, -1, "bad stage/side/source");
+    CU2(c, cudaSetDevice(c->cfg.device));
+    return unpack2(c, stage, side, src, (cudaStream_t)cuda_stream);
+}
+
+int lbm2p_slab_stage(lbm2p_ctx *c, int stage, void *cuda_stream) {
+    CTX2(c);
+    if (!c->inited || !c->halo) FAIL2(c, -4, "needs an initialised x-slab context");
+    if (stage < 0 || stage > 2) FAIL2(c, -1, "stage must be 0 (first collision), 1 (colour) or 2 (main)");
+    CU2(c, cudaSetDevice(c->cfg.device));
+    c->stream = (cudaStream_t)cuda_stream;
+    return stage2(c, stage, c->stream);
+}
+
+int lbm2p_comm_init(lbm2p_ctx *c, const void *id128, int world, int rank) {
+    CTX2(c);
+    if (!c->inited || !c->halo) FAIL2(c, -4, "needs an initialised x-slab context");
+    if (world < 1 || rank < 0 || rank >= world) FAIL2(c, -1, "bad world/rank");
+    CU2(c, cudaSetDevice(c->cfg.device));
+    if (world > 1) {
+        if (!id128) FAIL2(c, -1, "null NCCL id");
+        std::string err;
+        if (!load_nccl(err)) FAIL2(c, -2, "%s", err.c_str());
+        NcclId id;
+        memcpy(&id, id128, sizeof id);
+        NC2(c, g_nccl.CommInitRank(&c->comm, world, id, rank));
+    }
+    c->comm_world = world;
+    c->comm_rank = rank;
+    for (int i = 0; i < 2; ++i) {
+        if (!c->d_send[i]) CU2(c, cudaMalloc(&c->d_send[i], halo_floats(c, 0) * sizeof(float)));
+        if (!c->d_recv[i]) CU2(c, cudaMalloc(&c->d_recv[i], halo_floats(c, 0) * sizeof(float)));
+    }
+    c->comm_ready = true;
+    return 0;
+}
+
+int lbm2p_comm_unique_id(void *out128) {
+    std::string err;
+    if (!out128) return -1;
+    if (!load_nccl(err)) { g2_create_error = err; return -2; }
+    NcclId id;
+    if (g_nccl.GetUniqueId(&id) != 0) { g2_create_error = "ncclGetUniqueId failed"; return -2; }
+    memcpy(out128, &id, sizeof id);
+    return 0;
+}
+
+// nsteps iterations of the main loop :626-632 on one x-slab, halo exchanges inside
+int lbm2p_run_slab(lbm2p_ctx *c, int nsteps, void *cuda_stream) {
+    CTX2(c);
+    if (!c->inited || !c->halo) FAIL2(c, -4, "needs an initialised x-slab context");
+    if (!c->comm_ready) FAIL2(c, -4, "lbm2p_comm_init has not been called");
+    if (nsteps <= 0) return 0;
+    CU2(c, cudaSetDevice(c->cfg.device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    c->stream = st;
+    if (!c->pipe_valid) {
+        int r = stage2(c, 0, st);
+        if (r < 0) return r;
+        r = exchange2(c, 0, st);
+        if (r) return r;
+        nsteps -= 1;
+    }
+    for (int it = 0; it < nsteps; ++it) {
+        int r = stage2(c, 1, st);                  // rho_r, rho_b, psi of the step just collided
+        if (r < 0) return r;
+        r = exchange2(c, 1, st);                   // psi of the boundary planes -> neighbours' ghosts
+        if (r) return r;
+        r = stage2(c, 2, st);                      // stream/BC/macro + next collision
+        if (r < 0) return r;
+        r = exchange2(c, 0, st);                   // f* (5 + 5 populations) and colour records
+        if (r) return r;
+    }
     return 0;
 }
 

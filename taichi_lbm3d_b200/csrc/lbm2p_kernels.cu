@@ -195,6 +195,17 @@ __device__ __forceinline__ void collide2(float (&f)[19], const Step2Args &A, boo
 }
 #endif
 
+// Accumulators of the colour pass: one running sum per colour, every term weighted before it
+// is added, directions ascending (the oracle's order; the reference's float atomics have none).
+// (Summing unweighted per weight class and weighting once at the end saves 4 of 12 flops per
+// direction but no time -- the pass is bound by its 38 gathers per node -- and its different
+// rounding flips the |rho_r - rho_b| > 0.9 wetting switch (:271) at a few nodes of config 4.)
+struct ColourSum {
+    float r = 0.f, b = 0.f;                  // accumulators start at 0 (:596)
+    __device__ __forceinline__ float red() const { return r; }
+    __device__ __forceinline__ float blue() const { return b; }
+};
+
 // Contribution of one pull source to rho_r, rho_b: the recoloured g_r[s], g_b[s] (:345-363) of
 // the source node, re-evaluated from its colour record, for the direction sg*e_S (sg = -1:
 // the opposite direction LR[S], evaluated on the node's OWN record when the source is solid
@@ -204,10 +215,10 @@ __device__ __forceinline__ void collide2(float (&f)[19], const Step2Args &A, boo
 // bit-identically to the reference's pairwise update.
 template <int S, int EX, int EY, int EZ>
 __device__ __forceinline__ void colour_add(float sg, const float4 ra, const float2 rq, const float4 *__restrict__ pc,
-                                           float &rr, float &rb) {
+                                           ColourSum &acc) {
     const float eu = sg * edotu<EX, EY, EZ>(ra.z, ra.w, rq.x);
-    float gr, gb;
 #ifdef LBM_STRICT
+    float gr, gb;
     const float uv = ra.z * ra.z + ra.w * ra.w + rq.x * rq.x;
     const float T1 = 1.0f + 3.0f * eu + 4.5f * eu * eu - 1.5f * uv;        // feq :161-170
     gr = weight(S) * ra.x * T1;
@@ -225,11 +236,12 @@ __device__ __forceinline__ void colour_add(float sg, const float4 ra, const floa
         gr = gr + cs;
         gb = gb - cs;
     }
+    acc.r = acc.r + gr;
+    acc.b = acc.b + gb;
 #else
     // feq(s) = w rho t with t = q + eu (3 + 4.5 eu); the opposite direction has t - 6 eu
     const float t = fabsf(rq.y) + eu * (3.0f + 4.5f * eu);
-    gr = ra.x * t;
-    gb = ra.y * t;
+    float gr = ra.x * t, gb = ra.y * t;
     if (S > 0 && rq.y < 0.f) {                   // interface node; most nodes skip this
         const float4 rc = __ldg(pc);
         const float to = t - 6.0f * eu;
@@ -238,11 +250,9 @@ __device__ __forceinline__ void colour_add(float sg, const float4 ra, const floa
         gr = gr + cs;
         gb = gb - cs;
     }
-    gr *= weight(S);
-    gb *= weight(S);
+    acc.r = acc.r + gr * weight(S);
+    acc.b = acc.b + gb * weight(S);
 #endif
-    rr = rr + gr;
-    rb = rb + gb;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -269,22 +279,24 @@ __global__ void __launch_bounds__(256, LBM2P_COLOUR_MINB) k2p_colour(const Step2
     const float4 *__restrict__ pA = A.recA + idx;
     const float2 *__restrict__ pB = A.recB + idx;
     const float4 *__restrict__ pC = A.recC + idx;
-    float rr = 0.f, rb = 0.f;        // accumulators start at 0 (:596)
+    ColourSum acc;
     uint32_t fl = 0;
     if (cls == NODE_BULK) {
         // no solid link, no wrap: sources at uniform offsets
 #define X(s, ex, ey, ez, o)                                                                    \
     {                                                                                          \
         const int off = -((ex) * sx + (ey) * sy + (ez));                                       \
-        colour_add<s, ex, ey, ez>(1.0f, __ldg(pA + off), __ldg(pB + off), pC + off, rr, rb);   \
+        colour_add<s, ex, ey, ez>(1.0f, __ldg(pA + off), __ldg(pB + off), pC + off, acc);   \
     }
         D3Q19_DIRS(X)
 #undef X
     } else {
         fl = a.flags[idx];
+        // with ghost planes (x-slab) the x neighbours are always at -+sx: no periodic wrap
+        const uint32_t flw = a.halo_x ? fl & ~(FL_AT_X0 | FL_AT_X1) : fl;
         // node-linear offsets to x-1 / x+1 ... with the periodic wrap of periodic_index :377-387
-        const int oxm = (fl & FL_AT_X0) ? (a.nx - 1) * sx : -sx;
-        const int oxp = (fl & FL_AT_X1) ? -(a.nx - 1) * sx : sx;
+        const int oxm = (flw & FL_AT_X0) ? (a.nx - 1) * sx : -sx;
+        const int oxp = (flw & FL_AT_X1) ? -(a.nx - 1) * sx : sx;
         const int oym = (fl & FL_AT_Y0) ? (a.ny - 1) * sy : -sy;
         const int oyp = (fl & FL_AT_Y1) ? -(a.ny - 1) * sy : sy;
         const int ozm = (fl & FL_AT_Z0) ? (a.nz - 1) : -1;
@@ -296,12 +308,13 @@ __global__ void __launch_bounds__(256, LBM2P_COLOUR_MINB) k2p_colour(const Step2
     {                                                                                          \
         const bool bounce = (fl >> s) & 1u;                                                    \
         const int off = (s == 0 || bounce) ? 0 : OFF(ex, ey, ez);                              \
-        colour_add<s, ex, ey, ez>(bounce ? -1.0f : 1.0f, __ldg(pA + off), __ldg(pB + off), pC + off, rr, rb); \
+        colour_add<s, ex, ey, ez>(bounce ? -1.0f : 1.0f, __ldg(pA + off), __ldg(pB + off), pC + off, acc); \
     }
         D3Q19_DIRS(X)
 #undef X
 #undef OFF
     }
+    float rr = acc.red(), rb = acc.blue();
     float psi = rr - rb / (rr + rb);         // :605, precedence as written
     // Boundary_condition_psi :445-486, faces in order, the last matching face wins
     int win = -1;
@@ -321,131 +334,6 @@ __global__ void __launch_bounds__(256, LBM2P_COLOUR_MINB) k2p_colour(const Step2
     A.rho_r[idx] = rr;
     A.rho_b[idx] = rb;
     A.psi[idx] = psi;
-}
-
-// Colour pass, tiled: a block owns a (CT_Y x CT_Z) column of nodes and MARCHES along x.  The
-// records of the plane ahead (tile + one-node halo, periodic wrap applied by the loader) are
-// requested into registers while the current plane is evaluated, then parked in a 4-slot ring
-// in shared memory; the 19 record reads per node come from there.  Every record is read from
-// L2 1.33 times instead of 19 times through L1 (the gather version is bound by L1 tag/data
-// throughput: 26 sectors per node).  Same arithmetic, same ascending-s sum.
-#define CT_Z 32
-#define CT_Y 8
-#define CT_HALO ((CT_Y + 2) * (CT_Z + 2))
-__global__ void __launch_bounds__(CT_Y *CT_Z, 6) k2p_colour_tiled(const Step2Args A, int xseg) {
-    const StepArgs &a = A.a;
-    __shared__ float4 sA[4][CT_Y + 2][CT_Z + 2];
-    __shared__ float2 sB[4][CT_Y + 2][CT_Z + 2];
-    const int tz = threadIdx.x, ty = threadIdx.y, tid = ty * CT_Z + tz;
-    const int z0 = blockIdx.x * CT_Z, y0 = blockIdx.y * CT_Y;
-    const int xfirst = (int)(a.row_first / (uint32_t)a.ny);
-    const int xlast = xfirst + (int)(a.row_count / (uint32_t)a.ny);       // exclusive
-    const int xb = xfirst + (int)blockIdx.z * xseg;
-    const int xe = min(xlast, xb + xseg);
-    const int sx = a.ny * a.nz, sy = a.nz;
-    // loader slots: halo record l = tid and tid + 256 (CT_HALO = 340 <= 512)
-    int lrow[2], lhy[2], lhz[2];
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        const int l = tid + k * (CT_Y * CT_Z);
-        lhy[k] = l / (CT_Z + 2);
-        lhz[k] = l % (CT_Z + 2);
-        int gy = (y0 + lhy[k] - 1) % a.ny, gz = (z0 + lhz[k] - 1) % a.nz;
-        if (gy < 0) gy += a.ny;
-        if (gz < 0) gz += a.nz;
-        lrow[k] = l < CT_HALO ? gy * sy + gz : -1;
-    }
-    float4 ra[2];
-    float2 rq[2];
-    auto fetch = [&](int x) {
-        int gx = x % a.nx;
-        if (gx < 0) gx += a.nx;
-#pragma unroll
-        for (int k = 0; k < 2; ++k)
-            if (lrow[k] >= 0) {
-                const size_t e = (size_t)gx * sx + lrow[k];
-                ra[k] = __ldg(A.recA + e);
-                rq[k] = __ldg(A.recB + e);
-            }
-    };
-    auto park = [&](int x) {
-        const int slot = x & 3;
-#pragma unroll
-        for (int k = 0; k < 2; ++k)
-            if (lrow[k] >= 0) {
-                sA[slot][lhy[k]][lhz[k]] = ra[k];
-                sB[slot][lhy[k]][lhz[k]] = rq[k];
-            }
-    };
-    if (xb >= xe) return;
-    fetch(xb - 1); park(xb - 1);
-    fetch(xb); park(xb);
-    fetch(xb + 1);
-    const int y = y0 + ty, z = z0 + tz;
-    const bool inside = y < a.ny && z < a.nz;
-    for (int x = xb; x < xe; ++x) {
-        park(x + 1);
-        __syncthreads();
-        if (x + 1 < xe) fetch(x + 2);
-        if (!inside) continue;
-        const uint32_t idx = ((uint32_t)x * (uint32_t)a.ny + (uint32_t)y) * (uint32_t)a.nz + (uint32_t)z;
-        const uint8_t cls = a.cls[idx];
-        if (cls == NODE_SOLID || cls == NODE_SOLID_WRITE) continue;
-        const float4 *__restrict__ pC = A.recC + idx;
-        float rr = 0.f, rb = 0.f;        // accumulators start at 0 (:596)
-        uint32_t fl = 0;
-        // source of direction s: node (x-ex, y-ey, z-ez) -> ring slot (x-ex)&3, tile (ty+1-ey, tz+1-ez)
-#define REC_A(ex, ey, ez) sA[(x - (ex)) & 3][ty + 1 - (ey)][tz + 1 - (ez)]
-#define REC_B(ex, ey, ez) sB[(x - (ex)) & 3][ty + 1 - (ey)][tz + 1 - (ez)]
-        if (cls == NODE_BULK) {
-#define X(s, ex, ey, ez, o)                                                                    \
-    colour_add<s, ex, ey, ez>(1.0f, REC_A(ex, ey, ez), REC_B(ex, ey, ez), pC - ((ex) * sx + (ey) * sy + (ez)), rr, rb);
-            D3Q19_DIRS(X)
-#undef X
-        } else {
-            fl = a.flags[idx];
-            const int oxm = (fl & FL_AT_X0) ? (a.nx - 1) * sx : -sx;
-            const int oxp = (fl & FL_AT_X1) ? -(a.nx - 1) * sx : sx;
-            const int oym = (fl & FL_AT_Y0) ? (a.ny - 1) * sy : -sy;
-            const int oyp = (fl & FL_AT_Y1) ? -(a.ny - 1) * sy : sy;
-            const int ozm = (fl & FL_AT_Z0) ? (a.nz - 1) : -1;
-            const int ozp = (fl & FL_AT_Z1) ? -(a.nz - 1) : 1;
-#define OFF(ex, ey, ez)                                                                        \
-    ((ex > 0 ? oxm : (ex < 0 ? oxp : 0)) + (ey > 0 ? oym : (ey < 0 ? oyp : 0)) +               \
-     (ez > 0 ? ozm : (ez < 0 ? ozp : 0)))
-#define X(s, ex, ey, ez, o)                                                                    \
-    {                                                                                          \
-        const bool bounce = (fl >> s) & 1u;                                                    \
-        const float4 qa = bounce ? REC_A(0, 0, 0) : REC_A(ex, ey, ez);                         \
-        const float2 qb = bounce ? REC_B(0, 0, 0) : REC_B(ex, ey, ez);                         \
-        colour_add<s, ex, ey, ez>(bounce ? -1.0f : 1.0f, qa, qb, pC + ((s == 0 || bounce) ? 0 : OFF(ex, ey, ez)), rr, rb); \
-    }
-            D3Q19_DIRS(X)
-#undef X
-#undef OFF
-        }
-#undef REC_A
-#undef REC_B
-        float psi = rr - rb / (rr + rb);         // :605, precedence as written
-        // Boundary_condition_psi :445-486, faces in order, the last matching face wins
-        int win = -1;
-        if (fl & (FL_AT_X0 | FL_AT_X1 | FL_AT_Y0 | FL_AT_Y1 | FL_AT_Z0 | FL_AT_Z1)) {
-            if ((fl & FL_AT_X0) && A.bc_psi_type[0] == 1) win = 0;
-            if ((fl & FL_AT_X1) && A.bc_psi_type[1] == 1) win = 1;
-            if ((fl & FL_AT_Y0) && A.bc_psi_type[2] == 1) win = 2;
-            if ((fl & FL_AT_Y1) && A.bc_psi_type[3] == 1) win = 3;
-            if ((fl & FL_AT_Z0) && A.bc_psi_type[4] == 1) win = 4;
-            if ((fl & FL_AT_Z1) && A.bc_psi_type[5] == 1) win = 5;
-        }
-        if (win >= 0) {
-            psi = A.bc_psi_val[win];
-            rr = (psi + 1.0f) / 2.0f;
-            rb = 1.0f - rr;
-        }
-        A.rho_r[idx] = rr;
-        A.rho_b[idx] = rb;
-        A.psi[idx] = psi;
-    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -507,9 +395,11 @@ __global__ void __launch_bounds__(256, LBM2P_MAIN_MINB) k2p_main(const Step2Args
         if (MODE == MODE_EXTRACT && !compute) return;
         if (cls == NODE_SPECIAL) {
             fl = a.flags[idx];
+            // with ghost planes (x-slab) the x neighbours are always at -+sx: no periodic wrap
+            const uint32_t flw = a.halo_x ? fl & ~(FL_AT_X0 | FL_AT_X1) : fl;
             const int sx = a.ny * (int)a.prow, sy = (int)a.prow;
-            const int oxm = (fl & FL_AT_X0) ? (a.nx - 1) * sx : -sx;
-            const int oxp = (fl & FL_AT_X1) ? -(a.nx - 1) * sx : sx;
+            const int oxm = (flw & FL_AT_X0) ? (a.nx - 1) * sx : -sx;
+            const int oxp = (flw & FL_AT_X1) ? -(a.nx - 1) * sx : sx;
             const int oym = (fl & FL_AT_Y0) ? (a.ny - 1) * sy : -sy;
             const int oyp = (fl & FL_AT_Y1) ? -(a.ny - 1) * sy : sy;
             const int ozm = (fl & FL_AT_Z0) ? (a.nz - 1) : -1;
@@ -518,7 +408,7 @@ __global__ void __launch_bounds__(256, LBM2P_MAIN_MINB) k2p_main(const Step2Args
     ((ex > 0 ? oxm : (ex < 0 ? oxp : 0)) + (ey > 0 ? oym : (ey < 0 ? oyp : 0)) +               \
      (ez > 0 ? ozm : (ez < 0 ? ozp : 0)))
 #define WRAPS(ex, ey, ez)                                                                      \
-    (fl & ((ex > 0 ? FL_AT_X0 : (ex < 0 ? FL_AT_X1 : 0u)) | (ey > 0 ? FL_AT_Y0 : (ey < 0 ? FL_AT_Y1 : 0u)) | \
+    (flw & ((ex > 0 ? FL_AT_X0 : (ex < 0 ? FL_AT_X1 : 0u)) | (ey > 0 ? FL_AT_Y0 : (ey < 0 ? FL_AT_Y1 : 0u)) | \
            (ez > 0 ? FL_AT_Z0 : (ez < 0 ? FL_AT_Z1 : 0u))))
 #define X(s, ex, ey, ez, o)                                                                    \
     if (s > 0) {                                                                               \
@@ -585,8 +475,8 @@ __global__ void __launch_bounds__(256, LBM2P_MAIN_MINB) k2p_main(const Step2Args
         const int sx = a.ny * a.nz, sy = a.nz;
         int oxm = -sx, oxp = sx, oym = -sy, oyp = sy, ozm = -1, ozp = 1;
         if (fl & (FL_AT_X0 | FL_AT_X1 | FL_AT_Y0 | FL_AT_Y1 | FL_AT_Z0 | FL_AT_Z1)) {
-            if (fl & FL_AT_X0) oxm = A.bc_psi_type[0] == 0 ? (a.nx - 1) * sx : 0;
-            if (fl & FL_AT_X1) oxp = A.bc_psi_type[1] == 0 ? -(a.nx - 1) * sx : 0;
+            if (fl & FL_AT_X0) oxm = A.bc_psi_type[0] == 0 ? (a.halo_x ? -sx : (a.nx - 1) * sx) : 0;
+            if (fl & FL_AT_X1) oxp = A.bc_psi_type[1] == 0 ? (a.halo_x ? sx : -(a.nx - 1) * sx) : 0;
             if (fl & FL_AT_Y0) oym = A.bc_psi_type[2] == 0 ? (a.ny - 1) * sy : 0;
             if (fl & FL_AT_Y1) oyp = A.bc_psi_type[3] == 0 ? -(a.ny - 1) * sy : 0;
             if (fl & FL_AT_Z0) ozm = A.bc_psi_type[4] == 0 ? (a.nz - 1) : 0;
@@ -665,28 +555,11 @@ cudaError_t launch_main(int mode, const Step2Args &A, int block, cudaStream_t st
 cudaError_t launch_colour(const Step2Args &A, int block, cudaStream_t st) {
     if (A.a.row_count == 0) return cudaSuccess;
     dim3 grid, blk;
-    static int tiled = -1, zmax = 0, xseg_env = 0;
-    if (tiled < 0) {
-        const char *t = getenv("LBM3D_COLOUR_TILED");    // tuning knobs
-        tiled = t ? atoi(t) : 1;
-        const char *e = getenv("LBM3D_COLOUR_BX");
+    static int zmax = 0;
+    if (zmax == 0) {
+        const char *e = getenv("LBM3D_COLOUR_BX");       // tuning knob
         zmax = e ? atoi(e) : 32;
         if (zmax < 32 || zmax > 256 || zmax % 32) zmax = 32;
-        const char *xs = getenv("LBM3D_COLOUR_XSEG");
-        xseg_env = xs ? atoi(xs) : 0;
-    }
-    if (tiled && A.a.row_first % (uint32_t)A.a.ny == 0 && A.a.row_count % (uint32_t)A.a.ny == 0) {
-        const int planes = (int)(A.a.row_count / (uint32_t)A.a.ny);
-        const unsigned tiles = (unsigned)((A.a.nz + CT_Z - 1) / CT_Z) * (unsigned)((A.a.ny + CT_Y - 1) / CT_Y);
-        // march long enough to amortise the two-plane prologue, but keep >= ~4 waves of blocks
-        int xseg = xseg_env > 0 ? xseg_env : 32;
-        while (xseg > 8 && (unsigned long long)tiles * ((planes + xseg - 1) / xseg) < 148ull * 6 * 4) xseg /= 2;
-        if (xseg > planes) xseg = planes;
-        dim3 g((A.a.nz + CT_Z - 1) / CT_Z, (A.a.ny + CT_Y - 1) / CT_Y, (planes + xseg - 1) / xseg);
-        if (g.y <= 65535u && g.z <= 65535u) {
-            k2p_colour_tiled<<<g, dim3(CT_Z, CT_Y, 1), 0, st>>>(A, xseg);
-            return cudaGetLastError();
-        }
     }
     geometry(A.a, block, grid, blk, zmax);
     k2p_colour<<<grid, blk, 0, st>>>(A);

@@ -4,8 +4,6 @@
 // pipeline state (post-collision f*), getters/setters, halo staging.
 //
 // Reference: Single_phase/LBM_3D_SinglePhase_Solver.py (line numbers below).
-#include <dlfcn.h>
-
 #include <cub/cub.cuh>
 #include <thrust/iterator/transform_iterator.h>
 #include <cuda_runtime.h>
@@ -19,6 +17,7 @@
 #include "../../include/lbm3d.h"
 #include "lbm_kernels.cuh"
 #include "lbm_geometry.cuh"
+#include "lbm_nccl.cuh"
 
 namespace {
 
@@ -270,28 +269,6 @@ __global__ void k_decode_table(StepArgs a, uint32_t nf, int32_t *__restrict__ ou
 #undef X
 }
 
-// halo staging: 5 populations of one lattice plane <-> contiguous buffer [5][count]
-struct HaloDirs { int s[5]; };
-// generic over both storage modes: node i of the plane lives at  plane_s + (row0 + i/nz)*prow + i%nz
-// (dense; SoA has prow = nz) or at  plane_s + first + i  (sparse: nz = 0)
-__global__ void k_halo_pack(StepArgs a, uint32_t row0, uint32_t first, uint32_t count, HaloDirs d,
-                            float *__restrict__ dst) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    const uint32_t e = a.nz ? (row0 + i / (uint32_t)a.nz) * a.prow + i % (uint32_t)a.nz : first + i;
-#pragma unroll
-    for (int q = 0; q < 5; ++q) dst[(size_t)q * count + i] = a.pown[d.s[q]][e];
-}
-__global__ void k_halo_unpack(StepArgs a, uint32_t row0, uint32_t first, uint32_t count, HaloDirs d,
-                              const float *__restrict__ src) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    const uint32_t e = a.nz ? (row0 + i / (uint32_t)a.nz) * a.prow + i % (uint32_t)a.nz : first + i;
-#pragma unroll
-    for (int q = 0; q < 5; ++q) a.pout[d.s[q]][e] = src[(size_t)q * count + i];
-}
-
-
 void default_relaxation(double niu, int textbook, float S[19]) {
     // init_simulation :126-131, same double arithmetic as the Python source
     const double tau_f = textbook ? 3.0 * niu + 0.5 : niu / 3.0 + 0.5;
@@ -324,6 +301,7 @@ void fill_args(const lbm_ctx *c, StepArgs &a) {
     a.prow = c->prow;
     a.spec = c->spec;
     a.nx = c->cfg.nx; a.ny = c->cfg.ny; a.nz = c->cfg.nz;
+    a.halo_x = c->cfg.halo_x ? 1 : 0;
     a.flags = c->d_flags;
     a.cls = c->d_cls;
     for (int s = 0; s < 18; ++s) {
@@ -418,48 +396,6 @@ int copy_out(lbm_ctx *c, void *dst, const void *src, size_t bytes) {
     CU(c, cudaStreamSynchronize(c->stream));
     CU(c, cudaMemcpy(dst, src, bytes, cudaMemcpyDefault));
     return LBM_OK;
-}
-
-// ---- NCCL, bound at run time from the library torch has already loaded -----------------------
-// (prototypes from nccl.h 2.28: ncclUniqueId is 128 bytes, ncclFloat = 7, ncclSuccess = 0)
-struct NcclId { char internal[128]; };
-struct NcclApi {
-    void *h = nullptr;
-    int (*GetUniqueId)(NcclId *) = nullptr;
-    int (*CommInitRank)(void **, int, NcclId, int) = nullptr;
-    int (*CommDestroy)(void *) = nullptr;
-    int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
-    int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
-    int (*GroupStart)() = nullptr;
-    int (*GroupEnd)() = nullptr;
-    const char *(*GetErrorString)(int) = nullptr;
-    bool ok = false;
-};
-NcclApi g_nccl;
-
-bool load_nccl(std::string &err) {
-    if (g_nccl.ok) return true;
-    const char *names[] = {getenv("LBM3D_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
-    for (const char *n : names) {
-        if (!n) continue;
-        g_nccl.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
-        if (g_nccl.h) break;
-    }
-    if (!g_nccl.h) { err = std::string("cannot load NCCL: ") + dlerror(); return false; }
-#define BIND(field, sym)                                                                       \
-    *(void **)(&g_nccl.field) = dlsym(g_nccl.h, sym);                                          \
-    if (!g_nccl.field) { err = std::string("NCCL symbol missing: ") + sym; return false; }
-    BIND(GetUniqueId, "ncclGetUniqueId")
-    BIND(CommInitRank, "ncclCommInitRank")
-    BIND(CommDestroy, "ncclCommDestroy")
-    BIND(Send, "ncclSend")
-    BIND(Recv, "ncclRecv")
-    BIND(GroupStart, "ncclGroupStart")
-    BIND(GroupEnd, "ncclGroupEnd")
-    BIND(GetErrorString, "ncclGetErrorString")
-#undef BIND
-    g_nccl.ok = true;
-    return true;
 }
 
 #define NC(ctx, call)                                                                          \

@@ -102,6 +102,11 @@ __global__ void k_build_flags(const GeoParams g, const int8_t *__restrict__ soli
     if (!g.halo_x) {
         if (x == 0) fl |= FL_AT_X0;
         if (x == g.nx - 1) fl |= FL_AT_X1;
+    } else if (g.two_phase) {
+        // x-slab of the two-phase solver: the at-face bits mark the GLOBAL x faces (velocity and
+        // psi BCs, clamped psi stencil); the kernels never wrap x when ghost planes exist
+        if (x == g.xface0) fl |= FL_AT_X0;
+        if (x == g.xface1) fl |= FL_AT_X1;
     }
     if (y == 0) fl |= FL_AT_Y0;
     if (y == g.ny - 1) fl |= FL_AT_Y1;
@@ -115,9 +120,15 @@ __global__ void k_build_flags(const GeoParams g, const int8_t *__restrict__ soli
         bool near = false;
         for (int s = 1; s < 19; ++s) {
             int q[3] = {x + c_e[s][0], y + c_e[s][1], z + c_e[s][2]};
-            for (int d = 0; d < 3; ++d) {
+            for (int d = g.halo_x ? 1 : 0; d < 3; ++d) {
                 if (q[d] < 0) q[d] = g.bc_psi_type[2 * d] == 0 ? n[d] - 1 : 0;
                 if (q[d] > n[d] - 1) q[d] = g.bc_psi_type[2 * d + 1] == 0 ? 0 : n[d] - 1;
+            }
+            if (g.halo_x) {
+                // ghost planes carry the periodic images; a constant-psi GLOBAL face clamps
+                if (x == g.xface0 && q[0] < x && g.bc_psi_type[0] != 0) q[0] = x;
+                if (x == g.xface1 && q[0] > x && g.bc_psi_type[1] != 0) q[0] = x;
+                if (q[0] < 0 || q[0] > g.nx - 1) continue;      // ghost node itself: never updated
             }
             if (solid[((size_t)q[0] * g.ny + q[1]) * g.nz + q[2]] != 0) near = true;
         }
@@ -160,6 +171,27 @@ __global__ void k_max_v(const float *__restrict__ v, size_t n, float *out) {
 }
 
 inline unsigned nblocks(size_t n, int b) { return (unsigned)((n + b - 1) / b); }
+
+// halo staging: 5 populations of one lattice plane <-> contiguous buffer [5][count]
+struct HaloDirs { int s[5]; };
+// generic over both storage modes: node i of the plane lives at  plane_s + (row0 + i/nz)*prow + i%nz
+// (dense; SoA has prow = nz) or at  plane_s + first + i  (sparse: nz = 0)
+__global__ void k_halo_pack(StepArgs a, uint32_t row0, uint32_t first, uint32_t count, HaloDirs d,
+                            float *__restrict__ dst) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint32_t e = a.nz ? (row0 + i / (uint32_t)a.nz) * a.prow + i % (uint32_t)a.nz : first + i;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) dst[(size_t)q * count + i] = a.pown[d.s[q]][e];
+}
+__global__ void k_halo_unpack(StepArgs a, uint32_t row0, uint32_t first, uint32_t count, HaloDirs d,
+                              const float *__restrict__ src) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint32_t e = a.nz ? (row0 + i / (uint32_t)a.nz) * a.prow + i % (uint32_t)a.nz : first + i;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) a.pout[d.s[q]][e] = src[(size_t)q * count + i];
+}
 
 // exact inverse of M (:64-83) as rationals; every non-zero entry rounds to the same f32 as
 // np.linalg.inv's (tests/test_abi_cpu.py); LAPACK's 1e-17 noise entries are exactly 0 here.

@@ -49,6 +49,7 @@ struct StepArgs {
     uint32_t row_first, row_count, prow;
     int spec;                       // 1: speculative pull (few solid nodes)
     int nx, ny, nz;                 // extents of this context's lattice (incl. ghost planes)
+    int halo_x;                     // 1: planes 0 and nx-1 are ghost planes, x never wraps
     // dense: link word per node.  sparse: BC word per stored node (bits 20..23), may be null
     const uint32_t *flags;
     // dense: node class byte (NODE_BULK / NODE_SOLID / NODE_SPECIAL); only NODE_SPECIAL nodes

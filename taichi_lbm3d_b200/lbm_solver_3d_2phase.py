@@ -102,6 +102,10 @@ class LB3D_Solver_Two_Phase:
             np.reshape(ph, (self.nx, self.ny, self.nz), order='F').astype(np.float32))
         return self._solid_host, self._psi_host
 
+    def _config_flags(self):
+        """lbm2p_config.reserved: 0 for a whole lattice (x-slabs override this, multi_gpu.py)"""
+        return 0
+
     # ---- static_init + init :205-228, :173-186 -----------------------------------------------------
     def init_simulation(self):
         import torch
@@ -112,7 +116,8 @@ class LB3D_Solver_Two_Phase:
             lib.lbm2p_destroy(self._ctx)
             self._ctx = None
         dev = torch.cuda.current_device() if self.device is None else torch.device(self.device).index or 0
-        cfg = _lib.Lbm2pConfig(nx=self.nx, ny=self.ny, nz=self.nz, strict=int(self.strict), device=int(dev), reserved=0)
+        cfg = _lib.Lbm2pConfig(nx=self.nx, ny=self.ny, nz=self.nz, strict=int(self.strict), device=int(dev),
+                               reserved=int(self._config_flags()))
         ctx = ctypes.c_void_p()
         st = lib.lbm2p_create(ctypes.byref(cfg), ctypes.byref(ctx))
         if st < 0:

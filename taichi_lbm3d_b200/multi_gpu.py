@@ -300,3 +300,148 @@ class SlabSolver:
         if self.part.rank != dst:
             return None
         return np.concatenate(parts, axis=0)
+
+
+# ---------------------------------------------------------------------------------------------
+# two-phase colour-gradient solver over x-slabs
+# ---------------------------------------------------------------------------------------------
+def _two_phase_slab_class():
+    from .lbm_solver_3d_2phase import LB3D_Solver_Two_Phase
+
+    class _Slab(LB3D_Solver_Two_Phase):
+        def __init__(self, part, ny, nz, **kw):
+            super().__init__(part.local_nx, ny, nz, **kw)
+            self._part = part
+
+        def _config_flags(self):
+            m = self._part.x_face_mask
+            return 1 | (2 if m & 1 else 0) | (4 if m & 2 else 0)       # LBM2P_HALO_X | HOLDS_X0 | HOLDS_X1
+
+    return _Slab
+
+
+class TwoPhaseSlabSolver:
+    """Two-phase colour-gradient solver over `world_size` GPUs (x-slabs).  The attributes of
+    LB3D_Solver_Two_Phase (niu_l, CapA, bc_psi_x_left, ...) are set on ``.local``; geometry and
+    phase field are given globally (set_fields) or per slab (set_local_fields).
+
+    Per step and cut (include/lbm3d_2phase.h): after the colour pass psi of the boundary plane
+    (4 B per face node), after the main pass the 5 crossing populations and the 24(+16)-byte
+    colour record (60 B per face node).  transport="native": ncclSend/ncclRecv inside the C
+    library (lbm2p_run_slab); "torch": the same schedule over torch.distributed P2P ops."""
+
+    def __init__(self, nx, ny, nz, strict=False, transport="native"):
+        if transport not in ("native", "torch"):
+            raise ValueError("transport must be 'native' or 'torch'")
+        import torch
+        import torch.distributed as dist
+        self.torch, self.transport = torch, transport
+        self.dist = dist if (dist.is_available() and dist.is_initialized()) else None
+        world = self.dist.get_world_size() if self.dist else 1
+        rank = self.dist.get_rank() if self.dist else 0
+        self.nx, self.ny, self.nz = nx, ny, nz
+        self.part = SlabPartition(nx, world, rank)
+        self.local = _two_phase_slab_class()(self.part, ny, nz, strict=strict)
+        self._started = False
+
+    # ---- setup -------------------------------------------------------------------------------
+    def set_fields(self, global_solid, global_psi):
+        self.local.solid.from_numpy(self.part.local_solid(global_solid))
+        psi = np.asarray(global_psi, np.float32)
+        self.local.psi.from_numpy(np.ascontiguousarray(np.take(psi, self.part.local_planes(), axis=0)))
+
+    def set_local_fields(self, local_solid_with_ghosts, local_psi_with_ghosts):
+        self.local.solid.from_numpy(local_solid_with_ghosts)
+        self.local.psi.from_numpy(local_psi_with_ghosts)
+
+    def init_simulation(self):
+        loc = self.local
+        loc.init_simulation()
+        lib, ctx = loc._lib, loc._ctx
+        self._started = False
+        dev = self.torch.device("cuda", self.torch.cuda.current_device())
+        n0 = int(lib.lbm2p_halo_floats(ctx, 0))
+        self._send = [self.torch.empty(n0, dtype=self.torch.float32, device=dev) for _ in range(2)]
+        self._recv = [self.torch.empty(n0, dtype=self.torch.float32, device=dev) for _ in range(2)]
+        self._count = [n0, int(lib.lbm2p_halo_floats(ctx, 1))]
+        if self.transport == "native":
+            ident = (ctypes.c_char * 128)()
+            if self.part.world > 1:
+                if self.dist.get_backend() != "nccl":
+                    raise _lib.LbmError("transport='native' needs the nccl process group")
+                box = [None]
+                if self.part.rank == 0:
+                    loc._ck(lib.lbm2p_comm_unique_id(ident), "lbm2p_comm_unique_id")
+                    box[0] = bytes(ident.raw)
+                self.dist.broadcast_object_list(box, src=0)
+                ident.raw = box[0]
+            loc._ck(lib.lbm2p_comm_init(ctx, ident, self.part.world, self.part.rank), "lbm2p_comm_init")
+
+    # ---- stepping ------------------------------------------------------------------------------
+    def _stream(self):
+        return ctypes.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+
+    def _stage(self, stage):
+        loc = self.local
+        return loc._ck(loc._lib.lbm2p_slab_stage(loc._ctx, stage, self._stream()), "lbm2p_slab_stage")
+
+    def _exchange(self, stage):
+        loc, p = self.local, self.part
+        lib, ctx, n = loc._lib, loc._ctx, self._count[stage]
+        for side in (0, 1):
+            loc._ck(lib.lbm2p_halo_pack(ctx, stage, side, ctypes.c_void_p(self._send[side].data_ptr()),
+                                        self._stream()), "lbm2p_halo_pack")
+        if p.world == 1 or self.dist is None:
+            src = [self._send[1], self._send[0]]          # ring of one slab
+        else:
+            dist = self.dist
+            ops = [dist.P2POp(dist.isend, self._send[1][:n], p.right), dist.P2POp(dist.isend, self._send[0][:n], p.left),
+                   dist.P2POp(dist.irecv, self._recv[0][:n], p.left), dist.P2POp(dist.irecv, self._recv[1][:n], p.right)]
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+            src = self._recv
+        for side in (0, 1):
+            loc._ck(lib.lbm2p_halo_unpack(ctx, stage, side, ctypes.c_void_p(src[side].data_ptr()), self._stream()),
+                    "lbm2p_halo_unpack")
+
+    def step(self):
+        self.run(1)
+
+    def run(self, nsteps):
+        n = int(nsteps)
+        if n <= 0:
+            return
+        loc = self.local
+        if self.transport == "native":
+            loc._ck(loc._lib.lbm2p_run_slab(loc._ctx, n, self._stream()), "lbm2p_run_slab")
+            self._started = True
+            return
+        if not self._started:
+            self._stage(0)
+            self._exchange(0)
+            self._started = True
+            n -= 1
+        for _ in range(n):
+            self._stage(1)
+            self._exchange(1)
+            self._stage(2)
+            self._exchange(0)
+
+    # ---- results ---------------------------------------------------------------------------------
+    @property
+    def launch_count(self):
+        return self.local.launch_count
+
+    def local_field(self, name):
+        """owned planes of rho / v / F / psi / rho_r / rho_b / solid on this rank"""
+        return self.part.owned(getattr(self.local, name).to_numpy())
+
+    def gather_field(self, name, dst=0):
+        loc = self.local_field(name)
+        if not self.dist:
+            return loc
+        parts = [None] * self.part.world if self.part.rank == dst else None
+        self.dist.gather_object(loc, parts, dst=dst)
+        if self.part.rank != dst:
+            return None
+        return np.concatenate(parts, axis=0)
