@@ -299,7 +299,7 @@ def main():
            "h2d_bytes_per_step": h2d * n_gpus / args.steps,
            "d2h_bytes_per_step": (rho_h.nbytes + v_h.nbytes + 4) * n_gpus / args.steps,
            "job": "geometry upload + init_simulation + %d x step() + rho, v, max_v to host%s"
-                  % (args.steps, "" if world == 1 else " (every rank its slab)"),
+                  % (args.steps, "" if world == 1 else " (every rank its slab; includes creating the NCCL communicator)"),
            "seconds": dt, "max_v": mv}
     del lb2
 

@@ -275,10 +275,10 @@ class SlabSolver:
         return self.local.launch_count
 
     def get_max_v(self):
-        loc = self.local
-        # ghost planes hold v = 0 / stale values; reduce over owned planes only
-        v = loc.v.to_numpy()[1:-1]
-        m = float(np.sqrt((v.astype(np.float32) ** 2).sum(-1, dtype=np.float32)).max()) if v.size else -1e10
+        """max |v| over the whole domain (cal_max_v :399-402): device reduction per slab, then
+        MAX over the ranks.  Ghost planes are never written by a step and hold v = 0 from
+        init_simulation, so the reduction may run over the whole local lattice."""
+        m = self.local.get_max_v()
         if self.dist:
             t = self.torch.tensor([m], dtype=self.torch.float32,
                                   device="cuda" if self.dist.get_backend() == "nccl" else "cpu")
