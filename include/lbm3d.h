@@ -83,6 +83,12 @@ int lbm_set_geometry(lbm_ctx *ctx, const int8_t *solid_host_or_dev);
 int lbm_set_bc(lbm_ctx *ctx, int face, int type, float rho, const float vel[3]);
 /* set_force (:457); force_flag as :137-140 */
 int lbm_set_force(lbm_ctx *ctx, const float force[3]);
+/* per-node force [nx][ny][nz][3] (host or device; copied): the array form of the reference's
+ * override point cal_local_force(i,j,k) (:217-220, overridden by
+ * Phase_change/LBM_3D_SinglePhase_Solute_Solver.py:185-190 to add buoyancy).  Used by the
+ * collision (:230-238) and by the velocity shift of streaming3 (:388) in place of the uniform
+ * force; after lbm_init, may be replaced between steps; NULL returns to lbm_set_force. */
+int lbm_set_force_field(lbm_ctx *ctx, const float *force3_host_or_dev);
 /* set_viscosity + the relaxation rates of init_simulation (:126-131), evaluated in
  * double exactly as the Python source does, rounded once to fp32.
  * textbook_tau = 0: tau = niu/3 + 0.5 (the class, :127); 1: tau = 3 niu + 0.5 (:126,

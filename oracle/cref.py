@@ -42,7 +42,8 @@ def _params_struct(ctype):
         _fields_ = [("nx", ctypes.c_int), ("ny", ctypes.c_int), ("nz", ctypes.c_int),
                     ("force_flag", ctypes.c_int), ("bc_type", ctypes.c_int * 6),
                     ("S", ctype * 19), ("invM", ctype * 361), ("w", ctype * 19),
-                    ("force", ctype * 3), ("bc_rho", ctype * 6), ("bc_vel", (ctype * 3) * 6)]
+                    ("force", ctype * 3), ("bc_rho", ctype * 6), ("bc_vel", (ctype * 3) * 6),
+                    ("force_field", ctypes.c_void_p)]
     return P
 
 
@@ -91,7 +92,15 @@ class RefSinglePhaseC(_np_ref.RefSinglePhase):
             p.invM[i] = flat[i]
         for c in range(3):
             p.force[c] = self.ext_f[c]
+        ff = getattr(self, "force_field", None)
+        p.force_field = None if ff is None else ff.ctypes.data
         self._p = p
+
+    def set_force_field(self, force):
+        super().set_force_field(force)
+        if getattr(self, "_p", None) is not None:
+            self._p.force_field = None if self.force_field is None else self.force_field.ctypes.data
+            self._p.force_flag = 1 if self.force_field is not None else self.force_flag
 
     def colission(self):
         self._fn("ref_sp_colission")(ctypes.byref(self._p), self._ptr(self.solid), self._ptr(self.F),

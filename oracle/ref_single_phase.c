@@ -68,6 +68,7 @@ typedef struct {
     REAL force[3];           /* :134-136 */
     REAL bc_rho[6];
     REAL bc_vel[6][3];
+    const REAL *force_field; /* [n][3] per-node force = cal_local_force(i,j,k) :217-220, or NULL */
 } FN(ref_params);
 typedef FN(ref_params) params_t;
 
@@ -107,7 +108,7 @@ void FN(ref_sp_colission)(const params_t *p, const int8_t *solid, const REAL *F,
         meq[13] = u[0] * u[1]; meq[14] = u[1] * u[2]; meq[15] = u[0] * u[2];
         for (int s = 0; s < 19; ++s) m[s] = m[s] - p->S[s] * (m[s] - meq[s]);   /* :228 */
         if (p->force_flag == 1) {                            /* :230-238 */
-            const REAL *fo = p->force;
+            const REAL *fo = p->force_field ? p->force_field + c * 3 : p->force;      /* :231 */
             for (int s = 0; s < 19; ++s) {
                 REAL f_guo = R(0);
                 for (int l = 0; l < 19; ++l) {
@@ -196,9 +197,10 @@ void FN(ref_sp_streaming3)(const params_t *p, const int8_t *solid, const REAL *F
             for (int s = 0; s < 19; ++s)
                 for (int d = 0; d < 3; ++d)
                     if (Ei[s][d] != 0) u[d] = u[d] + R(Ei[s][d]) * F[c * 19 + s];
+            const REAL *fo = p->force_field ? p->force_field + c * 3 : p->force;      /* :385 */
             for (int d = 0; d < 3; ++d) {
                 u[d] = u[d] / r;
-                u[d] = u[d] + (p->force[d] / R(2)) / r;
+                u[d] = u[d] + (fo[d] / R(2)) / r;
             }
             rho[c] = r;
             v[c * 3 + 0] = u[0]; v[c * 3 + 1] = u[1]; v[c * 3 + 2] = u[2];

@@ -97,6 +97,7 @@ class RefSinglePhase:
         self.tau_mode = tau_mode
         # :17-18
         self.fx, self.fy, self.fz = 0.0e-6, 0.0, 0.0
+        self.force_field = None             # array form of an overridden cal_local_force
         self.niu = 0.16667
         # :23-28   [type, rho, vx, vy, vz] per face, order x0,x1,y0,y1,z0,z1
         self.bc_type = [0] * 6
@@ -138,12 +139,24 @@ class RefSinglePhase:
     def set_force(self, force):           # :457
         self.fx, self.fy, self.fz = force[0], force[1], force[2]
 
+    def set_force_field(self, force):
+        """what a subclass overriding cal_local_force(i,j,k) (:217-220) returns, as an array
+        (nx,ny,nz,3); None = the uniform force"""
+        self.force_field = None if force is None else np.ascontiguousarray(np.asarray(force).astype(self.dtype))
+
+    def cal_local_force(self, fl):
+        """:217-220 for every fluid node: (n,3) or the uniform (1,3)"""
+        if getattr(self, "force_field", None) is not None:
+            return self.force_field[fl]
+        return self.ext_f[None, :]
+
     def init_simulation(self):
         """:118-149 then init() :160-170 (dense branch: every node)."""
         dt = self.dtype
         self.S = relaxation_rates(self.niu, self.tau_mode).astype(dt)   # :127-131
         self.ext_f = np.array([self.fx, self.fy, self.fz]).astype(dt)   # :134-136
-        self.force_flag = int(abs(self.fx) > 0 or abs(self.fy) > 0 or abs(self.fz) > 0)
+        self.force_flag = int(abs(self.fx) > 0 or abs(self.fy) > 0 or abs(self.fz) > 0
+                              or getattr(self, "force_field", None) is not None)
         self.rho[...] = 1.0
         self.v[...] = 0.0
         for s in range(19):
@@ -200,16 +213,16 @@ class RefSinglePhase:
         meq = self._meq(rho, v)                                # :227
         m = m - self.S[None, :] * (m - meq)                    # :228
         if self.force_flag == 1:                               # :230-238
-            f = self.ext_f
+            f = self.cal_local_force(fl)                       # :231
             for s in range(19):
                 f_guo = np.zeros(Fn.shape[0], self.dtype)
                 for l in range(19):
                     if self.M[s, l] == 0:
                         continue            # term multiplied by M[s,l]==0 contributes exactly 0
                     e = self.e_f[l]
-                    emv_f = (e[0] - v[:, 0]) * f[0] + (e[1] - v[:, 1]) * f[1] + (e[2] - v[:, 2]) * f[2]
+                    emv_f = (e[0] - v[:, 0]) * f[:, 0] + (e[1] - v[:, 1]) * f[:, 1] + (e[2] - v[:, 2]) * f[:, 2]
                     ev = e[0] * v[:, 0] + e[1] * v[:, 1] + e[2] * v[:, 2]
-                    ef = e[0] * f[0] + e[1] * f[1] + e[2] * f[2]
+                    ef = e[0] * f[:, 0] + e[1] * f[:, 1] + e[2] * f[:, 2]
                     f_guo = f_guo + self.w[l] * (emv_f / dt(3.0) + (ev * ef) / dt(9.0)) * self.M[s, l]
                 m[:, s] = m[:, s] + (dt(1) - dt(0.5) * self.S[s]) * f_guo
         self.f[fl] = self._matvec(self.inv_M, m)               # :240-241
@@ -275,8 +288,8 @@ class RefSinglePhase:
                 if E[s, c] != 0:
                     v[:, c] = v[:, c] + self.e_f[s, c] * Fn[:, s]
         v = v / rho[:, None]
-        fvec = self.ext_f
-        v = v + (fvec[None, :] / dt(2)) / rho[:, None]
+        fvec = self.cal_local_force(fl)                        # :385
+        v = v + (fvec / dt(2)) / rho[:, None]
         self.rho[fl] = rho
         self.v[fl] = v
         self.rho[~fl] = 1.0

@@ -85,6 +85,7 @@ class LB3D_Solver_Single_Phase:
         self.tau_mode = tau_mode
         self.device = device
         self._solid_host = np.zeros((nx, ny, nz), np.int8)
+        self._force_field = None
         self._ctx = None
         self._lib = None
         self.solid = _Field(self, "solid", (nx, ny, nz), np.int8)
@@ -153,6 +154,23 @@ class LB3D_Solver_Single_Phase:
     def set_force(self, force):
         self.fx = force[0]; self.fy = force[1]; self.fz = force[2]
 
+    def set_force_field(self, force):
+        """Per-node force, shape (nx, ny, nz, 3): the array form of the reference's override
+        point ``cal_local_force(i, j, k)`` (:217-220; the solute solver overrides it to add
+        buoyancy).  May be replaced between steps; ``None`` returns to ``set_force``."""
+        if force is not None:
+            force = np.ascontiguousarray(np.asarray(force, dtype=np.float32))
+            if force.shape != (self.nx, self.ny, self.nz, 3):
+                raise ValueError("force field must have shape %s" % ((self.nx, self.ny, self.nz, 3),))
+        self._force_field = force
+        if self._ctx is not None:
+            self._apply_force_field()
+
+    def _apply_force_field(self):
+        ff = self._force_field
+        ptr = ctypes.c_void_p(None) if ff is None else ff.ctypes.data_as(ctypes.c_void_p)
+        self._ck(self._lib.lbm_set_force_field(self._ctx, ptr), "lbm_set_force_field")
+
     # ---- geometry, reference :173-177 ---------------------------------------------------------
     def init_geo(self, filename):
         from .geometry import load_geometry
@@ -211,6 +229,8 @@ class LB3D_Solver_Single_Phase:
             inv = np.ascontiguousarray(np.linalg.inv(M_np).astype(np.float32))   # :83, :110
             self._ck(lib.lbm_set_inverse_matrix(ctx, inv.ctypes.data_as(_lib._FP)), "lbm_set_inverse_matrix")
         self._ck(lib.lbm_init(ctx), "lbm_init")
+        if self._force_field is not None:
+            self._apply_force_field()
 
     # ---- time stepping, reference :477-481 -----------------------------------------------------
     def _stream(self):

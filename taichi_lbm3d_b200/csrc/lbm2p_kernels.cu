@@ -53,7 +53,7 @@ __device__ __forceinline__ void s_local(const Step2Args &A, float psi, float &sv
 // ---- literal evaluation order (oracle/ref_two_phase.c) ----------------------------------------
 __device__ __forceinline__ void macro2(const float (&f)[19], const LbmParams &P, float &rho, float &ux,
                                        float &uy, float &uz) {
-    macro(f, P, true, rho, ux, uy, uz);       // same interleaved sums as streaming3 :596-602
+    macro(f, P.force, true, rho, ux, uy, uz);       // same interleaved sums as streaming3 :596-602
 }
 
 __device__ __forceinline__ void collide2(float (&f)[19], const Step2Args &A, bool force, float rho, float ux,
@@ -142,7 +142,7 @@ __device__ __forceinline__ void collide2(float (&f)[19], const Step2Args &A, boo
 // ---- production arithmetic ---------------------------------------------------------------------
 __device__ __forceinline__ void macro2(const float (&f)[19], const LbmParams &P, float &rho, float &ux,
                                        float &uy, float &uz) {
-    macro(f, P, true, rho, ux, uy, uz);
+    macro(f, P.force, true, rho, ux, uy, uz);
 }
 
 __device__ __forceinline__ void collide2(float (&f)[19], const Step2Args &A, bool force, float rho, float ux,

@@ -76,6 +76,10 @@ struct lbm_ctx {
     float *d_vbc = nullptr;
     uint32_t vbc_off[6]{};
     float *d_scalar = nullptr;
+    float *d_ff = nullptr;         // per-node force, [3][ff_stride] in stored order (null: uniform force)
+    float *d_ffm = nullptr;        // the array the PENDING step was collided with (valid while ffm_pending)
+    bool ffm_pending = false;
+    size_t ff_stride = 0;
     // state machine
     bool aa = false;             // sparse in-place (AA-pattern) stepping on one buffer
     int parity = 0;              // aa: 0 = natural layout, 1 = arrival layout (see lbm_kernels.cuh)
@@ -269,6 +273,15 @@ __global__ void k_decode_table(StepArgs a, uint32_t nf, int32_t *__restrict__ ou
 #undef X
 }
 
+// user force array [N][3] (reference layout) -> three planes in stored order
+__global__ void k_force_planes(const float *__restrict__ src, const uint32_t *__restrict__ lin, size_t n,
+                               size_t stride, float *__restrict__ dst) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t node = lin ? lin[i] : i;
+    for (int k = 0; k < 3; ++k) dst[(size_t)k * stride + i] = src[node * 3 + k];
+}
+
 void default_relaxation(double niu, int textbook, float S[19]) {
     // init_simulation :126-131, same double arithmetic as the Python source
     const double tau_f = textbook ? 3.0 * niu + 0.5 : niu / 3.0 + 0.5;
@@ -286,6 +299,8 @@ void free_device(lbm_ctx *c) {
     c->d_rb16 = nullptr; c->d_blk = nullptr; c->d_exc = nullptr;
     cudaFree(c->d_cls); c->d_cls = nullptr; c->d_fbase[0] = c->d_fbase[1] = nullptr;
     cudaFree(c->d_v); cudaFree(c->d_F); cudaFree(c->d_vbc); cudaFree(c->d_scalar);
+    cudaFree(c->d_ff); c->d_ff = nullptr;
+    cudaFree(c->d_ffm); c->d_ffm = nullptr; c->ffm_pending = false;
     c->d_solid = nullptr; c->d_flags = nullptr; c->d_nbr = nullptr; c->d_lin = nullptr;
     c->d_rank = nullptr; c->d_f[0] = c->d_f[1] = nullptr; c->d_rho = c->d_v = c->d_F = nullptr;
     c->d_vbc = nullptr; c->d_scalar = nullptr;
@@ -318,6 +333,14 @@ void fill_args(const lbm_ctx *c, StepArgs &a) {
     a.vbc = c->d_vbc;
     for (int i = 0; i < 6; ++i) a.vbc_off[i] = c->vbc_off[i];
     a.force = (fabsf(c->force[0]) > 0.f || fabsf(c->force[1]) > 0.f || fabsf(c->force[2]) > 0.f) ? 1 : 0;
+    if (c->d_ff) {
+        a.force = 2;
+        for (int k = 0; k < 3; ++k) a.ff[k] = c->d_ff + (size_t)k * c->ff_stride;
+        if (c->ffm_pending) {
+            a.force = 3;
+            for (int k = 0; k < 3; ++k) a.ffm[k] = c->d_ffm + (size_t)k * c->ff_stride;
+        }
+    }
     a.has_bc = 0;
     for (int i = 0; i < 19; ++i) a.P.S[i] = c->S[i];
     for (int i = 0; i < 3; ++i) a.P.force[i] = c->force[i];
@@ -384,11 +407,26 @@ int sync_fields(lbm_ctx *c, bool need_F) {
         set_buffers(c, a, c->d_f[c->cur], nullptr);
         a.F = need_F ? c->d_F : nullptr;
         if (c->aa && c->parity) a.aa = AA_EVEN;      // arrival layout: the streamed state is local
+        if (a.force == 3) {                          // the pending step ran with the previous array
+            a.force = 2;
+            for (int k = 0; k < 3; ++k) a.ff[k] = a.ffm[k];
+        }
         int r = launch(c, MODE_EXTRACT, a, c->stream);
         if (r) return r;
         c->macro_valid = true;
         if (need_F) c->F_valid = true;
     }
+    return LBM_OK;
+}
+
+// close the pending step into the user-visible state (F, rho, v) and restart the pipeline from
+// there: used when a parameter of the collision changes in a way a fused launch cannot bridge
+int flush_pipeline(lbm_ctx *c) {
+    if (!c->pipe_valid) return LBM_OK;
+    int r = sync_fields(c, true);
+    if (r) return r;
+    c->pipe_valid = false;
+    c->ffm_pending = false;
     return LBM_OK;
 }
 
@@ -550,7 +588,65 @@ int lbm_set_bc(lbm_ctx *ctx, int face, int type, float rho, const float vel[3]) 
 int lbm_set_force(lbm_ctx *ctx, const float force[3]) {
     CTX_CHECK(ctx);
     if (!force) FAIL(ctx, LBM_ERR_INVALID, "null force");
+    const bool changed = force[0] != ctx->force[0] || force[1] != ctx->force[1] || force[2] != ctx->force[2];
+    if (ctx->inited && ctx->pipe_valid && changed) {
+        // the pending step was collided with the old force and must be closed with it (:385-388)
+        int r = flush_pipeline(ctx);
+        if (r) return r;
+    }
     for (int k = 0; k < 3; ++k) ctx->force[k] = force[k];
+    return LBM_OK;
+}
+
+int lbm_set_force_field(lbm_ctx *c, const float *force3) {
+    CTX_CHECK(c);
+    if (!c->inited) FAIL(c, LBM_ERR_STATE, "the force array is set after lbm_init (it is stored in node order)");
+    CU(c, cudaSetDevice(c->cfg.device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    // A fused launch closes step k (macro with the force of step k) and opens step k+1 (collision
+    // with the new force).  Array -> array: keep the old planes as `ffm` for that one launch.
+    // Uniform <-> array: close the pending step first and restart from the user-visible state.
+    if (c->pipe_valid && (force3 == nullptr || c->d_ff == nullptr)) {
+        int r = flush_pipeline(c);
+        if (r) return r;
+    }
+    if (!force3) {                       // back to the uniform force of lbm_set_force
+        cudaFree(c->d_ff); cudaFree(c->d_ffm);
+        c->d_ff = c->d_ffm = nullptr;
+        c->ffm_pending = false;
+        return LBM_OK;
+    }
+    const size_t n = c->cfg.sparse ? c->nf : c->N;
+    c->ff_stride = c->stride;
+    const size_t bytes = 3 * c->ff_stride * sizeof(float);
+    if (c->d_ff && c->pipe_valid && !c->ffm_pending) {
+        float *t = c->d_ffm;             // the current array becomes the pending step's
+        c->d_ffm = c->d_ff;
+        c->d_ff = t;
+        c->ffm_pending = true;
+    }
+    if (!c->d_ff) CU(c, cudaMalloc(&c->d_ff, bytes));
+    // stage the caller's array on the device if it lives on the host
+    cudaPointerAttributes at{};
+    const bool dev = cudaPointerGetAttributes(&at, force3) == cudaSuccess && at.type == cudaMemoryTypeDevice;
+    cudaGetLastError();
+    const float *src = force3;
+    float *tmp = nullptr;
+    if (!dev) {
+        CU(c, cudaMalloc(&tmp, c->N * 3 * sizeof(float)));
+        cudaError_t e = cudaMemcpy(tmp, force3, c->N * 3 * sizeof(float), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { cudaFree(tmp); CU(c, e); }
+        src = tmp;
+    }
+    cudaError_t e = cudaMemset(c->d_ff, 0, bytes);
+    if (e == cudaSuccess && n) {
+        k_force_planes<<<nblocks(n, 256), 256>>>(src, c->cfg.sparse ? c->d_lin : nullptr, n, c->ff_stride, c->d_ff);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaFree(tmp);
+    CU(c, e);
+    c->launches++;
     return LBM_OK;
 }
 
@@ -837,6 +933,10 @@ int lbm_step(lbm_ctx *c, int nsteps, void *cuda_stream) {
         if (r) return r;
         if (c->aa) c->parity ^= 1;
         else c->cur ^= 1;
+        if (c->ffm_pending) {            // only the first launch after a new force array closes an old step
+            c->ffm_pending = false;
+            fill_args(c, a);
+        }
     }
     c->macro_valid = false;
     c->F_valid = false;
@@ -893,6 +993,7 @@ static int set_field(lbm_ctx *c, const float *src, int which) {
     const size_t n = which == 0 ? c->N : (which == 1 ? c->N * 3 : c->N * 19);
     CU(c, cudaMemcpy(dst, src, n * sizeof(float), cudaMemcpyDefault));
     c->pipe_valid = false;            // next step restarts from the user-visible state
+    c->ffm_pending = false;
     c->macro_valid = true;
     c->F_valid = true;
     return LBM_OK;
@@ -1089,6 +1190,7 @@ int lbm_run_slab(lbm_ctx *c, int nsteps, int overlap, void *cuda_stream) {
             int r = launch(c, MODE_STEP, a, st);
             if (r) return r;
             c->cur ^= 1;
+            c->ffm_pending = false;
             r = exchange_impl(c, 0, st);
             if (r) return r;
             continue;
@@ -1107,6 +1209,7 @@ int lbm_run_slab(lbm_ctx *c, int nsteps, int overlap, void *cuda_stream) {
         if (r) return r;
         CU(c, cudaStreamWaitEvent(st, c->ev_comm, 0));
         c->cur ^= 1;
+        c->ffm_pending = false;
     }
     c->macro_valid = false;
     c->F_valid = false;
@@ -1151,6 +1254,7 @@ int lbm_step_flip(lbm_ctx *c) {
     if (!c->inited || !c->pipe_valid) FAIL(c, LBM_ERR_STATE, "pipeline not started");
     if (c->aa) FAIL(c, LBM_ERR_STATE, "plane-wise stepping needs two buffers (create the context with sparse = 1)");
     c->cur ^= 1;
+    c->ffm_pending = false;
     c->macro_valid = false;
     c->F_valid = false;
     return LBM_OK;

@@ -40,7 +40,7 @@ __host__ __device__ constexpr float weight(int s) { return s == 0 ? W_REST : (s 
 
 struct LbmParams {
     float S[19];          // S_dig :131
-    float force[3];       // ext_f :134-136
+    float force[3];       // ext_f :134-136 (uniform force; a per-node force array replaces it)
     int bc_type[6];       // x0,x1,y0,y1,z0,z1
     float bc_rho[6];
     float bc_vel[6][3];
@@ -77,7 +77,7 @@ __device__ __forceinline__ void feq_all(float (&f)[19], float rho, float ux, flo
 // -------------------------------------------------------------------------------------------
 static __constant__ float c_invM[361];   // inv_M :110, uploaded by the API (one copy per TU)
 
-__device__ __forceinline__ void macro(const float (&f)[19], const LbmParams &P, bool force,
+__device__ __forceinline__ void macro(const float (&f)[19], const float (&frc)[3], bool force,
                                       float &rho, float &ux, float &uy, float &uz) {
     float r = 0.f;
 #pragma unroll
@@ -91,15 +91,15 @@ __device__ __forceinline__ void macro(const float (&f)[19], const LbmParams &P, 
 #undef X
     x = x / r; y = y / r; z = z / r;                      // :387
     // :388   v += (f/2)/rho   (adding an exact zero when there is no force changes nothing)
-    x = x + (P.force[0] / 2.0f) / r;
-    y = y + (P.force[1] / 2.0f) / r;
-    z = z + (P.force[2] / 2.0f) / r;
+    x = x + (frc[0] / 2.0f) / r;
+    y = y + (frc[1] / 2.0f) / r;
+    z = z + (frc[2] / 2.0f) / r;
     (void)force;
     rho = r; ux = x; uy = y; uz = z;
 }
 
-__device__ __forceinline__ void collide(float (&f)[19], const LbmParams &P, bool force, float rho,
-                                        float ux, float uy, float uz) {
+__device__ __forceinline__ void collide(float (&f)[19], const LbmParams &P, const float (&frc)[3], bool force,
+                                        float rho, float ux, float uy, float uz) {
     constexpr int M[19][19] = {
         {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1},
         {-1, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1},
@@ -142,7 +142,7 @@ __device__ __forceinline__ void collide(float (&f)[19], const LbmParams &P, bool
 #pragma unroll
     for (int s = 0; s < 19; ++s) m[s] = m[s] - P.S[s] * (m[s] - meq[s]);   // :228
     if (force) {                                           // :230-238
-        const float fx = P.force[0], fy = P.force[1], fz = P.force[2];
+        const float fx = frc[0], fy = frc[1], fz = frc[2];
 #pragma unroll
         for (int s = 0; s < 19; ++s) {
             float f_guo = 0.f;
@@ -242,7 +242,7 @@ __device__ __forceinline__ void inverse(const float (&m)[19], float (&f)[19]) {
 }
 
 // rho, v of streaming3 (:380-388): rho = m0, momentum = (m3, m5, m7).
-__device__ __forceinline__ void macro(const float (&f)[19], const LbmParams &P, bool force,
+__device__ __forceinline__ void macro(const float (&f)[19], const float (&frc)[3], bool force,
                                       float &rho, float &ux, float &uy, float &uz) {
     const float px = f[1] + f[2], py = f[3] + f[4], pz = f[5] + f[6];
     const float a1 = f[7] + f[8], a2 = f[9] + f[10], c1 = f[11] + f[12], c2 = f[13] + f[14];
@@ -255,9 +255,9 @@ __device__ __forceinline__ void macro(const float (&f)[19], const LbmParams &P, 
     float z = (f[5] - f[6]) + ((g1 - g2) + (k1 - k2));
     const float inv = 1.0f / r;
     if (force) {
-        x = (x + 0.5f * P.force[0]) * inv;
-        y = (y + 0.5f * P.force[1]) * inv;
-        z = (z + 0.5f * P.force[2]) * inv;
+        x = (x + 0.5f * frc[0]) * inv;
+        y = (y + 0.5f * frc[1]) * inv;
+        z = (z + 0.5f * frc[2]) * inv;
     } else {
         x *= inv; y *= inv; z *= inv;
     }
@@ -266,8 +266,8 @@ __device__ __forceinline__ void macro(const float (&f)[19], const LbmParams &P, 
 
 // colission :222-241.  Guo term in closed form: sum_l w_l[((e_l-v).F)/3 + (e_l.v)(e_l.F)/9] M[s,l]
 // is non-zero only for s in {0,1,3,5,7,9,11,13,14,15} (derived symbolically).
-__device__ __forceinline__ void collide(float (&f)[19], const LbmParams &P, bool force, float rho,
-                                        float ux, float uy, float uz) {
+__device__ __forceinline__ void collide(float (&f)[19], const LbmParams &P, const float (&frc)[3], bool force,
+                                        float rho, float ux, float uy, float uz) {
     float m[19];
     forward(f, m);
     const float uxx = ux * ux, uyy = uy * uy, uzz = uz * uz;
@@ -292,7 +292,7 @@ __device__ __forceinline__ void collide(float (&f)[19], const LbmParams &P, bool
     m[17] = m[17] - P.S[17] * m[17];
     m[18] = m[18] - P.S[18] * m[18];
     if (force) {                                                               // :230-238
-        const float fx = P.force[0], fy = P.force[1], fz = P.force[2];
+        const float fx = frc[0], fy = frc[1], fz = frc[2];
         const float xx = fx * ux, yy = fy * uy, zz = fz * uz;
         const float vf = xx + yy + zz;
         m[0] += (1.0f - 0.5f * P.S[0]) * (-8.0f / 27.0f) * vf;

@@ -50,9 +50,23 @@ __device__ __forceinline__ uint32_t vbc_slot(const StepArgs &a, int face, uint32
 }
 
 // Face BCs -> macro -> (collide).  `f` holds the streamed populations on entry.
-template <bool FORCE, int MODE>
+// force acting on a node (cal_local_force :217-220): the uniform ext_f, or the node's entry of
+// the force array (FORCE == 2); `node` indexes the stored order (dense: linear index)
+template <int FORCE>
+__device__ __forceinline__ void local_force(const StepArgs &a, uint32_t node, float (&frc)[3]) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) frc[k] = FORCE >= 2 ? __ldg(a.ff[k] + node) : a.P.force[k];
+}
+// force of the step being CLOSED by a fused launch (differs only when the array was replaced)
+template <int FORCE>
+__device__ __forceinline__ void macro_force(const StepArgs &a, uint32_t node, float (&frc)[3]) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) frc[k] = FORCE == 3 ? __ldg(a.ffm[k] + node) : (FORCE == 2 ? __ldg(a.ff[k] + node) : a.P.force[k]);
+}
+
+template <int FORCE, int MODE>
 __device__ __forceinline__ void node_update(float (&f)[19], const StepArgs &a, uint32_t fl,
-                                            uint32_t lin, float &rho, float &ux, float &uy,
+                                            uint32_t lin, uint32_t node, float &rho, float &ux, float &uy,
                                             float &uz) {
     uint32_t slot = 0;
     bool pressure = false;
@@ -76,21 +90,24 @@ __device__ __forceinline__ void node_update(float (&f)[19], const StepArgs &a, u
             }
         }
     }
-    macro(f, a.P, FORCE, rho, ux, uy, uz);
+    float frc[3];
+    macro_force<FORCE>(a, node, frc);
+    macro(f, frc, FORCE != 0, rho, ux, uy, uz);
     if (MODE == MODE_STEP) {
         if (pressure) {
             a.vbc[3 * (size_t)slot + 0] = ux;
             a.vbc[3 * (size_t)slot + 1] = uy;
             a.vbc[3 * (size_t)slot + 2] = uz;
         }
-        collide(f, a.P, FORCE, rho, ux, uy, uz);
+        if (FORCE == 3) local_force<FORCE>(a, node, frc);
+        collide(f, a.P, frc, FORCE != 0, rho, ux, uy, uz);
     }
 }
 
 // MODE_COLLIDE: the reference's colission() on the user-visible state.
-template <bool FORCE>
+template <int FORCE>
 __device__ __forceinline__ void node_collide_only(float (&f)[19], const StepArgs &a, uint32_t fl,
-                                                  uint32_t lin) {
+                                                  uint32_t lin, uint32_t node) {
     float rho = 1.0f, ux = 0.f, uy = 0.f, uz = 0.f;
     if (a.F != nullptr) {
 #pragma unroll
@@ -112,7 +129,9 @@ __device__ __forceinline__ void node_collide_only(float (&f)[19], const StepArgs
             a.vbc[3 * (size_t)slot + 2] = uz;
         }
     }
-    collide(f, a.P, FORCE, rho, ux, uy, uz);
+    float frc[3];
+    local_force<FORCE>(a, node, frc);
+    collide(f, a.P, frc, FORCE != 0, rho, ux, uy, uz);
 }
 
 template <int MODE>
@@ -132,7 +151,7 @@ __device__ __forceinline__ void write_user_fields(const StepArgs &a, uint32_t li
 // ---------------------------------------------------------------------------------------------
 // dense lattice: direct addressing, node = linear index i*ny*nz + j*nz + k (z fastest)
 // ---------------------------------------------------------------------------------------------
-template <bool FORCE, int MODE, bool SPEC>
+template <int FORCE, int MODE, bool SPEC>
 __global__ void __launch_bounds__(256) k_dense(const StepArgs a) {
     // blockIdx.x walks the z-chunks of a row (fastest), (blockIdx.z, blockIdx.y) the row groups:
     // blocks that run together then cover whole z-rows, i.e. contiguous 19*nzp*4-byte chunks
@@ -148,7 +167,7 @@ __global__ void __launch_bounds__(256) k_dense(const StepArgs a) {
     if (MODE == MODE_COLLIDE) {
         const uint32_t fl = a.flags[idx];
         if (fl & FL_SOLID) return;
-        node_collide_only<FORCE>(f, a, fl, idx);
+        node_collide_only<FORCE>(f, a, fl, idx, idx);
     } else {
         // Speculative pull (SPEC): the class byte and all 19 populations of the common node
         // (no solid link, no wrap, no BC) are requested together, so a bulk node pays ONE
@@ -222,14 +241,17 @@ __global__ void __launch_bounds__(256) k_dense(const StepArgs a) {
         }
         // one copy of the arithmetic for every fluid lane of the warp
         if (compute) {
-            macro(f, a.P, FORCE, rho, ux, uy, uz);
+            float frc[3];
+            macro_force<FORCE>(a, idx, frc);
+            macro(f, frc, FORCE != 0, rho, ux, uy, uz);
             if (MODE == MODE_STEP) {
                 if (pressure) {
                     a.vbc[3 * (size_t)slot + 0] = ux;
                     a.vbc[3 * (size_t)slot + 1] = uy;
                     a.vbc[3 * (size_t)slot + 2] = uz;
                 }
-                collide(f, a.P, FORCE, rho, ux, uy, uz);
+                if (FORCE == 3) local_force<FORCE>(a, idx, frc);
+                collide(f, a.P, frc, FORCE != 0, rho, ux, uy, uz);
             }
         }
         if (MODE == MODE_EXTRACT) {
@@ -328,7 +350,7 @@ __device__ __forceinline__ void table_fetch(const StepArgs &a, uint32_t blk, Spa
 
 // one stored node: pull (through the table slice in shared memory once `bar` flips to
 // `parity`), BC, macro, collide, store
-template <bool FORCE, int MODE, bool COMP, int AA>
+template <int FORCE, int MODE, bool COMP, int AA>
 __device__ __forceinline__ void sparse_node(const StepArgs &a, const SparseTable &s_tab, uint64_t *s_bar,
                                             uint32_t parity, uint32_t i) {
     const bool active = i >= a.first && i < a.first + a.count;
@@ -341,7 +363,7 @@ __device__ __forceinline__ void sparse_node(const StepArgs &a, const SparseTable
     if (MODE == MODE_COLLIDE) {
         if (!active) return;
         fl = a.flags[i];
-        node_collide_only<FORCE>(f, a, fl, a.lin[i]);
+        node_collide_only<FORCE>(f, a, fl, a.lin[i], i);
     } else {
         if (AA == AA_EVEN) {
             // arrival layout: everything this node needs sits in its own 19 slots
@@ -386,7 +408,7 @@ __device__ __forceinline__ void sparse_node(const StepArgs &a, const SparseTable
         }
         float rho, ux, uy, uz;
         const uint32_t lin = (MODE == MODE_EXTRACT || a.has_bc) ? a.lin[i] : 0u;
-        node_update<FORCE, MODE>(f, a, fl, lin, rho, ux, uy, uz);
+        node_update<FORCE, MODE>(f, a, fl, lin, i, rho, ux, uy, uz);
         if (MODE == MODE_EXTRACT) {
             write_user_fields<MODE>(a, lin, f, rho, ux, uy, uz);
             return;
@@ -419,7 +441,7 @@ __device__ __forceinline__ void sparse_node(const StepArgs &a, const SparseTable
 
 // occupancy: 8 blocks (32 registers) per SM, except the in-place odd step, which keeps the 19
 // pull locations live across the collision and is faster unspilled at 6 blocks (40 registers)
-template <bool FORCE, int MODE, bool COMP, int AA>
+template <int FORCE, int MODE, bool COMP, int AA>
 __global__ void __launch_bounds__(SPARSE_BLOCK, (AA == AA_ODD && MODE == MODE_STEP) ? LBM_SPARSE_MINB_ODD : LBM_SPARSE_MINB)
 k_sparse(const StepArgs a) {
     constexpr bool TABLE = COMP && MODE != MODE_COLLIDE && AA != AA_EVEN;   // phase 1 needed
@@ -446,7 +468,7 @@ k_sparse(const StepArgs a) {
     sparse_node<FORCE, MODE, COMP, AA>(a, s_tab, &s_bar, 0u, blk * SPARSE_BLOCK + threadIdx.x);
 }
 
-template <bool FORCE, int MODE>
+template <int FORCE, int MODE>
 static void launch_dense_t(const StepArgs &a, int block, cudaStream_t st) {
     // block = (BX along z, BY rows); BX = nz rounded up to a warp, capped at `block`
     // split a z-row into the fewest chunks of at most `block` threads, of equal (warp-rounded) size
@@ -465,7 +487,7 @@ static void launch_dense_t(const StepArgs &a, int block, cudaStream_t st) {
         k_dense<FORCE, MODE, false><<<grid, blk, 0, st>>>(a);
 }
 
-template <bool FORCE, int MODE>
+template <int FORCE, int MODE>
 static void launch_sparse_t(const StepArgs &a, int block, cudaStream_t st) {
     (void)block;
     block = SPARSE_BLOCK;
@@ -482,13 +504,17 @@ static void launch_sparse_t(const StepArgs &a, int block, cudaStream_t st) {
 }
 
 #define DISPATCH(FN)                                                                           \
-    switch ((a.force ? 4 : 0) | mode) {                                                        \
-        case 0: FN<false, MODE_STEP>(a, block, st); break;                                     \
-        case 1: FN<false, MODE_EXTRACT>(a, block, st); break;                                  \
-        case 2: FN<false, MODE_COLLIDE>(a, block, st); break;                                  \
-        case 4: FN<true, MODE_STEP>(a, block, st); break;                                      \
-        case 5: FN<true, MODE_EXTRACT>(a, block, st); break;                                   \
-        case 6: FN<true, MODE_COLLIDE>(a, block, st); break;                                   \
+    switch (a.force * 4 + mode) {                                                              \
+        case 0: FN<0, MODE_STEP>(a, block, st); break;                                         \
+        case 1: FN<0, MODE_EXTRACT>(a, block, st); break;                                      \
+        case 2: FN<0, MODE_COLLIDE>(a, block, st); break;                                      \
+        case 4: FN<1, MODE_STEP>(a, block, st); break;                                         \
+        case 5: FN<1, MODE_EXTRACT>(a, block, st); break;                                      \
+        case 6: FN<1, MODE_COLLIDE>(a, block, st); break;                                      \
+        case 8: FN<2, MODE_STEP>(a, block, st); break;                                         \
+        case 9: FN<2, MODE_EXTRACT>(a, block, st); break;                                      \
+        case 10: FN<2, MODE_COLLIDE>(a, block, st); break;                                     \
+        case 12: FN<3, MODE_STEP>(a, block, st); break;                                        \
         default: return cudaErrorInvalidValue;                                                 \
     }
 

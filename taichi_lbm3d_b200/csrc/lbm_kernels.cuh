@@ -88,7 +88,13 @@ struct StepArgs {
     // previous-step velocity of pressure-BC nodes (:279-281 read self.v before streaming3)
     float *vbc;                     // [sum of face sizes][3]
     uint32_t vbc_off[6];            // first slot of each face
-    int force;                      // force_flag :137-140
+    int force;                      // force_flag :137-140; 2 = per-node force array `ff`; 3 = `ff` + `ffm`
+    // per-node force (replaces the cal_local_force override point :217-220): three planes in the
+    // order of the stored nodes (dense: [3][N], sparse: [3][stride]); null = uniform P.force.
+    // A fused launch closes step k (macro, :385-388) and opens step k+1 (collision, :230-238): when
+    // the array was replaced in between, `ffm` is the one step k ran with (force == 3).
+    const float *ff[3];
+    const float *ffm[3];
     int has_bc;                     // any face with type != 0
     d3q19::LbmParams P;
 };

@@ -9,8 +9,10 @@ FACE_SETTERS_VEL = ["set_bc_vel_x0", "set_bc_vel_x1", "set_bc_vel_y0", "set_bc_v
 
 
 class Case:
-    def __init__(self, name, solid, bc=(), force=None, niu=None, perturb=0.0, tau_mode="class"):
+    def __init__(self, name, solid, bc=(), force=None, niu=None, perturb=0.0, tau_mode="class",
+                 force_field=None):
         self.name = name
+        self.force_field = force_field   # (nx,ny,nz,3): per-node force (cal_local_force override)
         self.solid = np.ascontiguousarray(solid, dtype=np.int8)
         self.shape = self.solid.shape
         self.bc = list(bc)              # (face, "rho", value) | (face, "vel", [vx,vy,vz])
@@ -29,6 +31,8 @@ class Case:
             o.set_force(self.force)
         if self.niu is not None:
             o.set_viscosity(self.niu)
+        if self.force_field is not None:
+            o.set_force_field(self.force_field)
         o.init_simulation()
         if self.perturb:
             fl = o.solid == 0
@@ -56,6 +60,8 @@ class Case:
             lb.set_force(self.force)
         if self.niu is not None:
             lb.set_viscosity(self.niu)
+        if self.force_field is not None:
+            lb.set_force_field(self.force_field)
         lb.init_simulation()
         return lb
 
@@ -80,6 +86,19 @@ def case_mixed_bc(shape=(12, 10, 9)):
 
 def case_periodic_force(shape=(11, 7, 13)):
     return Case("periodic_force", random_porous(shape, 0.3, 11), force=[1e-5, 2e-5, -1e-5], perturb=1e-3)
+
+
+def case_force_field(shape=(11, 9, 13)):
+    """buoyancy-like per-node force (what Phase_change/...Solute_Solver.py:185-190 returns from
+    its cal_local_force override): uniform part + a smooth field + noise, pressure faces in z"""
+    rng = np.random.default_rng(17)
+    x, y, z = np.meshgrid(*[np.arange(n) for n in shape], indexing='ij')
+    ff = np.zeros(shape + (3,), np.float32)
+    ff[..., 0] = 1e-5 + 2e-6 * np.sin(2 * np.pi * y / shape[1])
+    ff[..., 1] = -3e-6 * np.cos(2 * np.pi * z / shape[2])
+    ff[..., 2] = 4e-6 * rng.standard_normal(shape)
+    return Case("force_field", random_porous(shape, 0.3, 23), bc=[(4, "rho", 1.0), (5, "rho", 0.995)],
+                force_field=ff, perturb=1e-3)
 
 
 def case_all_faces():

@@ -74,7 +74,7 @@ def _compare(lb, o, exact, case=None, steps=None):
     return F, rho, v
 
 
-CASES = [cases.case_mixed_bc, cases.case_periodic_force, cases.case_all_faces]
+CASES = [cases.case_mixed_bc, cases.case_periodic_force, cases.case_all_faces, cases.case_force_field]
 
 
 @pytest.mark.parametrize("make", CASES)
@@ -204,6 +204,27 @@ def test_wide_table_blocks_bit_identical(cuda, sparse):
     case = cases.Case("wide", solid, force=[1e-5, 2e-6, -3e-6], perturb=1e-3)
     o, o0 = _oracle(case, 3)
     lb = _run_solver(case, 3, sparse, True, o0)
+    _compare(lb, o, exact=True)
+
+
+@pytest.mark.parametrize("sparse", [False, True, "aa"])
+def test_force_field_replaced_between_steps(cuda, sparse):
+    """the per-node force array (cal_local_force override point :217-220) may change between
+    steps (buoyancy follows the temperature field in the solute solver) and be switched off"""
+    case = cases.case_force_field()
+    o, o0 = _oracle(case, 3)
+    lb = _run_solver(case, 3, sparse, True, o0)
+    ff2 = (case.force_field * np.float32(-0.5)).astype(np.float32)
+    o.set_force_field(ff2)
+    lb.set_force_field(ff2)
+    o.run(3)
+    lb.run(3)
+    _compare(lb, o, exact=True)
+    o.set_force_field(None)              # back to the uniform force (zero here)
+    o._p.force_flag = 0
+    lb.set_force_field(None)
+    o.run(2)
+    lb.run(2)
     _compare(lb, o, exact=True)
 
 

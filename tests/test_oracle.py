@@ -39,7 +39,22 @@ def test_meq_is_M_feq():
         assert np.allclose(m, meq, atol=1e-15)
 
 
-@pytest.mark.parametrize("make", [cases.case_mixed_bc, cases.case_all_faces, cases.case_periodic_force])
+def test_force_field_generalises_uniform_force():
+    """a constant force ARRAY gives bit for bit what set_force gives (cal_local_force :217-220
+    returns the same vector at every node), in the NumPy and the C form"""
+    base = cases.case_periodic_force()
+    ff = np.broadcast_to(np.asarray(base.force, np.float32), base.shape + (3,)).copy()
+    arr = cases.Case("ff", base.solid, force_field=ff, perturb=base.perturb)
+    for cls in (ref.RefSinglePhase, RefSinglePhaseC):
+        a, b = base.make_oracle(cls), arr.make_oracle(cls)
+        for _ in range(4):
+            a.step()
+            b.step()
+        assert np.array_equal(a.F, b.F) and np.array_equal(a.v, b.v)
+
+
+@pytest.mark.parametrize("make", [cases.case_mixed_bc, cases.case_all_faces, cases.case_periodic_force,
+                                  cases.case_force_field])
 def test_numpy_and_c_forms_bit_identical(make):
     case = make()
     a = case.make_oracle(ref.RefSinglePhase)
