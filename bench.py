@@ -272,8 +272,11 @@ def main():
         lb2.solid.from_numpy(pinned.numpy())            # host geometry in
         configure(lb2)
         lb2.init_simulation()                           # H2D + table build
+        t_init = time.perf_counter() - t0
         for _ in range(args.steps):                     # the reference scripts' loop: one call per step
             lb2.step()
+        lb2.synchronize()
+        t_steps = time.perf_counter() - t0 - t_init
         rho_h = lb2.rho.to_numpy(out=rho_pin.numpy())   # D2H results into pinned host buffers
         v_h = lb2.v.to_numpy(out=v_pin.numpy())
         h2d = solid.nbytes
@@ -282,8 +285,11 @@ def main():
         lb2.set_solid(pinned.numpy())
         configure(lb2)
         lb2.init_simulation()
+        t_init = time.perf_counter() - t0
         for _ in range(args.steps):
             lb2.step()
+        torch.cuda.synchronize()
+        t_steps = time.perf_counter() - t0 - t_init
         rho_pin.numpy()[...] = lb2.local_field("rho")
         v_pin.numpy()[...] = lb2.local_field("v")
         rho_h, v_h = rho_pin.numpy(), v_pin.numpy()
@@ -300,7 +306,8 @@ def main():
            "d2h_bytes_per_step": (rho_h.nbytes + v_h.nbytes + 4) * n_gpus / args.steps,
            "job": "geometry upload + init_simulation + %d x step() + rho, v, max_v to host%s"
                   % (args.steps, "" if world == 1 else " (every rank its slab; includes creating the NCCL communicator)"),
-           "seconds": dt, "max_v": mv}
+           "seconds": dt, "seconds_init": t_init, "seconds_steps": t_steps,
+           "seconds_readback": dt - t_init - t_steps, "max_v": mv}
     del lb2
 
     if rank != 0:

@@ -83,6 +83,10 @@ int lbm_set_geometry(lbm_ctx *ctx, const int8_t *solid_host_or_dev);
 int lbm_set_bc(lbm_ctx *ctx, int face, int type, float rho, const float vel[3]);
 /* set_force (:457); force_flag as :137-140 */
 int lbm_set_force(lbm_ctx *ctx, const float force[3]);
+/* form of the Guo force term in the collision: 0 = the class (:236, parts divided by 3 and 9:
+ * effective body force f/9), 1 = un-scaled, as in the other copy of the solver
+ * (Phase_change/LBM_3D_SinglePhase_Solver.py:235) and the script variants.  Before lbm_init. */
+int lbm_set_guo_form(lbm_ctx *ctx, int unscaled);
 /* per-node force [nx][ny][nz][3] (host or device; copied): the array form of the reference's
  * override point cal_local_force(i,j,k) (:217-220, overridden by
  * Phase_change/LBM_3D_SinglePhase_Solute_Solver.py:185-190 to add buoyancy).  Used by the

@@ -43,7 +43,7 @@ def _params_struct(ctype):
                     ("force_flag", ctypes.c_int), ("bc_type", ctypes.c_int * 6),
                     ("S", ctype * 19), ("invM", ctype * 361), ("w", ctype * 19),
                     ("force", ctype * 3), ("bc_rho", ctype * 6), ("bc_vel", (ctype * 3) * 6),
-                    ("force_field", ctypes.c_void_p)]
+                    ("force_field", ctypes.c_void_p), ("guo_unscaled", ctypes.c_int)]
     return P
 
 
@@ -54,8 +54,8 @@ _P64 = _params_struct(ctypes.c_double)
 class RefSinglePhaseC(_np_ref.RefSinglePhase):
     """Same state and setters as the NumPy oracle; the four passes run in C."""
 
-    def __init__(self, nx, ny, nz, dtype=np.float32, tau_mode="class", kind="strict"):
-        super().__init__(nx, ny, nz, dtype=dtype, tau_mode=tau_mode)
+    def __init__(self, nx, ny, nz, dtype=np.float32, tau_mode="class", kind="strict", guo_mode="class"):
+        super().__init__(nx, ny, nz, dtype=dtype, tau_mode=tau_mode, guo_mode=guo_mode)
         self._lib = load(kind)
         self._suf = "f32" if self.dtype == np.float32 else "f64"
         self._ct = ctypes.c_float if self.dtype == np.float32 else ctypes.c_double
@@ -94,6 +94,7 @@ class RefSinglePhaseC(_np_ref.RefSinglePhase):
             p.force[c] = self.ext_f[c]
         ff = getattr(self, "force_field", None)
         p.force_field = None if ff is None else ff.ctypes.data
+        p.guo_unscaled = 1 if self.guo_mode == "unscaled" else 0
         self._p = p
 
     def set_force_field(self, force):

@@ -69,6 +69,7 @@ typedef struct {
     REAL bc_rho[6];
     REAL bc_vel[6][3];
     const REAL *force_field; /* [n][3] per-node force = cal_local_force(i,j,k) :217-220, or NULL */
+    int guo_unscaled;        /* 1: Phase_change/LBM_3D_SinglePhase_Solver.py:235 (no /3, /9) */
 } FN(ref_params);
 typedef FN(ref_params) params_t;
 
@@ -117,7 +118,8 @@ void FN(ref_sp_colission)(const params_t *p, const int8_t *solid, const REAL *F,
                     REAL emv_f = (e0 - u[0]) * fo[0] + (e1 - u[1]) * fo[1] + (e2 - u[2]) * fo[2];
                     REAL ev = e0 * u[0] + e1 * u[1] + e2 * u[2];
                     REAL ef = e0 * fo[0] + e1 * fo[1] + e2 * fo[2];
-                    f_guo = f_guo + p->w[l] * (emv_f / R(3.0) + (ev * ef) / R(9.0)) * R(Mi[s][l]);
+                    REAL term = p->guo_unscaled ? emv_f + (ev * ef) : emv_f / R(3.0) + (ev * ef) / R(9.0);
+                    f_guo = f_guo + p->w[l] * term * R(Mi[s][l]);
                 }
                 m[s] = m[s] + (R(1) - R(0.5) * p->S[s]) * f_guo;
             }

@@ -91,10 +91,11 @@ class RefSinglePhase:
     nodes keep f = F = w, rho = 1, v = 0.
     """
 
-    def __init__(self, nx, ny, nz, dtype=np.float32, tau_mode="class"):
+    def __init__(self, nx, ny, nz, dtype=np.float32, tau_mode="class", guo_mode="class"):
         self.nx, self.ny, self.nz = nx, ny, nz
         self.dtype = np.dtype(dtype)
         self.tau_mode = tau_mode
+        self.guo_mode = guo_mode            # "unscaled": Phase_change/LBM_3D_SinglePhase_Solver.py:235
         # :17-18
         self.fx, self.fy, self.fz = 0.0e-6, 0.0, 0.0
         self.force_field = None             # array form of an overridden cal_local_force
@@ -223,7 +224,8 @@ class RefSinglePhase:
                     emv_f = (e[0] - v[:, 0]) * f[:, 0] + (e[1] - v[:, 1]) * f[:, 1] + (e[2] - v[:, 2]) * f[:, 2]
                     ev = e[0] * v[:, 0] + e[1] * v[:, 1] + e[2] * v[:, 2]
                     ef = e[0] * f[:, 0] + e[1] * f[:, 1] + e[2] * f[:, 2]
-                    f_guo = f_guo + self.w[l] * (emv_f / dt(3.0) + (ev * ef) / dt(9.0)) * self.M[s, l]
+                    term = emv_f + (ev * ef) if self.guo_mode == "unscaled" else emv_f / dt(3.0) + (ev * ef) / dt(9.0)
+                    f_guo = f_guo + self.w[l] * term * self.M[s, l]
                 m[:, s] = m[:, s] + (dt(1) - dt(0.5) * self.S[s]) * f_guo
         self.f[fl] = self._matvec(self.inv_M, m)               # :240-241
 

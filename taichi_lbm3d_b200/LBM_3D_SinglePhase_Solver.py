@@ -7,7 +7,9 @@ the fused sm_100a CUDA step behind the C ABI of ``include/lbm3d.h``.  The case s
 the reference run after dropping their two Taichi lines (``import taichi`` / ``ti.init``).
 
 Additions that the reference does not have: ``run(n)`` (n steps, one launch each, no
-Python in between), ``in_place`` (sparse storage on ONE population buffer, AA pattern), ``tau_mode`` (the textbook relaxation time the other copies of the
+Python in between), ``in_place`` (sparse storage on ONE population buffer, AA pattern),
+``set_force_field`` (per-node force: the array form of overriding ``cal_local_force``),
+``guo_mode`` (the un-scaled force term of the solver's other copies), ``tau_mode`` (the textbook relaxation time the other copies of the
 solver use), ``strict`` (oracle-order arithmetic for verification), ``to_torch`` on fields.
 
 There is no CPU path: constructing the solver is cheap, ``init_simulation`` needs a GPU.
@@ -65,7 +67,7 @@ class _Field:
 
 class LB3D_Solver_Single_Phase:
     def __init__(self, nx, ny, nz, sparse_storage=False, strict=False, tau_mode="class", device=None,
-                 in_place=None):
+                 in_place=None, guo_mode="class"):
         # reference :13-28
         self.enable_projection = True
         self.sparse_storage = sparse_storage
@@ -83,6 +85,11 @@ class LB3D_Solver_Single_Phase:
         self.bc_z_right, self.rho_bczr, self.vx_bczr, self.vy_bczr, self.vz_bczr = 0, 1.0, 0.0, 0.0, 0.0
         self.strict = bool(strict)
         self.tau_mode = tau_mode
+        # "class": Guo term as the class writes it (:236, divided by 3 and 9); "unscaled": as in
+        # Phase_change/LBM_3D_SinglePhase_Solver.py:235 (with tau_mode="textbook" that copy's physics)
+        if guo_mode not in ("class", "unscaled"):
+            raise ValueError("guo_mode must be 'class' or 'unscaled'")
+        self.guo_mode = guo_mode
         self.device = device
         self._solid_host = np.zeros((nx, ny, nz), np.int8)
         self._force_field = None
@@ -223,6 +230,7 @@ class LB3D_Solver_Single_Phase:
             self._ck(lib.lbm_set_bc(ctx, face, int(t), ctypes.c_float(float(np.float32(rho))), velc), "lbm_set_bc")
         fc = (ctypes.c_float * 3)(float(np.float32(self.fx)), float(np.float32(self.fy)), float(np.float32(self.fz)))
         self._ck(lib.lbm_set_force(ctx, fc), "lbm_set_force")
+        self._ck(lib.lbm_set_guo_form(ctx, 1 if self.guo_mode == "unscaled" else 0), "lbm_set_guo_form")
         self._ck(lib.lbm_set_relaxation(ctx, S.ctypes.data_as(_lib._FP)), "lbm_set_relaxation")
         if self.strict:
             from .constants import M_np

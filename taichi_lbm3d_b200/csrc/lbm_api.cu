@@ -38,6 +38,7 @@ struct lbm_ctx {
     // parameters
     float S[19]{};
     float force[3] = {0.f, 0.f, 0.f};
+    int guo_unscaled = 0;
     Face face[6];
     float invM[361]{};
     bool have_geometry = false;
@@ -344,6 +345,17 @@ void fill_args(const lbm_ctx *c, StepArgs &a) {
     a.has_bc = 0;
     for (int i = 0; i < 19; ++i) a.P.S[i] = c->S[i];
     for (int i = 0; i < 3; ++i) a.P.force[i] = c->force[i];
+    {
+        // Guo term = A/ga + B/gb with A from (e-v).f and B from (e.v)(e.f): (ga, gb) = (3, 9) in the
+        // class (:236), (1, 1) in the script variants; closed-form coefficients per moment group
+        const double ga = c->guo_unscaled ? 1.0 : 1.0 / 3.0, gb = c->guo_unscaled ? 1.0 : 1.0 / 9.0;
+        a.P.guo_unscaled = c->guo_unscaled;
+        a.P.gc[0] = (float)(-ga + gb / 3.0);
+        a.P.gc[1] = (float)(2.0 * gb / 9.0);
+        a.P.gc[2] = (float)(ga / 3.0);
+        a.P.gc[3] = (float)(2.0 * gb / 9.0);
+        a.P.gc[4] = (float)(gb / 9.0);
+    }
     for (int i = 0; i < 6; ++i) {
         a.P.bc_type[i] = c->face[i].type;
         a.P.bc_rho[i] = c->face[i].rho;
@@ -595,6 +607,13 @@ int lbm_set_force(lbm_ctx *ctx, const float force[3]) {
         if (r) return r;
     }
     for (int k = 0; k < 3; ++k) ctx->force[k] = force[k];
+    return LBM_OK;
+}
+
+int lbm_set_guo_form(lbm_ctx *ctx, int unscaled) {
+    CTX_CHECK(ctx);
+    if (ctx->inited) FAIL(ctx, LBM_ERR_STATE, "the form of the force term is fixed at lbm_init");
+    ctx->guo_unscaled = unscaled ? 1 : 0;
     return LBM_OK;
 }
 

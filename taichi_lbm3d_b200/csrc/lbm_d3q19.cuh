@@ -41,6 +41,12 @@ __host__ __device__ constexpr float weight(int s) { return s == 0 ? W_REST : (s 
 struct LbmParams {
     float S[19];          // S_dig :131
     float force[3];       // ext_f :134-136 (uniform force; a per-node force array replaces it)
+    // Guo force term (:230-238).  The class divides its two parts by 3 and 9 (:236); the other
+    // copy of the solver (Phase_change/LBM_3D_SinglePhase_Solver.py:235) does not.  guo_unscaled
+    // selects the form (verification arithmetic); gc[] are the closed-form coefficients of the
+    // production arithmetic: moment 0, 1, (3,5,7), (9,11), (13,14,15).
+    int guo_unscaled;
+    float gc[5];
     int bc_type[6];       // x0,x1,y0,y1,z0,z1
     float bc_rho[6];
     float bc_vel[6][3];
@@ -153,7 +159,8 @@ __device__ __forceinline__ void collide(float (&f)[19], const LbmParams &P, cons
                 const float emv_f = (e0 - ux) * fx + (e1 - uy) * fy + (e2 - uz) * fz;
                 const float ev = e0 * ux + e1 * uy + e2 * uz;
                 const float ef = e0 * fx + e1 * fy + e2 * fz;
-                f_guo = f_guo + weight(l) * (emv_f / 3.0f + (ev * ef) / 9.0f) * (float)M[s][l];
+                const float term = P.guo_unscaled ? emv_f + (ev * ef) : emv_f / 3.0f + (ev * ef) / 9.0f;
+                f_guo = f_guo + weight(l) * term * (float)M[s][l];
             }
             m[s] = m[s] + (1.0f - 0.5f * P.S[s]) * f_guo;
         }
@@ -295,16 +302,17 @@ __device__ __forceinline__ void collide(float (&f)[19], const LbmParams &P, cons
         const float fx = frc[0], fy = frc[1], fz = frc[2];
         const float xx = fx * ux, yy = fy * uy, zz = fz * uz;
         const float vf = xx + yy + zz;
-        m[0] += (1.0f - 0.5f * P.S[0]) * (-8.0f / 27.0f) * vf;
-        m[1] += (1.0f - 0.5f * P.S[1]) * (2.0f / 81.0f) * vf;
-        m[3] += (1.0f - 0.5f * P.S[3]) * (1.0f / 9.0f) * fx;
-        m[5] += (1.0f - 0.5f * P.S[5]) * (1.0f / 9.0f) * fy;
-        m[7] += (1.0f - 0.5f * P.S[7]) * (1.0f / 9.0f) * fz;
-        m[9] += (1.0f - 0.5f * P.S[9]) * (2.0f / 81.0f) * (2.0f * xx - yy - zz);
-        m[11] += (1.0f - 0.5f * P.S[11]) * (2.0f / 81.0f) * (yy - zz);
-        m[13] += (1.0f - 0.5f * P.S[13]) * (1.0f / 81.0f) * (fx * uy + fy * ux);
-        m[14] += (1.0f - 0.5f * P.S[14]) * (1.0f / 81.0f) * (fy * uz + fz * uy);
-        m[15] += (1.0f - 0.5f * P.S[15]) * (1.0f / 81.0f) * (fx * uz + fz * ux);
+        // class form: gc = (-8/27, 2/81, 1/9, 2/81, 1/81); un-scaled: (-2/3, 2/9, 1/3, 2/9, 1/9)
+        m[0] += (1.0f - 0.5f * P.S[0]) * P.gc[0] * vf;
+        m[1] += (1.0f - 0.5f * P.S[1]) * P.gc[1] * vf;
+        m[3] += (1.0f - 0.5f * P.S[3]) * P.gc[2] * fx;
+        m[5] += (1.0f - 0.5f * P.S[5]) * P.gc[2] * fy;
+        m[7] += (1.0f - 0.5f * P.S[7]) * P.gc[2] * fz;
+        m[9] += (1.0f - 0.5f * P.S[9]) * P.gc[3] * (2.0f * xx - yy - zz);
+        m[11] += (1.0f - 0.5f * P.S[11]) * P.gc[3] * (yy - zz);
+        m[13] += (1.0f - 0.5f * P.S[13]) * P.gc[4] * (fx * uy + fy * ux);
+        m[14] += (1.0f - 0.5f * P.S[14]) * P.gc[4] * (fy * uz + fz * uy);
+        m[15] += (1.0f - 0.5f * P.S[15]) * P.gc[4] * (fx * uz + fz * ux);
     }
     inverse(m, f);
 }

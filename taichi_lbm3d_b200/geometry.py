@@ -66,7 +66,7 @@ def sphere_pack(nx, ny, nz, solid_fraction=0.80, r_min=8.0, r_max=16.0, seed=512
     g = np.zeros((nx, ny, nz), bool)
     n = np.array([nx, ny, nz])
     target = solid_fraction * g.size
-    count = 0
+    count = 0                       # solid cells so far, kept incrementally (checked once per batch)
     while count < target:
         for _ in range(batch):
             c = rng.random(3) * n
@@ -85,8 +85,16 @@ def sphere_pack(nx, ny, nz, solid_fraction=0.80, r_min=8.0, r_max=16.0, seed=512
                 axes.append((idx, dist))
             (ix, dx), (iy, dy), (iz, dz) = axes
             mask = (dx[:, None, None] ** 2 + dy[None, :, None] ** 2 + dz[None, None, :] ** 2) <= r * r
-            g[np.ix_(ix, iy, iz)] |= mask
-        count = int(g.sum())
+            if periodic and (len(set(ix.tolist())) < ix.size or len(set(iy.tolist())) < iy.size
+                             or len(set(iz.tolist())) < iz.size):
+                # sphere wider than the box: wrapped indices repeat, count the slow way
+                g[np.ix_(ix, iy, iz)] |= mask
+                count = int(g.sum())
+                continue
+            sel = np.ix_(ix, iy, iz)
+            sub = g[sel]
+            count += int(np.count_nonzero(mask & ~sub))
+            g[sel] = sub | mask
     return g.astype(np.int8)
 
 

@@ -10,8 +10,9 @@ FACE_SETTERS_VEL = ["set_bc_vel_x0", "set_bc_vel_x1", "set_bc_vel_y0", "set_bc_v
 
 class Case:
     def __init__(self, name, solid, bc=(), force=None, niu=None, perturb=0.0, tau_mode="class",
-                 force_field=None):
+                 force_field=None, guo_mode="class"):
         self.name = name
+        self.guo_mode = guo_mode
         self.force_field = force_field   # (nx,ny,nz,3): per-node force (cal_local_force override)
         self.solid = np.ascontiguousarray(solid, dtype=np.int8)
         self.shape = self.solid.shape
@@ -23,7 +24,7 @@ class Case:
 
     # ---- oracle -------------------------------------------------------------------------
     def make_oracle(self, cls, **kw):
-        o = cls(*self.shape, tau_mode=self.tau_mode, **kw)
+        o = cls(*self.shape, tau_mode=self.tau_mode, guo_mode=self.guo_mode, **kw)
         o.set_solid(self.solid)
         for face, kind, val in self.bc:
             (o.set_bc_rho if kind == "rho" else o.set_bc_vel)(face, val)
@@ -52,7 +53,7 @@ class Case:
         """sparse: False (dense), True (compact list, two buffers), "aa" (compact list, in place)"""
         from taichi_lbm3d_b200 import LB3D_Solver_Single_Phase
         lb = LB3D_Solver_Single_Phase(*self.shape, sparse_storage=bool(sparse), strict=strict,
-                                      tau_mode=self.tau_mode, in_place=(sparse == "aa"))
+                                      tau_mode=self.tau_mode, in_place=(sparse == "aa"), guo_mode=self.guo_mode)
         lb.solid.from_numpy(self.solid)
         for face, kind, val in self.bc:
             getattr(lb, (FACE_SETTERS_RHO if kind == "rho" else FACE_SETTERS_VEL)[face])(val)
@@ -99,6 +100,13 @@ def case_force_field(shape=(11, 9, 13)):
     ff[..., 2] = 4e-6 * rng.standard_normal(shape)
     return Case("force_field", random_porous(shape, 0.3, 23), bc=[(4, "rho", 1.0), (5, "rho", 0.995)],
                 force_field=ff, perturb=1e-3)
+
+
+def case_other_copy(shape=(10, 9, 12)):
+    """the physics of the solver's other copy (Phase_change/LBM_3D_SinglePhase_Solver.py:126,235):
+    tau = 3 niu + 0.5 and the un-scaled Guo term"""
+    return Case("other_copy", random_porous(shape, 0.25, 31), force=[2e-5, -1e-5, 5e-6], niu=0.1,
+                perturb=1e-3, tau_mode="textbook", guo_mode="unscaled")
 
 
 def case_all_faces():

@@ -74,7 +74,8 @@ def _compare(lb, o, exact, case=None, steps=None):
     return F, rho, v
 
 
-CASES = [cases.case_mixed_bc, cases.case_periodic_force, cases.case_all_faces, cases.case_force_field]
+CASES = [cases.case_mixed_bc, cases.case_periodic_force, cases.case_all_faces, cases.case_force_field,
+         cases.case_other_copy]
 
 
 @pytest.mark.parametrize("make", CASES)
@@ -270,6 +271,34 @@ def test_full_size_properties_256(cuda):
     lba = case.make_solver(sparse="aa")                  # in place == two buffers, bit for bit
     lba.run(100)
     assert np.array_equal(lba.v.to_numpy(), lbs.v.to_numpy())
+
+
+def test_full_size_properties_config3(cuda):
+    """BASELINE config 3 at full size (512^3 periodic sphere pack, porosity 0.20, fx = 1e-6,
+    sparse storage): properties that need no oracle run -- two-buffer == in-place bit for bit,
+    sparse == dense, flow along the force, mass drift bounded by the reference's own Guo mass
+    source (moment 0 gets (-8/27) v.f per step)."""
+    from taichi_lbm3d_b200.geometry import sphere_pack
+    n = 512
+    solid = sphere_pack(n, n, n, 0.80, 8.0, 16.0, seed=n, periodic=True)
+    case = cases.Case("cfg3", solid, force=[1e-6, 0.0, 0.0])
+    fl = solid == 0
+    lb = case.make_solver(sparse=True)
+    assert lb.num_fluid() == int(fl.sum()) == 26809316
+    lb.run(60)
+    rho, v = lb.rho.to_numpy(), lb.v.to_numpy()
+    assert np.isfinite(rho).all() and np.isfinite(v).all()
+    assert v[fl][:, 0].mean() > 0 and abs(v[fl][:, 1].mean()) < 0.05 * v[fl][:, 0].mean()
+    assert abs(rho[fl].astype(np.float64).mean() - 1.0) < 1e-6
+    del lb
+    lba = case.make_solver(sparse="aa")
+    lba.run(60)
+    assert np.array_equal(lba.v.to_numpy(), v) and np.array_equal(lba.rho.to_numpy(), rho)
+    del lba
+    lbd = case.make_solver(sparse=False)
+    lbd.run(60)
+    assert rel_linf(lbd.rho.to_numpy()[fl], rho[fl]) <= 1e-6
+    assert np.abs(lbd.v.to_numpy()[fl] - v[fl]).max() <= TOL * np.abs(v[fl]).max()
 
 
 def test_launches_are_counted(cuda):

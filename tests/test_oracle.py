@@ -54,7 +54,7 @@ def test_force_field_generalises_uniform_force():
 
 
 @pytest.mark.parametrize("make", [cases.case_mixed_bc, cases.case_all_faces, cases.case_periodic_force,
-                                  cases.case_force_field])
+                                  cases.case_force_field, cases.case_other_copy])
 def test_numpy_and_c_forms_bit_identical(make):
     case = make()
     a = case.make_oracle(ref.RefSinglePhase)
@@ -131,6 +131,23 @@ def test_poiseuille_known_answer():
     z = np.arange(1, 7)
     ana = (fy / 9.0) / (2 * niu / 9.0) * (z - 0.5) * (6.5 - z)
     j = o.rho[1, 2, 1:7] * o.v[1, 2, 1:7, 1] - fy / 2 + (fy / 9.0) / 2
+    assert rel_linf(j, ana) < 1e-5
+
+
+def test_poiseuille_known_answer_other_copy():
+    """same plates with the physics of the solver's other copy (tau = 3 niu + 1/2 :126 of
+    Phase_change/LBM_3D_SinglePhase_Solver.py, Guo term not divided :235): effective force
+    g = fy/3 (the 1/cs^2 factor of Guo's scheme is still missing), nu = niu."""
+    g = np.zeros((3, 4, 8), np.int8)
+    g[:, :, 0] = 1
+    g[:, :, -1] = 1
+    fy, niu = 1e-5, 0.1667
+    o = cases.Case("p", g, force=[0.0, fy, 0.0], niu=niu, tau_mode="textbook",
+                   guo_mode="unscaled").make_oracle(RefSinglePhaseC, dtype=np.float64)
+    o.run(4000)
+    z = np.arange(1, 7)
+    ana = (fy / 3.0) / (2 * niu) * (z - 0.5) * (6.5 - z)
+    j = o.rho[1, 2, 1:7] * o.v[1, 2, 1:7, 1] - fy / 2 + (fy / 3.0) / 2
     assert rel_linf(j, ana) < 1e-5
 
 
