@@ -28,12 +28,15 @@ typedef struct lbm2p_ctx lbm2p_ctx;
 #define LBM2P_HALO_X 1     /* planes x=0 and x=nx-1 are ghost planes owned by the slab neighbours */
 #define LBM2P_HOLDS_X0 2   /* this slab's first owned plane is the global x0 face */
 #define LBM2P_HOLDS_X1 4   /* this slab's last owned plane is the global x1 face */
+#define LBM2P_SPARSE 8     /* compact fluid-node list + pull table instead of the full lattice: the
+                              storage of 2phase/lbm_solver_3d_2phase_sparse.py (:54-75), as the
+                              single-phase sparse mode does it; not combined with LBM2P_HALO_X */
 
 typedef struct {
     int32_t nx, ny, nz;   /* :17 */
     int32_t strict;       /* 1: oracle evaluation order, no FMA contraction (verification) */
     int32_t device;
-    int32_t reserved;     /* 0, or LBM2P_HALO_X | LBM2P_HOLDS_X0 | LBM2P_HOLDS_X1 */
+    int32_t reserved;     /* 0, LBM2P_SPARSE, or LBM2P_HALO_X | LBM2P_HOLDS_X0 | LBM2P_HOLDS_X1 */
 } lbm2p_config;
 
 int lbm2p_create(const lbm2p_config *cfg, lbm2p_ctx **out);

@@ -16,8 +16,8 @@ from taichi_lbm3d_b200.geometry import ftb131_standin  # noqa: E402
 B2P = 176.0
 
 
-def run(name, solid, psi, steps=200, warmup=20):
-    lb = LB3D_Solver_Two_Phase(*solid.shape)
+def run(name, solid, psi, steps=200, warmup=20, sparse=False):
+    lb = LB3D_Solver_Two_Phase(*solid.shape, sparse_storage=sparse)
     lb.solid.from_numpy(solid)
     lb.psi.from_numpy(psi)
     lb.niu_l, lb.niu_g, lb.CapA, lb.psi_solid = 0.05, 0.2, 0.005, 0.7
@@ -48,7 +48,8 @@ def main():
     solid = ftb131_standin()
     psi = np.ones(solid.shape, np.float32)
     psi[:13] = -1.0
-    out.append(run("drainage 131^3 sphere-pack stand-in (config 4 parameters)", solid, psi))
+    out.append(run("drainage 131^3 sphere-pack stand-in (config 4 parameters), dense storage", solid, psi))
+    out.append(run("drainage 131^3 sphere-pack stand-in (config 4 parameters), sparse storage", solid, psi, sparse=True))
     n = 256
     x, y, z = np.meshgrid(*[np.arange(n)] * 3, indexing='ij')
     r = np.sqrt((x - n / 2) ** 2 + (y - n / 2) ** 2 + (z - n / 2) ** 2)

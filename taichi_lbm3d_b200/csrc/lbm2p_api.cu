@@ -14,6 +14,7 @@
 #include "lbm2p_kernels.cuh"
 #include "lbm_geometry.cuh"
 #include "lbm_nccl.cuh"
+#include "lbm_sparse_build.cuh"
 
 namespace {
 thread_local std::string g2_create_error;
@@ -61,6 +62,10 @@ struct lbm2p_ctx {
     bool macro_valid = true, F_valid = true;
     cudaStream_t stream = nullptr;
     int64_t launches = 0;
+    // sparse storage (cfg.reserved & LBM2P_SPARSE): compact fluid list + pull table; the colour
+    // records, rho_r, rho_b, psi and the populations are indexed by stored node
+    bool sparse = false;
+    SparseTables sp;
     // x-slab (cfg.reserved bit0): planes 0 and nx-1 are ghost planes
     bool halo = false;
     int xface0 = 0, xface1 = 0;            // local x of the global x faces (-1: not in this slab)
@@ -131,7 +136,36 @@ __global__ void k2p_bake_psi(const int8_t *__restrict__ solid, float *psi, float
     if (i < n && solid[i] != 0) psi[i] = psi_solid;
 }
 
+// sparse storage: init :173-186 on the compact arrays; psi0 is the dense input phase field
+__global__ void k2p_init_compact(const uint32_t *__restrict__ lin, const float *__restrict__ psi0, size_t nf,
+                                 float *psi, float *rho_r, float *rho_b) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nf) return;
+    const float p = psi0[lin[i]];
+    psi[i] = p;
+    const float rr = (p + 1.0f) / 2.0f;
+    rho_r[i] = rr;
+    rho_b[i] = 1.0f - rr;
+}
+__global__ void k2p_init_macro(const int8_t *__restrict__ solid, size_t n, float *rho, float *v) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    rho[i] = solid[i] == 0 ? 1.0f : 0.f;
+    v[3 * i] = 0.f; v[3 * i + 1] = 0.f; v[3 * i + 2] = 0.f;
+}
+// compact -> dense (getters): `out` is pre-filled with what solid nodes show
+__global__ void k2p_scatter(const uint32_t *__restrict__ lin, const float *__restrict__ src, size_t nf, float *out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nf) out[lin[i]] = src[i];
+}
+// dense -> compact (set_state)
+__global__ void k2p_gather(const uint32_t *__restrict__ lin, const float *__restrict__ src, size_t nf, float *out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nf) out[i] = src[lin[i]];
+}
+
 void free2(lbm2p_ctx *c) {
+    free_sparse_tables(c->sp);
     cudaFree(c->d_flags); cudaFree(c->d_cls); cudaFree(c->d_fbase[0]); cudaFree(c->d_fbase[1]);
     cudaFree(c->d_recA); cudaFree(c->d_recB); cudaFree(c->d_recC); cudaFree(c->d_psibase); cudaFree(c->d_rho_r); cudaFree(c->d_rho_b);
     cudaFree(c->d_rho); cudaFree(c->d_v); cudaFree(c->d_F); cudaFree(c->d_vbc); cudaFree(c->d_scalar);
@@ -147,19 +181,31 @@ void fill2(const lbm2p_ctx *c, Step2Args &A, const float *fin, float *fout) {
         {0, 0, -1}, {1, 1, 0}, {-1, -1, 0}, {1, -1, 0}, {-1, 1, 0}, {1, 0, 1}, {-1, 0, -1},
         {1, 0, -1}, {-1, 0, 1}, {0, 1, 1}, {0, -1, -1}, {0, 1, -1}, {0, -1, 1}};
     const long long sy = (long long)c->prow, sx = (long long)c->cfg.ny * sy;
+    const size_t pstride = c->sparse ? c->sp.stride : (size_t)c->nzp;
     for (int s = 0; s < 19; ++s) {
-        a.pown[s] = fin ? fin + (size_t)s * c->nzp : nullptr;
+        a.pown[s] = fin ? fin + (size_t)s * pstride : nullptr;
         a.ppull[s] = fin ? a.pown[s] - (e[s][0] * sx + e[s][1] * sy + e[s][2]) : nullptr;
-        a.pout[s] = fout ? fout + (size_t)s * c->nzp : nullptr;
+        a.pout[s] = fout ? fout + (size_t)s * pstride : nullptr;
     }
     a.stride = 0;
+    A.sparse = c->sparse ? 1 : 0;
+    if (c->sparse) {
+        a.stride = c->sp.stride;
+        a.first = c->sp.own_first;
+        a.count = c->sp.own_count;
+        a.lin = c->sp.d_lin;
+        a.compressed = 1;
+        for (int k = 0; k < 8; ++k) a.rb16[k] = c->sp.d_rb16 + (size_t)k * c->sp.stride;
+        a.blk = c->sp.d_blk;
+        for (int k = 0; k < 18; ++k) a.exc[k] = c->sp.d_exc + (size_t)k * c->sp.exc_stride;
+    }
     a.row_first = c->row_first;
     a.row_count = c->row_count;
     a.halo_x = c->halo ? 1 : 0;
     a.prow = c->prow;
     a.spec = c->spec;
     a.nx = c->cfg.nx; a.ny = c->cfg.ny; a.nz = c->cfg.nz;
-    a.flags = c->d_flags;
+    a.flags = c->sparse ? c->sp.d_flags : c->d_flags;
     a.cls = c->d_cls;
     a.rho = c->d_rho; a.v = c->d_v; a.F = nullptr;
     a.vbc = c->d_vbc;
@@ -191,16 +237,24 @@ void fill2(const lbm2p_ctx *c, Step2Args &A, const float *fin, float *fout) {
 }
 
 int launch_main2(lbm2p_ctx *c, int mode, const Step2Args &A, cudaStream_t st) {
-    cudaError_t e = c->cfg.strict ? lbm2p_strict::launch_main(mode, A, c->block, st)
-                                  : lbm2p_fast::launch_main(mode, A, c->block, st);
+    cudaError_t e;
+    if (c->sparse)
+        e = c->cfg.strict ? lbm2p_strict::launch_main_sparse(mode, A, st) : lbm2p_fast::launch_main_sparse(mode, A, st);
+    else
+        e = c->cfg.strict ? lbm2p_strict::launch_main(mode, A, c->block, st)
+                          : lbm2p_fast::launch_main(mode, A, c->block, st);
     if (e != cudaSuccess) FAIL2(c, -2, "kernel launch failed: %s", cudaGetErrorString(e));
     c->launches++;
     return 0;
 }
 
 int launch_colour2(lbm2p_ctx *c, const Step2Args &A, cudaStream_t st) {
-    cudaError_t e = c->cfg.strict ? lbm2p_strict::launch_colour(A, c->block, st)
-                                  : lbm2p_fast::launch_colour(A, c->block, st);
+    cudaError_t e;
+    if (c->sparse)
+        e = c->cfg.strict ? lbm2p_strict::launch_colour_sparse(A, st) : lbm2p_fast::launch_colour_sparse(A, st);
+    else
+        e = c->cfg.strict ? lbm2p_strict::launch_colour(A, c->block, st)
+                          : lbm2p_fast::launch_colour(A, c->block, st);
     if (e != cudaSuccess) FAIL2(c, -2, "kernel launch failed: %s", cudaGetErrorString(e));
     c->launches++;
     return 0;
@@ -261,7 +315,9 @@ int lbm2p_create(const lbm2p_config *cfg, lbm2p_ctx **out) {
     if (cfg->nx < 2 || cfg->ny < 2 || cfg->nz < 2) { g2_create_error = "extents must be >= 2"; return -1; }
     const size_t N = (size_t)cfg->nx * cfg->ny * cfg->nz;
     const size_t nzp = ((size_t)cfg->nz + 31) / 32 * 32;
-    if ((size_t)cfg->nx * cfg->ny * 19 * nzp + 2 * ((size_t)cfg->ny + 2) * 19 * nzp >= ((size_t)1 << 32)) {
+    if (N >= ((size_t)1 << 32)) { g2_create_error = "lattice per context limited to 2^32 nodes"; return -1; }
+    if (!(cfg->reserved & LBM2P_SPARSE) &&
+        (size_t)cfg->nx * cfg->ny * 19 * nzp + 2 * ((size_t)cfg->ny + 2) * 19 * nzp >= ((size_t)1 << 32)) {
         g2_create_error = "two-phase lattice per context limited by the 32-bit population index";
         return -1;
     }
@@ -279,6 +335,8 @@ int lbm2p_create(const lbm2p_config *cfg, lbm2p_ctx **out) {
     c->cfg = *cfg;
     c->N = N;
     c->halo = (cfg->reserved & LBM2P_HALO_X) != 0;
+    c->sparse = (cfg->reserved & LBM2P_SPARSE) != 0;
+    if (c->halo && c->sparse) { g2_create_error = "x-slabs of the two-phase solver use dense storage"; delete c; return -1; }
     if (c->halo && cfg->nx < 3) { g2_create_error = "an x-slab needs nx >= 3 (two ghost planes)"; delete c; return -1; }
     if (const char *b = getenv("LBM3D_BLOCK")) {
         int v = atoi(b);
@@ -402,6 +460,46 @@ int lbm2p_init(lbm2p_ctx *c) {
     for (int i = 0; i < 6; ++i) { g.bc_type[i] = c->face[i].type; g.bc_psi_type[i] = c->bc_psi_type[i]; }
     g.two_phase = 1;
     CU2(c, cudaMalloc(&c->d_scalar, 16));
+    CU2(c, cudaMalloc(&c->d_rho, N * sizeof(float)));
+    CU2(c, cudaMalloc(&c->d_v, N * 3 * sizeof(float)));
+    if (c->sparse) {
+        // compact fluid list + pull table (lbm_sparse_build.cuh); link words carry the face and
+        // wetting bits of the two-phase kernels
+        std::string msg;
+        cudaError_t e = build_sparse_tables(g, c->d_solid, true, c->sp, msg);
+        c->launches += c->sp.launches;
+        if (!msg.empty()) FAIL2(c, -1, "%s", msg.c_str());
+        CU2(c, e);
+        c->nf = c->sp.nf;
+        const size_t st = c->sp.stride;
+        c->fsize = 19 * st;
+        c->pad = 0;
+        for (int b = 0; b < 2; ++b) {
+            CU2(c, cudaMalloc(&c->d_fbase[b], c->fsize * sizeof(float)));
+            CU2(c, cudaMemset(c->d_fbase[b], 0, c->fsize * sizeof(float)));
+            c->d_f[b] = c->d_fbase[b];
+        }
+        CU2(c, cudaMalloc(&c->d_recA, st * sizeof(float4)));
+        CU2(c, cudaMalloc(&c->d_recB, st * sizeof(float2)));
+        CU2(c, cudaMalloc(&c->d_recC, st * sizeof(float4)));
+        CU2(c, cudaMemset(c->d_recA, 0, st * sizeof(float4)));
+        CU2(c, cudaMemset(c->d_recB, 0, st * sizeof(float2)));
+        CU2(c, cudaMemset(c->d_recC, 0, st * sizeof(float4)));
+        CU2(c, cudaMalloc(&c->d_psibase, st * sizeof(float)));
+        CU2(c, cudaMemset(c->d_psibase, 0, st * sizeof(float)));
+        c->d_psi = c->d_psibase;
+        CU2(c, cudaMalloc(&c->d_rho_r, st * sizeof(float)));
+        CU2(c, cudaMalloc(&c->d_rho_b, st * sizeof(float)));
+        CU2(c, cudaMemset(c->d_rho_r, 0, st * sizeof(float)));
+        CU2(c, cudaMemset(c->d_rho_b, 0, st * sizeof(float)));
+        if (c->nf) {
+            k2p_init_compact<<<nblocks(c->nf, 256), 256>>>(c->sp.d_lin, c->d_psi0, c->nf, c->d_psi, c->d_rho_r, c->d_rho_b);
+            CU2(c, cudaGetLastError());
+        }
+        k2p_init_macro<<<nblocks(N, 256), 256>>>(c->d_solid, N, c->d_rho, c->d_v);
+        CU2(c, cudaGetLastError());
+        c->launches += 2;
+    } else {
     CU2(c, cudaMalloc(&c->d_flags, N * sizeof(uint32_t)));
     CU2(c, cudaMalloc(&c->d_cls, N));
     k_build_flags<<<nblocks(N, 256), 256>>>(g, c->d_solid, c->d_flags, c->d_cls);
@@ -448,12 +546,11 @@ int lbm2p_init(lbm2p_ctx *c) {
     c->d_psi = c->d_psibase + c->npad;
     CU2(c, cudaMalloc(&c->d_rho_r, N * sizeof(float)));
     CU2(c, cudaMalloc(&c->d_rho_b, N * sizeof(float)));
-    CU2(c, cudaMalloc(&c->d_rho, N * sizeof(float)));
-    CU2(c, cudaMalloc(&c->d_v, N * 3 * sizeof(float)));
     k2p_init_state<<<nblocks(N, 256), 256>>>(c->d_solid, c->d_psi0, N, (float)c->psi_solid, c->d_psi, c->d_rho_r,
                                               c->d_rho_b, c->d_rho, c->d_v);
     CU2(c, cudaGetLastError());
     c->launches++;
+    }
     const size_t fs[6] = {plane, plane, (size_t)nx * nz, (size_t)nx * nz, (size_t)nx * ny, (size_t)nx * ny};
     size_t tot = 0;
     for (int i = 0; i < 6; ++i) { c->vbc_off[i] = (uint32_t)tot; tot += fs[i]; }
@@ -736,25 +833,52 @@ int lbm2p_synchronize(lbm2p_ctx *c) {
 GETTER(lbm2p_get_rho, true, false, c->d_rho, c->N)
 GETTER(lbm2p_get_v, true, false, c->d_v, c->N * 3)
 GETTER(lbm2p_get_F, true, true, c->d_F, c->N * 19)
-GETTER(lbm2p_get_rho_r, false, false, c->d_rho_r, c->N)
-GETTER(lbm2p_get_rho_b, false, false, c->d_rho_b, c->N)
 #undef GETTER
 
-int lbm2p_get_psi(lbm2p_ctx *c, float *dst) {
-    CTX2(c);
-    if (!dst) FAIL2(c, -1, "null destination");
+// node-linear view of a colour field: dense storage holds it that way (solid nodes: 0); sparse
+// storage scatters the compact array over a zero-filled (or, for psi, input-filled) lattice
+static int get_colour_field(lbm2p_ctx *c, float *dst, const float *field, const float *solid_fill) {
     int r = sync2(c, false, false);
     if (r) return r;
+    if (!c->sparse && solid_fill == nullptr) return out2(c, dst, field, c->N * sizeof(float));
     float *tmp = nullptr;
     CU2(c, cudaMalloc(&tmp, c->N * sizeof(float)));
-    k2p_merge_psi<<<nblocks(c->N, 256), 256, 0, c->stream>>>(c->d_solid, c->d_psi0, c->d_psi, tmp, c->N);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = cudaSuccess;
+    if (c->sparse) {
+        e = solid_fill ? cudaMemcpyAsync(tmp, solid_fill, c->N * sizeof(float), cudaMemcpyDeviceToDevice, c->stream)
+                       : cudaMemsetAsync(tmp, 0, c->N * sizeof(float), c->stream);
+        if (e == cudaSuccess && c->nf) {
+            k2p_scatter<<<nblocks(c->nf, 256), 256, 0, c->stream>>>(c->sp.d_lin, field, c->nf, tmp);
+            e = cudaGetLastError();
+        }
+    } else {
+        k2p_merge_psi<<<nblocks(c->N, 256), 256, 0, c->stream>>>(c->d_solid, solid_fill, field, tmp, c->N);
+        e = cudaGetLastError();
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     if (e == cudaSuccess) e = cudaMemcpy(dst, tmp, c->N * sizeof(float), cudaMemcpyDefault);
     cudaFree(tmp);
     CU2(c, e);
     c->launches++;
     return 0;
+}
+
+int lbm2p_get_rho_r(lbm2p_ctx *c, float *dst) {
+    CTX2(c);
+    if (!dst) FAIL2(c, -1, "null destination");
+    return get_colour_field(c, dst, c->d_rho_r, nullptr);
+}
+
+int lbm2p_get_rho_b(lbm2p_ctx *c, float *dst) {
+    CTX2(c);
+    if (!dst) FAIL2(c, -1, "null destination");
+    return get_colour_field(c, dst, c->d_rho_b, nullptr);
+}
+
+int lbm2p_get_psi(lbm2p_ctx *c, float *dst) {
+    CTX2(c);
+    if (!dst) FAIL2(c, -1, "null destination");
+    return get_colour_field(c, dst, c->d_psi, c->d_psi0);      // solid nodes keep the input value
 }
 
 int lbm2p_get_solid(lbm2p_ctx *c, int8_t *dst) {
@@ -779,10 +903,28 @@ int lbm2p_set_state(lbm2p_ctx *c, const float *F, const float *rho, const float 
     CU2(c, cudaMemcpy(c->d_rho, rho, c->N * sizeof(float), cudaMemcpyDefault));
     CU2(c, cudaMemcpy(c->d_v, v, c->N * 3 * sizeof(float), cudaMemcpyDefault));
     CU2(c, cudaMemcpy(c->d_psi0, psi, c->N * sizeof(float), cudaMemcpyDefault));
+    if (c->sparse) {
+        float *tmp = nullptr;
+        CU2(c, cudaMalloc(&tmp, c->N * sizeof(float)));
+        const float *src[3] = {psi, rho_r, rho_b};
+        float *dstc[3] = {c->d_psi, c->d_rho_r, c->d_rho_b};
+        cudaError_t e = cudaSuccess;
+        for (int k = 0; k < 3 && e == cudaSuccess; ++k) {
+            e = cudaMemcpy(tmp, src[k], c->N * sizeof(float), cudaMemcpyDefault);
+            if (e == cudaSuccess && c->nf) {
+                k2p_gather<<<nblocks(c->nf, 256), 256>>>(c->sp.d_lin, tmp, c->nf, dstc[k]);
+                e = cudaGetLastError();
+            }
+            if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        }
+        cudaFree(tmp);
+        CU2(c, e);
+    } else {
     CU2(c, cudaMemcpy(c->d_psi, psi, c->N * sizeof(float), cudaMemcpyDefault));
     CU2(c, cudaMemcpy(c->d_rho_r, rho_r, c->N * sizeof(float), cudaMemcpyDefault));
     CU2(c, cudaMemcpy(c->d_rho_b, rho_b, c->N * sizeof(float), cudaMemcpyDefault));
     k2p_bake_psi<<<nblocks(c->N, 256), 256>>>(c->d_solid, c->d_psi, (float)c->psi_solid, c->N);
+    }
     CU2(c, cudaGetLastError());
     CU2(c, cudaDeviceSynchronize());
     c->launches++;

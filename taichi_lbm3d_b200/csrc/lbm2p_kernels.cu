@@ -21,6 +21,7 @@
 #include <cstdlib>
 
 #include "lbm2p_kernels.cuh"
+#include "lbm_sparse_table.cuh"
 
 #ifdef LBM_STRICT
 #define LBM2P_NS lbm2p_strict
@@ -508,6 +509,267 @@ __global__ void __launch_bounds__(256, LBM2P_MAIN_MINB) k2p_main(const Step2Args
     }
 #pragma unroll
     for (int s = 0; s < 19; ++s) a.pout[s][pidx] = f[s];
+}
+
+// ---------------------------------------------------------------------------------------------
+// sparse storage (2phase/lbm_solver_3d_2phase_sparse.py: same arithmetic as the dense script,
+// pointer-SNode allocation): compact fluid list + the compressed pull table of the single-phase
+// solver.  The node at i + e_s is the pull source of the opposite direction, so one table serves
+// the populations (sources i - e_s), the colour records (same sources) and the psi stencil.
+// ---------------------------------------------------------------------------------------------
+static __constant__ int8_t c_ev[19][3] = {{0, 0, 0}, {1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1},
+    {0, 0, -1}, {1, 1, 0}, {-1, -1, 0}, {1, -1, 0}, {-1, 1, 0}, {1, 0, 1}, {-1, 0, -1}, {1, 0, -1},
+    {-1, 0, 1}, {0, 1, 1}, {0, -1, -1}, {0, 1, -1}, {0, -1, 1}};
+static __constant__ int8_t c_lr[19] = {0, 2, 1, 4, 3, 6, 5, 8, 7, 10, 9, 12, 11, 14, 13, 16, 15, 18, 17};
+// direction index of an offset (cx,cy,cz) in {-1,0,1}^3, -1 if it is not a D3Q19 direction
+static __constant__ int8_t c_dir27[27] = {-1, 8, -1, 12, 2, 14, -1, 10, -1, 16, 4, 18, 6, 0, 5, 17, 3, 15,
+                                          -1, 9, -1, 13, 1, 11, -1, 7, -1};
+
+// stored index of the pull source of direction s (the node at i - e_s), s a run-time value
+__device__ __noinline__ int32_t source_rt(int s, uint32_t i, uint32_t fl, const int32_t (&rb)[8]) {
+    switch (s) {
+#define X(s_, ex, ey, ez, o) case s_: return s_ == 0 ? (int32_t)i : comp_source<ex, ey, ez>(i, fl, rb);
+        D3Q19_DIRS(X)
+#undef X
+    }
+    return (int32_t)i;
+}
+
+// psi stencil of Compute_C (:259-275) for a node on a constant-psi face: periodic_index_for_psi
+// (:390-428) clamps the out-of-range coordinate, i.e. the neighbour loses that component of e_s
+__device__ __noinline__ void gradient_clamped(const Step2Args &A, uint32_t i, uint32_t fl, const int32_t (&rb)[8],
+                                              bool exc, uint32_t slot, float &Cx, float &Cy, float &Cz) {
+    const StepArgs &a = A.a;
+    const float psi_i = A.psi[i];
+    Cx = 0.f; Cy = 0.f; Cz = 0.f;
+    for (int s = 1; s < 19; ++s) {
+        int c[3] = {c_ev[s][0], c_ev[s][1], c_ev[s][2]};
+        for (int d = 0; d < 3; ++d) {
+            if (c[d] < 0 && (fl & (FL_AT_X0 << (2 * d))) && A.bc_psi_type[2 * d] == 1) c[d] = 0;
+            if (c[d] > 0 && (fl & (FL_AT_X1 << (2 * d))) && A.bc_psi_type[2 * d + 1] == 1) c[d] = 0;
+        }
+        const int sp = c_dir27[(c[0] + 1) * 9 + (c[1] + 1) * 3 + (c[2] + 1)];
+        float val = psi_i;
+        if (sp > 0) {
+            const int o = c_lr[sp];                  // the neighbour at +e_sp is the pull source of o
+            if ((fl >> o) & 1u) val = A.psi_solid;
+            else val = A.psi[exc ? (uint32_t)__ldg(a.exc[o - 1] + slot) : (uint32_t)source_rt(o, i, fl, rb)];
+        }
+        const float w3 = 3.0f * weight(s);
+        if (c_ev[s][0] != 0) Cx = Cx + (w3 * (float)c_ev[s][0]) * val;
+        if (c_ev[s][1] != 0) Cy = Cy + (w3 * (float)c_ev[s][1]) * val;
+        if (c_ev[s][2] != 0) Cz = Cz + (w3 * (float)c_ev[s][2]) * val;
+    }
+}
+
+__global__ void __launch_bounds__(SPARSE_BLOCK, LBM2P_COLOUR_MINB) k2p_colour_sparse(const __grid_constant__ Step2Args A) {
+    const StepArgs &a = A.a;
+    __shared__ SparseTable s_tab;
+    __shared__ uint64_t s_bar;
+    const uint32_t blk = blockIdx.x + a.first / SPARSE_BLOCK;
+    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) table_fetch(a, blk, s_tab, &s_bar);
+    const uint32_t i = blk * SPARSE_BLOCK + threadIdx.x;
+    mbar_wait(&s_bar, 0);
+    if (i < a.first || i >= a.first + a.count) return;
+    const uint32_t fl = s_tab.fl[threadIdx.x];
+    const bool exc = fl & FL_EXCEPTION;
+    int32_t rb[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) rb[k] = s_tab.blk[k] + (int32_t)s_tab.rb[k][threadIdx.x];
+    const uint32_t slot = (uint32_t)s_tab.blk[8] + s_tab.rb[0][threadIdx.x];
+    ColourSum acc;
+#define X(s, ex, ey, ez, o)                                                                    \
+    {                                                                                          \
+        const bool bounce = s > 0 && ((fl >> s) & 1u);                                         \
+        uint32_t j = i;                                                                        \
+        if (s > 0 && !bounce) j = exc ? (uint32_t)__ldg(a.exc[s > 0 ? s - 1 : 0] + slot) : (uint32_t)comp_source<ex, ey, ez>(i, fl, rb); \
+        colour_add<s, ex, ey, ez>(bounce ? -1.0f : 1.0f, __ldg(A.recA + j), __ldg(A.recB + j), A.recC + j, acc); \
+    }
+    D3Q19_DIRS(X)
+#undef X
+    float rr = acc.red(), rbl = acc.blue();
+    float psi = rr - rbl / (rr + rbl);       // :605, precedence as written
+    // Boundary_condition_psi :445-486, faces in order, the last matching face wins
+    int win = -1;
+    if (fl & (FL_AT_X0 | FL_AT_X1 | FL_AT_Y0 | FL_AT_Y1 | FL_AT_Z0 | FL_AT_Z1)) {
+        if ((fl & FL_AT_X0) && A.bc_psi_type[0] == 1) win = 0;
+        if ((fl & FL_AT_X1) && A.bc_psi_type[1] == 1) win = 1;
+        if ((fl & FL_AT_Y0) && A.bc_psi_type[2] == 1) win = 2;
+        if ((fl & FL_AT_Y1) && A.bc_psi_type[3] == 1) win = 3;
+        if ((fl & FL_AT_Z0) && A.bc_psi_type[4] == 1) win = 4;
+        if ((fl & FL_AT_Z1) && A.bc_psi_type[5] == 1) win = 5;
+    }
+    if (win >= 0) {
+        psi = A.bc_psi_val[win];
+        rr = (psi + 1.0f) / 2.0f;
+        rbl = 1.0f - rr;
+    }
+    A.rho_r[i] = rr;
+    A.rho_b[i] = rbl;
+    A.psi[i] = psi;
+}
+
+template <bool FORCE, int MODE>
+__global__ void __launch_bounds__(SPARSE_BLOCK, LBM2P_MAIN_MINB) k2p_main_sparse(const __grid_constant__ Step2Args A) {
+    const StepArgs &a = A.a;
+    __shared__ SparseTable s_tab;
+    __shared__ uint64_t s_bar;
+    const uint32_t blk = blockIdx.x + a.first / SPARSE_BLOCK;
+    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) table_fetch(a, blk, s_tab, &s_bar);
+    const uint32_t i = blk * SPARSE_BLOCK + threadIdx.x;
+    mbar_wait(&s_bar, 0);
+    if (i < a.first || i >= a.first + a.count) return;
+    const uint32_t fl = s_tab.fl[threadIdx.x];
+    const bool exc = fl & FL_EXCEPTION;
+    int32_t rb[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) rb[k] = s_tab.blk[k] + (int32_t)s_tab.rb[k][threadIdx.x];
+    const uint32_t slot = (uint32_t)s_tab.blk[8] + s_tab.rb[0][threadIdx.x];
+    const bool need_lin = MODE != MODE_STEP || a.has_bc;
+    const uint32_t lin = need_lin ? a.lin[i] : 0u;
+    float f[19];
+    float rho = 1.0f, ux = 0.f, uy = 0.f, uz = 0.f;
+    bool pressure = false;
+    uint32_t vslot = 0;
+    if (MODE == MODE_COLLIDE) {
+        if (a.F != nullptr) {
+#pragma unroll
+            for (int s = 0; s < 19; ++s) f[s] = a.F[(size_t)lin * 19 + s];
+            rho = a.rho[lin];
+            ux = a.v[(size_t)lin * 3 + 0];
+            uy = a.v[(size_t)lin * 3 + 1];
+            uz = a.v[(size_t)lin * 3 + 2];
+        } else {                          // pristine init() :173-186: F = w, rho = 1, v = 0
+#pragma unroll
+            for (int s = 0; s < 19; ++s) f[s] = weight(s);
+        }
+        if (a.has_bc) {
+            const uint32_t bc = (fl >> FL_BC_SHIFT) & FL_BC_MASK;
+            if (bc && a.P.bc_type[bc - 1] == 1) {
+                vslot = vbc_slot2(a, (int)bc - 1, lin);
+                a.vbc[3 * (size_t)vslot + 0] = ux;
+                a.vbc[3 * (size_t)vslot + 1] = uy;
+                a.vbc[3 * (size_t)vslot + 2] = uz;
+            }
+        }
+    } else {
+        // pull-stream with half-way bounce-back (:431-443), one selected index per direction
+        const int32_t ip = (int32_t)i + (int32_t)a.stride, im = (int32_t)i - (int32_t)a.stride;
+#define X(s, ex, ey, ez, o)                                                                    \
+    if (s > 0) {                                                                               \
+        int32_t j;                                                                             \
+        if ((fl >> s) & 1u) j = (o) > (s) ? ip : im;                                           \
+        else j = exc ? __ldg(a.exc[s > 0 ? s - 1 : 0] + slot) : comp_source<ex, ey, ez>(i, fl, rb); \
+        f[s] = __ldg(a.pown[s] + j);                                                           \
+    }
+        D3Q19_DIRS(X)
+#undef X
+        f[0] = __ldg(a.pown[0] + i);
+        if (a.has_bc) {
+            // Boundary_condition :491-583 (see the dense kernel): last pressure face from the link
+            // word, then every later velocity face in order
+            const uint32_t bc = (fl >> FL_BC_SHIFT) & FL_BC_MASK;
+            int after = 0;
+            if (bc) {
+                const int face = (int)bc - 1;
+                float u0 = 0.f, u1 = 0.f, u2 = 0.f;
+                vslot = vbc_slot2(a, face, lin);
+                if (!(fl & FL_PIN_SOLID)) {
+                    u0 = a.vbc[3 * (size_t)vslot + 0];
+                    u1 = a.vbc[3 * (size_t)vslot + 1];
+                    u2 = a.vbc[3 * (size_t)vslot + 2];
+                }
+                feq_all(f, a.P.bc_rho[face], u0, u1, u2);
+                pressure = true;
+                after = face + 1;
+            }
+            for (int face = after; face < 6; ++face) {
+                if (a.P.bc_type[face] != 2 || !(fl & (FL_AT_X0 << face))) continue;
+                const float u0 = a.P.bc_vel[face][0], u1 = a.P.bc_vel[face][1], u2 = a.P.bc_vel[face][2];
+#define X(s, ex, ey, ez, o)                                                                    \
+    f[s] = feq<o, -(ex), -(ey), -(ez)>(1.0f, u0, u1, u2) - f[o] + feq<s, ex, ey, ez>(1.0f, u0, u1, u2);
+                D3Q19_DIRS(X)
+#undef X
+            }
+        }
+        macro2(f, a.P, rho, ux, uy, uz);
+        if (MODE == MODE_EXTRACT) {
+            a.rho[lin] = rho;
+            a.v[(size_t)lin * 3 + 0] = ux;
+            a.v[(size_t)lin * 3 + 1] = uy;
+            a.v[(size_t)lin * 3 + 2] = uz;
+            if (a.F != nullptr) {
+#pragma unroll
+                for (int s = 0; s < 19; ++s) a.F[(size_t)lin * 19 + s] = f[s];
+            }
+            return;
+        }
+        if (pressure) {
+            a.vbc[3 * (size_t)vslot + 0] = ux;
+            a.vbc[3 * (size_t)vslot + 1] = uy;
+            a.vbc[3 * (size_t)vslot + 2] = uz;
+        }
+    }
+    // Compute_C :259-275: C = sum_s 3 w_s e_s psi(i + e_s); a solid neighbour reads psi_solid
+    float Cx = 0.f, Cy = 0.f, Cz = 0.f;
+    uint32_t clamp = 0;
+#pragma unroll
+    for (int fc = 0; fc < 6; ++fc)
+        if (A.bc_psi_type[fc] == 1) clamp |= FL_AT_X0 << fc;
+    if (fl & clamp) {
+        gradient_clamped(A, i, fl, rb, exc, slot, Cx, Cy, Cz);
+    } else {
+#define X(s, ex, ey, ez, o)                                                                    \
+    if (s > 0) {                                                                               \
+        float val = A.psi_solid;                                                               \
+        if (!((fl >> o) & 1u))                                                                 \
+            val = __ldg(A.psi + (exc ? (uint32_t)__ldg(a.exc[o > 0 ? o - 1 : 0] + slot)        \
+                                     : (uint32_t)comp_source<-(ex), -(ey), -(ez)>(i, fl, rb))); \
+        if (ex != 0) Cx = Cx + (3.0f * weight(s) * (float)(ex)) * val;                         \
+        if (ey != 0) Cy = Cy + (3.0f * weight(s) * (float)(ey)) * val;                         \
+        if (ez != 0) Cz = Cz + (3.0f * weight(s) * (float)(ez)) * val;                         \
+    }
+        D3Q19_DIRS(X)
+#undef X
+    }
+    const float rr = A.rho_r[i], rbl = A.rho_b[i];
+    if ((fl & FL_NEAR_SOLID) && fabsf(rr - rbl) > 0.9f) { Cx = 0.f; Cy = 0.f; Cz = 0.f; }   // :271-273
+    const float psi = A.psi[i];
+    collide2(f, A, FORCE, rho, ux, uy, uz, psi, Cx, Cy, Cz);
+    const float ccn = sqrtf(Cx * Cx + Cy * Cy + Cz * Cz);
+    const float q = 1.0f - 1.5f * (ux * ux + uy * uy + uz * uz);
+    A.recA[i] = make_float4(rr, rbl, ux, uy);
+    A.recB[i] = make_float2(uz, ccn > 0.f ? -q : q);
+    if (ccn > 0.f) A.recC[i] = make_float4(Cx, Cy, Cz, 1.0f / ccn);
+#pragma unroll
+    for (int s = 0; s < 19; ++s) a.pout[s][i] = f[s];
+}
+
+cudaError_t launch_main_sparse(int mode, const Step2Args &A, cudaStream_t st) {
+    if (A.a.count == 0) return cudaSuccess;
+    const unsigned b0 = A.a.first / SPARSE_BLOCK, b1 = (A.a.first + A.a.count + SPARSE_BLOCK - 1) / SPARSE_BLOCK;
+    const unsigned grid = b1 - b0;
+    switch ((A.a.force ? 4 : 0) | mode) {
+        case 0: k2p_main_sparse<false, MODE_STEP><<<grid, SPARSE_BLOCK, 0, st>>>(A); break;
+        case 1: k2p_main_sparse<false, MODE_EXTRACT><<<grid, SPARSE_BLOCK, 0, st>>>(A); break;
+        case 2: k2p_main_sparse<false, MODE_COLLIDE><<<grid, SPARSE_BLOCK, 0, st>>>(A); break;
+        case 4: k2p_main_sparse<true, MODE_STEP><<<grid, SPARSE_BLOCK, 0, st>>>(A); break;
+        case 5: k2p_main_sparse<true, MODE_EXTRACT><<<grid, SPARSE_BLOCK, 0, st>>>(A); break;
+        case 6: k2p_main_sparse<true, MODE_COLLIDE><<<grid, SPARSE_BLOCK, 0, st>>>(A); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_colour_sparse(const Step2Args &A, cudaStream_t st) {
+    if (A.a.count == 0) return cudaSuccess;
+    const unsigned b0 = A.a.first / SPARSE_BLOCK, b1 = (A.a.first + A.a.count + SPARSE_BLOCK - 1) / SPARSE_BLOCK;
+    k2p_colour_sparse<<<b1 - b0, SPARSE_BLOCK, 0, st>>>(A);
+    return cudaGetLastError();
 }
 
 template <bool FORCE, int MODE>

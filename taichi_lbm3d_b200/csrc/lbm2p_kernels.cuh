@@ -20,12 +20,18 @@ struct Step2Args {
     float wl, wg, lg0, l1, l2, g1, g2;   // :100-108
     int bc_psi_type[6];       // :34-39
     float bc_psi_val[6];
+    // sparse storage (lbm_solver_3d_2phase_sparse.py): compact fluid list + the single-phase pull
+    // table (a.flags, a.rb16, a.blk, a.exc, a.lin, a.first, a.count); records, rho_r, rho_b, psi
+    // are then indexed by stored node and a solid neighbour of the psi stencil reads psi_solid
+    int sparse;
 };
 
 #define LBM2P_DECLARE_KERNEL_API(NS)                                                          \
     namespace NS {                                                                            \
     cudaError_t launch_main(int mode, const Step2Args &a, int block, cudaStream_t st);        \
     cudaError_t launch_colour(const Step2Args &a, int block, cudaStream_t st);                \
+    cudaError_t launch_main_sparse(int mode, const Step2Args &a, cudaStream_t st);            \
+    cudaError_t launch_colour_sparse(const Step2Args &a, cudaStream_t st);                    \
     cudaError_t set_inverse_matrix(const float *invM361);                                     \
     }
 LBM2P_DECLARE_KERNEL_API(lbm2p_fast)

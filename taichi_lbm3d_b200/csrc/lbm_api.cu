@@ -18,6 +18,7 @@
 #include "lbm_kernels.cuh"
 #include "lbm_geometry.cuh"
 #include "lbm_nccl.cuh"
+#include "lbm_sparse_build.cuh"
 
 namespace {
 
@@ -120,135 +121,6 @@ struct lbm_ctx {
     } while (0)
 
 namespace {
-
-// true pull sources of a fluid node: j[s-1] = compact index of i - e_s, or -1 (bounce)
-__device__ __forceinline__ void true_sources(const GeoParams &g, const int8_t *solid, const uint32_t *rank,
-                                             int x, int y, int z, int32_t (&j)[18]) {
-    for (int s = 1; s < 19; ++s) {
-        size_t src;
-        j[s - 1] = (pull_source(g, x, y, z, s, src) && solid[src] == 0) ? (int32_t)rank[src] : -1;
-    }
-}
-
-// Pass 1 of the sparse tables: linear index, link word (bounce bits + BC bits), and either
-// the full 18-entry pull table or the 8 neighbour-row ranks of the compressed one (32-bit,
-// temporary; nodes whose sources do not follow the rank rule are flagged).
-__global__ void k_build_sparse(const GeoParams g, const int8_t *__restrict__ solid,
-                               const uint32_t *__restrict__ rank, size_t stride,
-                               uint32_t *__restrict__ lin, uint32_t *__restrict__ flags,
-                               int32_t *__restrict__ nbr, int32_t *__restrict__ rb) {
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t N = (size_t)g.nx * g.ny * g.nz;
-    if (idx >= N || solid[idx] != 0) return;
-    const int z = (int)(idx % g.nz);
-    const size_t t = idx / g.nz;
-    const int y = (int)(t % g.ny), x = (int)(t / g.ny);
-    const uint32_t r = rank[idx];
-    lin[r] = (uint32_t)idx;
-    int32_t j[18];
-    true_sources(g, solid, rank, x, y, z, j);
-    uint32_t fl = bc_word(g, solid, x, y, z);
-    for (int s = 1; s < 19; ++s)
-        if (j[s - 1] < 0) fl |= 1u << s;
-    if (nbr != nullptr)
-        for (int s = 1; s < 19; ++s) nbr[(size_t)(s - 1) * stride + r] = j[s - 1];
-    if (rb != nullptr) {
-        const int center[8] = {1, 2, 3, 4, 7, 8, 9, 10};     // directions (ex,ey,0) of the 8 rows
-        int32_t rbv[8];
-        for (int k = 0; k < 8; ++k) {
-            size_t src;
-            rbv[k] = pull_source(g, x, y, z, center[k], src) ? (int32_t)rank[src] : 0;
-        }
-        bool ok = true;
-        const bool ghost = g.halo_x && (x == 0 || x == g.nx - 1);   // never updated
-#define X(s, ex, ey, ez, o)                                                                    \
-    if (s > 0 && j[s > 0 ? s - 1 : 0] >= 0 && comp_source<ex, ey, ez>(r, fl, rbv) != j[s > 0 ? s - 1 : 0]) ok = false;
-        D3Q19_DIRS(X)
-#undef X
-        if (!ok && !ghost) fl |= FL_EXCEPTION;
-        for (int k = 0; k < 8; ++k) rb[(size_t)k * stride + r] = rbv[k];
-    }
-    flags[r] = fl;
-}
-
-// Pass 2, one thread block per 256-node table block: 16-bit rank offsets from the block's
-// minimum.  A block whose ranks span more than 16 bits (a periodic x / y wrap falls inside
-// it) turns all its nodes into exceptions.  Exception nodes get consecutive slots from
-// blk[B][8]; their index inside the block goes to rb16[0].  Nodes outside [own_first, own_end)
-// (ghost planes of a slab) are never updated and do not take part.
-__global__ void __launch_bounds__(256) k_pack_table(uint32_t own_first, uint32_t own_end, size_t stride,
-                                                    const int32_t *__restrict__ rb32, uint32_t *__restrict__ flags,
-                                                    uint16_t *__restrict__ rb16, int32_t *__restrict__ blk,
-                                                    uint32_t *__restrict__ exc_count) {
-    __shared__ int s_min[8], s_max[8];
-    __shared__ uint32_t s_warp[8], s_base;
-    __shared__ int s_wide;
-    const uint32_t B = blockIdx.x, t = threadIdx.x, i = B * 256u + t;
-    const bool valid = i >= own_first && i < own_end;
-    uint32_t fl = valid ? flags[i] : 0u;
-    if (t < 8) { s_min[t] = INT32_MAX; s_max[t] = INT32_MIN; }
-    __syncthreads();
-    int32_t v[8];
-    for (int k = 0; k < 8; ++k) {
-        v[k] = valid ? rb32[(size_t)k * stride + i] : 0;
-        int lo = (valid && !(fl & FL_EXCEPTION)) ? v[k] : INT32_MAX;
-        int hi = (valid && !(fl & FL_EXCEPTION)) ? v[k] : INT32_MIN;
-        for (int o = 16; o > 0; o >>= 1) {
-            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-        }
-        if ((t & 31) == 0) { atomicMin(&s_min[k], lo); atomicMax(&s_max[k], hi); }
-    }
-    __syncthreads();
-    if (t == 0) {
-        int wide = 0;
-        for (int k = 0; k < 8; ++k)
-            if (s_max[k] >= s_min[k] && (int64_t)s_max[k] - (int64_t)s_min[k] > 65535) wide = 1;
-        s_wide = wide;
-    }
-    __syncthreads();
-    if (s_wide && valid) fl |= FL_EXCEPTION;
-    const bool exc = valid && (fl & FL_EXCEPTION);
-    const uint32_t bal = __ballot_sync(0xffffffffu, exc);
-    if ((t & 31) == 0) s_warp[t >> 5] = __popc(bal);
-    __syncthreads();
-    uint32_t before = __popc(bal & ((1u << (t & 31)) - 1u));
-    uint32_t total = 0;
-    for (int w = 0; w < 8; ++w) {
-        if (w < (int)(t >> 5)) before += s_warp[w];
-        total += s_warp[w];
-    }
-    if (t == 0) s_base = total ? atomicAdd(exc_count, total) : 0u;
-    __syncthreads();
-    if (t < 16) blk[(size_t)B * 16 + t] = t < 8 ? (s_max[t] >= s_min[t] && !s_wide ? s_min[t] : 0) : (t == 8 ? (int32_t)s_base : 0);
-    if (i < stride) {
-        for (int k = 0; k < 8; ++k) {
-            uint16_t w = 0;
-            if (exc) w = k == 0 ? (uint16_t)before : (uint16_t)0;
-            else if (valid) w = (uint16_t)(v[k] - s_min[k]);
-            rb16[(size_t)k * stride + i] = w;
-        }
-        if (valid) flags[i] = fl;
-    }
-}
-
-// Pass 3: explicit sources of the exception nodes
-__global__ void k_fill_exceptions(const GeoParams g, const int8_t *__restrict__ solid,
-                                  const uint32_t *__restrict__ rank, uint32_t nf, size_t stride,
-                                  const uint32_t *__restrict__ lin, const uint32_t *__restrict__ flags,
-                                  const uint16_t *__restrict__ rb16, const int32_t *__restrict__ blk,
-                                  int32_t *__restrict__ exc, size_t exc_stride) {
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= nf || !(flags[r] & FL_EXCEPTION)) return;
-    const size_t idx = lin[r];
-    const int z = (int)(idx % g.nz);
-    const size_t t = idx / g.nz;
-    const int y = (int)(t % g.ny), x = (int)(t / g.ny);
-    int32_t j[18];
-    true_sources(g, solid, rank, x, y, z, j);
-    const uint32_t slot = (uint32_t)blk[(size_t)(r / 256u) * 16 + 8] + rb16[r];
-    for (int s = 0; s < 18; ++s) exc[(size_t)s * exc_stride + slot] = j[s];
-}
 
 // lbm_get_neighbor_table: expand whichever table the step kernel uses into [18][nf]
 __global__ void k_decode_table(StepArgs a, uint32_t nf, int32_t *__restrict__ out) {
@@ -777,101 +649,30 @@ int lbm_init(lbm_ctx *c) {
             c->row_count = (uint32_t)(nx * ny);
         }
     } else {
-        // compacted fluid-node list, ascending linear index (replaces the pointer SNode tree :36-44)
-        CU(c, cudaMalloc(&c->d_rank, (N + 1) * sizeof(uint32_t)));
-        auto it = thrust::make_transform_iterator((const int8_t *)c->d_solid, IsFluid());
-        size_t tmp_bytes = 0;
-        void *tmp = nullptr;
-        CU(c, cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, it, c->d_rank, N));
-        CU(c, cudaMalloc(&tmp, tmp_bytes));
-        cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, it, c->d_rank, N);
-        cudaError_t e2 = cudaDeviceSynchronize();
-        cudaFree(tmp);
-        CU(c, e);
-        CU(c, e2);
-        c->launches += 2;
-        uint32_t last_rank = 0;
-        int8_t last_solid = 1;
-        CU(c, cudaMemcpy(&last_rank, c->d_rank + (N - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost));
-        CU(c, cudaMemcpy(&last_solid, c->d_solid + (N - 1), 1, cudaMemcpyDeviceToHost));
-        c->nf = (size_t)last_rank + (last_solid == 0 ? 1 : 0);
-        const uint32_t nf32 = (uint32_t)c->nf;
-        CU(c, cudaMemcpy(c->d_rank + N, &nf32, sizeof(uint32_t), cudaMemcpyHostToDevice));
-        // planes padded to the 256-node block: the sparse kernel bulk-copies whole table slices
-        c->stride = (c->nf + 255) / 256 * 256;
-        if (c->stride == 0) c->stride = 256;
-        // the step kernel reaches the opposite population of a node as index i +- stride (int32)
-        if (c->stride >= ((size_t)1 << 30))
-            FAIL(c, LBM_ERR_INVALID, "sparse storage holds at most 2^30 fluid nodes per context (got %zu): split the domain into x-slabs", c->nf);
-        CU(c, cudaMalloc(&c->d_lin, c->stride * sizeof(uint32_t)));
-        CU(c, cudaMalloc(&c->d_flags, c->stride * sizeof(uint32_t)));
+        // compacted fluid-node list + compressed pull table (replaces the pointer SNode tree :36-44)
+        c->compressed = 1;
+        if (const char *tb = getenv("LBM3D_SPARSE_TABLE")) c->compressed = strcmp(tb, "full") == 0 ? 0 : 1;
         // L2 prefetch of the table slice this many nodes ahead: off by default (measured on B200:
         // with the 20-byte table the step runs at the DRAM copy rate without it, 87.0 % vs 85.4 %
         // of the 152-byte roofline with one wave = 148 x 8 x 256 nodes ahead)
         c->prefetch_dist = 0;
         if (const char *pd = getenv("LBM3D_PREFETCH")) c->prefetch_dist = (uint32_t)atol(pd) / 256u * 256u;
-        c->compressed = 1;
-        if (const char *tb = getenv("LBM3D_SPARSE_TABLE")) c->compressed = strcmp(tb, "full") == 0 ? 0 : 1;
-        CU(c, cudaMemset(c->d_flags, 0, c->stride * sizeof(uint32_t)));
-        CU(c, cudaMemset(c->d_lin, 0, c->stride * sizeof(uint32_t)));
-        uint32_t *d_cnt = (uint32_t *)c->d_scalar;
-        CU(c, cudaMemset(d_cnt, 0, sizeof(uint32_t)));
-        c->plane_rank.assign((size_t)nx + 1, 0);
-        CU(c, cudaMemcpy2D(c->plane_rank.data(), sizeof(uint32_t), c->d_rank, plane * sizeof(uint32_t),
-                           sizeof(uint32_t), (size_t)nx + 1, cudaMemcpyDeviceToHost));
-        if (g.halo_x) {
-            const uint32_t r[4] = {c->plane_rank[1], c->plane_rank[2], c->plane_rank[nx - 2], c->plane_rank[nx - 1]};
-            c->own_first = r[0];
-            c->own_count = r[3] - r[0];
-            c->plane_first[0] = 0; c->plane_count[0] = r[0];
-            c->plane_first[1] = r[0]; c->plane_count[1] = r[1] - r[0];
-            c->plane_first[2] = r[2]; c->plane_count[2] = r[3] - r[2];
-            c->plane_first[3] = r[3]; c->plane_count[3] = nf32 - r[3];
-        } else {
-            c->own_first = 0;
-            c->own_count = nf32;
+        SparseTables t;
+        std::string msg;
+        cudaError_t e = build_sparse_tables(g, c->d_solid, c->compressed != 0, t, msg);
+        c->launches += t.launches;
+        if (e != cudaSuccess || !msg.empty()) {
+            free_sparse_tables(t);
+            if (!msg.empty()) FAIL(c, LBM_ERR_INVALID, "%s", msg.c_str());
+            CU(c, e);
         }
-        int32_t *d_rb32 = nullptr;     // 32-bit neighbour-row ranks, only while the table is built
-        if (c->compressed) {
-            CU(c, cudaMalloc(&d_rb32, c->stride * 8 * sizeof(int32_t)));
-            CU(c, cudaMemset(d_rb32, 0, c->stride * 8 * sizeof(int32_t)));
-        } else {
-            CU(c, cudaMalloc(&c->d_nbr, c->stride * 18 * sizeof(int32_t)));
-            CU(c, cudaMemset(c->d_nbr, 0xff, c->stride * 18 * sizeof(int32_t)));
-        }
-        k_build_sparse<<<nblocks(N, 256), 256>>>(g, c->d_solid, c->d_rank, c->stride, c->d_lin,
-                                                  c->d_flags, c->d_nbr, d_rb32);
-        cudaError_t eb = cudaGetLastError();
-        if (eb != cudaSuccess) cudaFree(d_rb32);
-        CU(c, eb);
-        c->launches++;
-        if (c->compressed) {
-            const unsigned nblk = (unsigned)(c->stride / 256);
-            cudaError_t ep = cudaMalloc(&c->d_rb16, c->stride * 8 * sizeof(uint16_t));
-            if (ep == cudaSuccess) ep = cudaMalloc(&c->d_blk, (size_t)nblk * 16 * sizeof(int32_t));
-            if (ep == cudaSuccess) {
-                k_pack_table<<<nblk, 256>>>(c->own_first, c->own_first + c->own_count, c->stride, d_rb32,
-                                            c->d_flags, c->d_rb16, c->d_blk, d_cnt);
-                ep = cudaGetLastError();
-            }
-            if (ep == cudaSuccess) ep = cudaDeviceSynchronize();
-            cudaFree(d_rb32);
-            CU(c, ep);
-            c->launches++;
-            uint32_t ne = 0;
-            CU(c, cudaMemcpy(&ne, d_cnt, sizeof ne, cudaMemcpyDeviceToHost));
-            c->n_exc = ne;
-            c->exc_stride = (ne + 31) / 32 * 32 + 32;
-            CU(c, cudaMalloc(&c->d_exc, c->exc_stride * 18 * sizeof(int32_t)));
-            CU(c, cudaMemset(c->d_exc, 0xff, c->exc_stride * 18 * sizeof(int32_t)));
-            if (ne) {
-                k_fill_exceptions<<<nblocks(c->nf, 256), 256>>>(g, c->d_solid, c->d_rank, nf32, c->stride, c->d_lin,
-                                                                c->d_flags, c->d_rb16, c->d_blk, c->d_exc,
-                                                                c->exc_stride);
-                CU(c, cudaGetLastError());
-                c->launches++;
-            }
-        }
+        // the context owns the tables from here on
+        c->nf = t.nf; c->stride = t.stride; c->n_exc = t.n_exc; c->exc_stride = t.exc_stride;
+        c->d_rank = t.d_rank; c->d_lin = t.d_lin; c->d_flags = t.d_flags; c->d_nbr = t.d_nbr;
+        c->d_rb16 = t.d_rb16; c->d_blk = t.d_blk; c->d_exc = t.d_exc;
+        c->plane_rank = t.plane_rank;
+        c->own_first = t.own_first; c->own_count = t.own_count;
+        for (int i = 0; i < 4; ++i) { c->plane_first[i] = t.plane_first[i]; c->plane_count[i] = t.plane_count[i]; }
     }
     // populations (A-B), user-visible macros, pressure-BC velocities
     // guard band: the dense kernel pulls speculatively from idx -/+ (plane + row + 1)

@@ -75,6 +75,47 @@ __device__ __forceinline__ uint32_t bc_word(const GeoParams &g, const int8_t *so
     return w;
 }
 
+// bits 24..29: the node sits on a lattice face.  Without ghost planes these are the faces
+// periodic_index wraps across (:247-257); in an x-slab of the two-phase solver the x bits mark the
+// GLOBAL x faces (velocity and psi BCs, clamped psi stencil) -- the kernels never wrap x when
+// ghost planes exist.
+__device__ __forceinline__ uint32_t at_face_bits(const GeoParams &g, int x, int y, int z) {
+    uint32_t fl = 0;
+    if (!g.halo_x) {
+        if (x == 0) fl |= FL_AT_X0;
+        if (x == g.nx - 1) fl |= FL_AT_X1;
+    } else if (g.two_phase) {
+        if (x == g.xface0) fl |= FL_AT_X0;
+        if (x == g.xface1) fl |= FL_AT_X1;
+    }
+    if (y == 0) fl |= FL_AT_Y0;
+    if (y == g.ny - 1) fl |= FL_AT_Y1;
+    if (z == 0) fl |= FL_AT_Z0;
+    if (z == g.nz - 1) fl |= FL_AT_Z1;
+    return fl;
+}
+
+// two-phase: Compute_C (2phase/lbm_solver_3d_2phase.py:259-275) looks at i + e_s with
+// periodic_index_for_psi (:390-428): wrap on periodic psi faces, clamp on constant ones
+__device__ __forceinline__ uint32_t near_solid_bit(const GeoParams &g, const int8_t *solid, int x, int y, int z) {
+    const int n[3] = {g.nx, g.ny, g.nz};
+    for (int s = 1; s < 19; ++s) {
+        int q[3] = {x + c_e[s][0], y + c_e[s][1], z + c_e[s][2]};
+        for (int d = g.halo_x ? 1 : 0; d < 3; ++d) {
+            if (q[d] < 0) q[d] = g.bc_psi_type[2 * d] == 0 ? n[d] - 1 : 0;
+            if (q[d] > n[d] - 1) q[d] = g.bc_psi_type[2 * d + 1] == 0 ? 0 : n[d] - 1;
+        }
+        if (g.halo_x) {
+            // ghost planes carry the periodic images; a constant-psi GLOBAL face clamps
+            if (x == g.xface0 && q[0] < x && g.bc_psi_type[0] != 0) q[0] = x;
+            if (x == g.xface1 && q[0] > x && g.bc_psi_type[1] != 0) q[0] = x;
+            if (q[0] < 0 || q[0] > g.nx - 1) continue;      // ghost node itself: never updated
+        }
+        if (solid[((size_t)q[0] * g.ny + q[1]) * g.nz + q[2]] != 0) return FL_NEAR_SOLID;
+    }
+    return 0u;
+}
+
 __global__ void k_build_flags(const GeoParams g, const int8_t *__restrict__ solid,
                               uint32_t *__restrict__ flags, uint8_t *__restrict__ cls) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -99,41 +140,9 @@ __global__ void k_build_flags(const GeoParams g, const int8_t *__restrict__ soli
         size_t src;
         if (!pull_source(g, x, y, z, s, src) || solid[src] != 0) fl |= 1u << s;
     }
-    if (!g.halo_x) {
-        if (x == 0) fl |= FL_AT_X0;
-        if (x == g.nx - 1) fl |= FL_AT_X1;
-    } else if (g.two_phase) {
-        // x-slab of the two-phase solver: the at-face bits mark the GLOBAL x faces (velocity and
-        // psi BCs, clamped psi stencil); the kernels never wrap x when ghost planes exist
-        if (x == g.xface0) fl |= FL_AT_X0;
-        if (x == g.xface1) fl |= FL_AT_X1;
-    }
-    if (y == 0) fl |= FL_AT_Y0;
-    if (y == g.ny - 1) fl |= FL_AT_Y1;
-    if (z == 0) fl |= FL_AT_Z0;
-    if (z == g.nz - 1) fl |= FL_AT_Z1;
+    fl |= at_face_bits(g, x, y, z);
     fl |= bc_word(g, solid, x, y, z);
-    if (g.two_phase) {
-        // Compute_C (2phase/lbm_solver_3d_2phase.py:259-275) looks at i + e_s with
-        // periodic_index_for_psi (:390-428): wrap on periodic psi faces, clamp on constant ones
-        const int n[3] = {g.nx, g.ny, g.nz};
-        bool near = false;
-        for (int s = 1; s < 19; ++s) {
-            int q[3] = {x + c_e[s][0], y + c_e[s][1], z + c_e[s][2]};
-            for (int d = g.halo_x ? 1 : 0; d < 3; ++d) {
-                if (q[d] < 0) q[d] = g.bc_psi_type[2 * d] == 0 ? n[d] - 1 : 0;
-                if (q[d] > n[d] - 1) q[d] = g.bc_psi_type[2 * d + 1] == 0 ? 0 : n[d] - 1;
-            }
-            if (g.halo_x) {
-                // ghost planes carry the periodic images; a constant-psi GLOBAL face clamps
-                if (x == g.xface0 && q[0] < x && g.bc_psi_type[0] != 0) q[0] = x;
-                if (x == g.xface1 && q[0] > x && g.bc_psi_type[1] != 0) q[0] = x;
-                if (q[0] < 0 || q[0] > g.nx - 1) continue;      // ghost node itself: never updated
-            }
-            if (solid[((size_t)q[0] * g.ny + q[1]) * g.nz + q[2]] != 0) near = true;
-        }
-        if (near) fl |= FL_NEAR_SOLID;
-    }
+    if (g.two_phase) fl |= near_solid_bit(g, solid, x, y, z);
     flags[idx] = fl;
     cls[idx] = fl == 0 ? NODE_BULK : NODE_SPECIAL;
 }

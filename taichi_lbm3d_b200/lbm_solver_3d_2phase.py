@@ -39,8 +39,11 @@ class _Field2:
 
 
 class LB3D_Solver_Two_Phase:
-    def __init__(self, nx, ny, nz, strict=False, device=None):
+    def __init__(self, nx, ny, nz, strict=False, device=None, sparse_storage=False):
         self.nx, self.ny, self.nz = nx, ny, nz
+        # compact fluid-node list instead of the full lattice: what the reference's second script,
+        # 2phase/lbm_solver_3d_2phase_sparse.py, does with a pointer SNode tree
+        self.sparse_storage = bool(sparse_storage)
         # script globals, same names and defaults (2phase/lbm_solver_3d_2phase.py:18-39)
         self.fx, self.fy, self.fz = 5.0e-5, -2e-5, 0.0
         self.niu_l = 0.1
@@ -103,8 +106,8 @@ class LB3D_Solver_Two_Phase:
         return self._solid_host, self._psi_host
 
     def _config_flags(self):
-        """lbm2p_config.reserved: 0 for a whole lattice (x-slabs override this, multi_gpu.py)"""
-        return 0
+        """lbm2p_config.reserved: storage flag of a whole lattice (x-slabs override this, multi_gpu.py)"""
+        return 8 if self.sparse_storage else 0           # LBM2P_SPARSE
 
     # ---- static_init + init :205-228, :173-186 -----------------------------------------------------
     def init_simulation(self):

@@ -33,9 +33,9 @@ class Case2P:
         o.init_simulation()
         return o
 
-    def make_solver(self, strict=False):
+    def make_solver(self, strict=False, sparse=False):
         from taichi_lbm3d_b200 import LB3D_Solver_Two_Phase
-        lb = LB3D_Solver_Two_Phase(*self.shape, strict=strict)
+        lb = LB3D_Solver_Two_Phase(*self.shape, strict=strict, sparse_storage=sparse)
         lb.solid.from_numpy(self.solid)
         lb.psi.from_numpy(self.psi)
         lb.set_force(self.force)

@@ -22,10 +22,11 @@ def _oracle(case, steps, **kw):
 
 @pytest.mark.parametrize("make", CASES)
 @pytest.mark.parametrize("steps", [1, 2, 20])
-def test_strict_bit_identical(cuda, make, steps):
+@pytest.mark.parametrize("sparse", [False, True])
+def test_strict_bit_identical(cuda, make, steps, sparse):
     case = make()
     o = _oracle(case, steps)
-    lb = case.make_solver(strict=True)
+    lb = case.make_solver(strict=True, sparse=sparse)
     lb.run(steps)
     fl = case.solid == 0
     for n in FIELDS:
@@ -44,13 +45,14 @@ def _yardstick(o32, o64, name, fl):
 
 
 @pytest.mark.parametrize("make", CASES)
-def test_fast_parity(cuda, make):
+@pytest.mark.parametrize("sparse", [False, True])
+def test_fast_parity(cuda, make, sparse):
     case = make()
     fl = case.solid == 0
     # short horizon: plain 1e-5 relative L-inf on everything but v
     o = _oracle(case, 50)
     o64 = _oracle(case, 50, dtype=np.float64)
-    lb = case.make_solver()
+    lb = case.make_solver(sparse=sparse)
     lb.run(50)
     for n in ("F", "rho", "psi", "rho_r", "rho_b"):
         assert rel_linf(getattr(lb, n).to_numpy()[fl], getattr(o, n)[fl]) <= TOL, n
@@ -65,10 +67,11 @@ def test_fast_parity(cuda, make):
         assert d <= _yardstick(o, o64, n, fl), (n, d)
 
 
-def test_step_equals_run_and_restart(cuda):
+@pytest.mark.parametrize("sparse", [False, True])
+def test_step_equals_run_and_restart(cuda, sparse):
     case = cases2p.case_drainage()
     o = _oracle(case, 9)
-    lb = case.make_solver(strict=True)
+    lb = case.make_solver(strict=True, sparse=sparse)
     for i in range(5):
         lb.step()
         if i == 2:
@@ -100,7 +103,8 @@ def test_drainage_131_properties(cuda):
     assert abs((rr + rb)[fl].mean() - 1.0) < 1e-3
 
 
-def test_config4_131_against_oracle(cuda):
+@pytest.mark.parametrize("sparse", [False, True])
+def test_config4_131_against_oracle(cuda, sparse):
     """BASELINE config 4 at full size (131^3 stand-in, README parameters niu_l=0.05, niu_g=0.2,
     CapA=0.005, psi_solid=0.7, constant psi=-1 on x0, force (5e-5,-2e-5,0)): 40 steps against
     the C oracle, production arithmetic 1e-5, verification arithmetic bit-identical."""
@@ -111,11 +115,11 @@ def test_config4_131_against_oracle(cuda):
     case = cases2p.Case2P("cfg4", solid, psi, niu_l=0.05, niu_g=0.2, CapA=0.005, psi_solid=0.7)
     o = _oracle(case, 40)
     fl = solid == 0
-    lb = case.make_solver(strict=True)
+    lb = case.make_solver(strict=True, sparse=sparse)
     lb.run(40)
     for n in FIELDS:
         assert np.array_equal(getattr(lb, n).to_numpy()[fl], getattr(o, n)[fl]), n
-    lbf = case.make_solver()
+    lbf = case.make_solver(sparse=sparse)
     lbf.run(40)
     for n in ("F", "rho", "psi", "rho_r", "rho_b"):
         assert rel_linf(getattr(lbf, n).to_numpy()[fl], getattr(o, n)[fl]) <= TOL, n
