@@ -50,6 +50,13 @@ def main():
     psi[:13] = -1.0
     out.append(run("drainage 131^3 sphere-pack stand-in (config 4 parameters), dense storage", solid, psi))
     out.append(run("drainage 131^3 sphere-pack stand-in (config 4 parameters), sparse storage", solid, psi, sparse=True))
+    from taichi_lbm3d_b200.geometry import sphere_pack
+    n = 384
+    solid = sphere_pack(n, n, n, 0.80, 6.0, 12.0, seed=n, periodic=True)
+    psi = np.ones(solid.shape, np.float32)
+    psi[:n // 4] = -1.0
+    out.append(run("drainage %d^3 periodic sphere pack (porosity 0.2), sparse storage" % n, solid, psi,
+                   steps=100, warmup=10, sparse=True))
     n = 256
     x, y, z = np.meshgrid(*[np.arange(n)] * 3, indexing='ij')
     r = np.sqrt((x - n / 2) ** 2 + (y - n / 2) ** 2 + (z - n / 2) ** 2)

@@ -74,6 +74,8 @@ struct lbm2p_ctx {
     int comm_world = 1, comm_rank = 0;
     bool comm_ready = false;
     float *d_send[2] = {nullptr, nullptr}, *d_recv[2] = {nullptr, nullptr};
+    cudaStream_t comm_stream = nullptr;    // highest priority: the exchanges run beside the interior kernels
+    cudaEvent_t ev_cb = nullptr, ev_xb = nullptr, ev_mb = nullptr, ev_xa = nullptr;
 };
 
 #define CTX2(ctx)                                                                              \
@@ -364,6 +366,9 @@ int lbm2p_destroy(lbm2p_ctx *c) {
     cudaDeviceSynchronize();
     if (c->comm && g_nccl.ok) g_nccl.CommDestroy(c->comm);
     for (int i = 0; i < 2; ++i) { cudaFree(c->d_send[i]); cudaFree(c->d_recv[i]); }
+    if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
+    for (cudaEvent_t ev : {c->ev_cb, c->ev_xb, c->ev_mb, c->ev_xa})
+        if (ev) cudaEventDestroy(ev);
     free2(c);
     cudaFree(c->d_solid);
     cudaFree(c->d_psi0);
@@ -770,6 +775,13 @@ int lbm2p_comm_init(lbm2p_ctx *c, const void *id128, int world, int rank) {
         if (!c->d_send[i]) CU2(c, cudaMalloc(&c->d_send[i], halo_floats(c, 0) * sizeof(float)));
         if (!c->d_recv[i]) CU2(c, cudaMalloc(&c->d_recv[i], halo_floats(c, 0) * sizeof(float)));
     }
+    if (!c->comm_stream) {
+        int lo = 0, hi = 0;
+        CU2(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU2(c, cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, hi));
+        for (cudaEvent_t *ev : {&c->ev_cb, &c->ev_xb, &c->ev_mb, &c->ev_xa})
+            CU2(c, cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+    }
     c->comm_ready = true;
     return 0;
 }
@@ -784,7 +796,27 @@ int lbm2p_comm_unique_id(void *out128) {
     return 0;
 }
 
-// nsteps iterations of the main loop :626-632 on one x-slab, halo exchanges inside
+// colour pass (kind 0) or main pass (kind 1) over the planes [x0, x1) of the slab
+static int launch_planes2(lbm2p_ctx *c, int kind, int x0, int x1, cudaStream_t st) {
+    if (x1 <= x0) return 0;
+    Step2Args A;
+    fill2(c, A, c->d_f[c->cur], kind ? c->d_f[c->cur ^ 1] : nullptr);
+    A.a.row_first = (uint32_t)(x0 * c->cfg.ny);
+    A.a.row_count = (uint32_t)((x1 - x0) * c->cfg.ny);
+    return kind ? launch_main2(c, MODE_STEP, A, st) : launch_colour2(c, A, st);
+}
+
+// nsteps iterations of the main loop :626-632 on one x-slab, halo exchanges inside.
+// Default: colour ; exchange(psi) ; main ; exchange(f*, records) on one stream.
+// LBM3D_2P_OVERLAP=1 (EXPERIMENTAL, off by default): boundary planes first, their exchange on a
+// highest-priority side stream while the interior planes are updated.  Bit-identical in the ring
+// of one and over NCCL on 2 B200 at 96x64x64, but the 2-GPU run at 256x256x256 did not finish
+// (suspected interaction of two NCCL groups per step with the saturating interior kernels), so it
+// is not enabled:
+//   main stream  colour(interior) . wait XA' . colour(boundary) . main(interior) . wait XB . main(boundary) ...
+//   side stream                                  XB = exchange(psi)                XA = exchange(f*, records)
+// (XA' = the exchange of the previous step; the colour pass of interior planes only reads records
+// of owned planes, so it runs beside it).
 int lbm2p_run_slab(lbm2p_ctx *c, int nsteps, void *cuda_stream) {
     CTX2(c);
     if (!c->inited || !c->halo) FAIL2(c, -4, "needs an initialised x-slab context");
@@ -800,16 +832,62 @@ int lbm2p_run_slab(lbm2p_ctx *c, int nsteps, void *cuda_stream) {
         if (r) return r;
         nsteps -= 1;
     }
-    for (int it = 0; it < nsteps; ++it) {
-        int r = stage2(c, 1, st);                  // rho_r, rho_b, psi of the step just collided
-        if (r < 0) return r;
-        r = exchange2(c, 1, st);                   // psi of the boundary planes -> neighbours' ghosts
-        if (r) return r;
-        r = stage2(c, 2, st);                      // stream/BC/macro + next collision
-        if (r < 0) return r;
-        r = exchange2(c, 0, st);                   // f* (5 + 5 populations) and colour records
-        if (r) return r;
+    const int nx = c->cfg.nx, own = nx - 2;
+    static const bool want_overlap = getenv("LBM3D_2P_OVERLAP") ? atoi(getenv("LBM3D_2P_OVERLAP")) != 0 : false;
+    if (!want_overlap || own < 3) {
+        for (int it = 0; it < nsteps; ++it) {
+            int r = stage2(c, 1, st);                  // rho_r, rho_b, psi of the step just collided
+            if (r < 0) return r;
+            r = exchange2(c, 1, st);                   // psi of the boundary planes -> neighbours' ghosts
+            if (r) return r;
+            r = stage2(c, 2, st);                      // stream/BC/macro + next collision
+            if (r < 0) return r;
+            r = exchange2(c, 0, st);                   // f* (5 + 5 populations) and colour records
+            if (r) return r;
+        }
+        return 0;
     }
+    bool xa_pending = false;
+    for (int it = 0; it < nsteps; ++it) {
+        int r = 0;
+        if (!c->colour_valid) {
+            r = launch_planes2(c, 0, 2, nx - 2, st);                       // colour, interior planes
+            if (r) return r;
+            if (xa_pending) CU2(c, cudaStreamWaitEvent(st, c->ev_xa, 0));  // ghost records have arrived
+            xa_pending = false;
+            r = launch_planes2(c, 0, 1, 2, st);                            // colour, boundary planes
+            if (r) return r;
+            r = launch_planes2(c, 0, nx - 2, nx - 1, st);
+            if (r) return r;
+            c->colour_valid = true;
+        } else if (xa_pending) {
+            CU2(c, cudaStreamWaitEvent(st, c->ev_xa, 0));
+            xa_pending = false;
+        }
+        CU2(c, cudaEventRecord(c->ev_cb, st));
+        CU2(c, cudaStreamWaitEvent(c->comm_stream, c->ev_cb, 0));
+        r = exchange2(c, 1, c->comm_stream);                               // XB: psi
+        if (r) return r;
+        CU2(c, cudaEventRecord(c->ev_xb, c->comm_stream));
+        r = launch_planes2(c, 1, 2, nx - 2, st);                           // main, interior planes
+        if (r) return r;
+        CU2(c, cudaStreamWaitEvent(st, c->ev_xb, 0));                      // ghost psi has arrived
+        r = launch_planes2(c, 1, 1, 2, st);                                // main, boundary planes
+        if (r) return r;
+        r = launch_planes2(c, 1, nx - 2, nx - 1, st);
+        if (r) return r;
+        c->cur ^= 1;
+        c->colour_valid = false;
+        c->macro_valid = false;
+        c->F_valid = false;
+        CU2(c, cudaEventRecord(c->ev_mb, st));
+        CU2(c, cudaStreamWaitEvent(c->comm_stream, c->ev_mb, 0));
+        r = exchange2(c, 0, c->comm_stream);                               // XA: f*, colour records
+        if (r) return r;
+        CU2(c, cudaEventRecord(c->ev_xa, c->comm_stream));
+        xa_pending = true;
+    }
+    if (xa_pending) CU2(c, cudaStreamWaitEvent(st, c->ev_xa, 0));
     return 0;
 }
 

@@ -152,7 +152,7 @@ struct SparseTables {
     size_t nf = 0, stride = 0, n_exc = 0, exc_stride = 0;
     uint32_t own_first = 0, own_count = 0;                 // node range a step updates
     uint32_t plane_first[4] = {0, 0, 0, 0}, plane_count[4] = {0, 0, 0, 0};   // halo planes (x-slab)
-    uint32_t *d_rank = nullptr;    // [N+1] exclusive fluid count
+    uint32_t *d_rank = nullptr;    // [N+1] exclusive fluid count (freed once the tables exist)
     uint32_t *d_lin = nullptr;     // [stride] linear index of each stored node
     uint32_t *d_flags = nullptr;   // [stride] link word
     int32_t *d_nbr = nullptr;      // full table [18][stride] (only when !compressed)
@@ -274,6 +274,8 @@ inline cudaError_t build_sparse_tables(const GeoParams &g, const int8_t *d_solid
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     cudaFree(d_rb32);
     cudaFree(d_cnt);
+    cudaFree(t.d_rank);            // 4 B per LATTICE node, only needed while the tables are built
+    t.d_rank = nullptr;
     return e;
 #undef SB_CU
 }
