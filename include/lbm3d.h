@@ -57,7 +57,10 @@ typedef struct {
                                 steps pull through the table and store back into the pulled
                                 locations, even steps are purely local -- half the memory and
                                 the table is read every other step.  Falls back to 1 with
-                                halo_x (slab exchange needs both buffers) */
+                                halo_x (slab exchange needs both buffers);
+                             3: the dense lattice of mode 0 stepped IN PLACE the same way (half
+                                the memory: 1024^3 fits one 180 GB B200).  Falls back to 0 with
+                                halo_x */
     int32_t strict;       /* 0: factored MRT transform, FMA allowed (production);
                              1: oracle evaluation order, no FMA contraction -> bit-identical
                                 to oracle/ref_single_phase.c (verification mode) */

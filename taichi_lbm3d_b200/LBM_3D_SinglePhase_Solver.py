@@ -71,8 +71,8 @@ class LB3D_Solver_Single_Phase:
         # reference :13-28
         self.enable_projection = True
         self.sparse_storage = sparse_storage
-        # sparse storage only: step IN PLACE on one population buffer (AA pattern: half the
-        # memory, 82 % instead of 87 % of the HBM roofline on B200); default from LBM3D_AA
+        # step IN PLACE on one population buffer (AA pattern): half the memory; sparse storage
+        # 82 % instead of 87 % of the HBM roofline on B200; default from LBM3D_AA
         self.in_place = in_place
         self.nx, self.ny, self.nz = nx, ny, nz
         self.fx, self.fy, self.fz = 0.0e-6, 0.0, 0.0
@@ -196,7 +196,7 @@ class LB3D_Solver_Single_Phase:
         dev = torch.cuda.current_device() if self.device is None else torch.device(self.device).index or 0
         import os
         in_place = os.environ.get("LBM3D_AA", "0") == "1" if self.in_place is None else bool(self.in_place)
-        mode = 0 if not self.sparse_storage else (2 if in_place else 1)
+        mode = (3 if in_place else 0) if not self.sparse_storage else (2 if in_place else 1)
         return _lib.LbmConfig(nx=self.nx, ny=self.ny, nz=self.nz, sparse=mode,
                               strict=int(self.strict), halo_x=0, device=int(dev), x_face_mask=0)
 

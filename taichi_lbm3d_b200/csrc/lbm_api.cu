@@ -83,7 +83,8 @@ struct lbm_ctx {
     bool ffm_pending = false;
     size_t ff_stride = 0;
     // state machine
-    bool aa = false;             // sparse in-place (AA-pattern) stepping on one buffer
+    bool dense_aa = false;       // cfg.sparse == 3: dense lattice stepped in place
+    bool aa = false;             // in-place (AA-pattern) stepping on one buffer
     int parity = 0;              // aa: 0 = natural layout, 1 = arrival layout (see lbm_kernels.cuh)
     int cur = 0;
     bool pipe_valid = false;     // d_f[cur] holds f* of the current step
@@ -413,6 +414,10 @@ int lbm_create(const lbm_config *cfg, lbm_ctx **out) {
     if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return LBM_ERR_CUDA; }
     lbm_ctx *c = new lbm_ctx();
     c->cfg = *cfg;
+    if (cfg->sparse == 3) {          // dense storage, one population buffer
+        c->dense_aa = true;
+        c->cfg.sparse = 0;
+    }
     c->N = N;
     if (const char *b = getenv("LBM3D_BLOCK")) {
         int v = atoi(b);
@@ -684,7 +689,7 @@ int lbm_init(lbm_ctx *c) {
         c->pad = (((size_t)ny + 1) * c->prow + 2 + 31) / 32 * 32;
     }
     const size_t fbytes = (c->fsize + 2 * c->pad) * sizeof(float);
-    c->aa = c->cfg.sparse == 2 && c->compressed && !c->cfg.halo_x;
+    c->aa = ((c->cfg.sparse == 2 && c->compressed) || c->dense_aa) && !c->cfg.halo_x;
     c->parity = 0;
     for (int b = 0; b < (c->aa ? 1 : 2); ++b) {
         CU(c, cudaMalloc(&c->d_fbase[b], fbytes));
@@ -1052,7 +1057,7 @@ int lbm_step_begin(lbm_ctx *c, void *cuda_stream) {
 int lbm_step_planes(lbm_ctx *c, int x_begin, int x_end, void *cuda_stream) {
     CTX_CHECK(c);
     if (!c->inited || !c->pipe_valid) FAIL(c, LBM_ERR_STATE, "pipeline not started");
-    if (c->aa) FAIL(c, LBM_ERR_STATE, "plane-wise stepping needs two buffers (create the context with sparse = 1)");
+    if (c->aa) FAIL(c, LBM_ERR_STATE, "plane-wise stepping needs two buffers (create the context with sparse = 0 or 1)");
     const int lo = c->cfg.halo_x ? 1 : 0, hi = c->cfg.halo_x ? c->cfg.nx - 1 : c->cfg.nx;
     if (x_begin < lo || x_end > hi || x_begin > x_end) FAIL(c, LBM_ERR_INVALID, "plane range outside the owned slab");
     CU(c, cudaSetDevice(c->cfg.device));

@@ -264,6 +264,122 @@ __global__ void __launch_bounds__(256) k_dense(const StepArgs a) {
     for (int s = 0; s < 19; ++s) a.pout[s][pidx] = f[s];
 }
 
+// Dense lattice stepped IN PLACE on one buffer (AA pattern, lbm_config.sparse = 3): the same two
+// alternating steps as the sparse in-place mode (lbm_kernels.cuh).  ODD: pull like k_dense
+// (speculative, special nodes re-fetch), then store f*_{LR[s]} back into the very location
+// direction s was pulled from -- neighbour slot, own opposite slot (bounce-back) or wrapped slot;
+// every location is read and written by exactly one thread.  EVEN: everything a node needs sits
+// in its own 19 slots (F_q = slot LR[q]); natural layout again afterwards.  Solid nodes never
+// store: a sector written here was read in the same launch, so a partial write merges in L2.
+template <int FORCE, int MODE, int AA>
+__global__ void __launch_bounds__(256) k_dense_aa(const StepArgs a) {
+    const uint32_t z = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t r = (blockIdx.z * gridDim.y + blockIdx.y) * blockDim.y + threadIdx.y;
+    if (z >= (uint32_t)a.nz || r >= a.row_count) return;
+    const uint32_t row = a.row_first + r;
+    const uint32_t idx = row * (uint32_t)a.nz + z;
+    const uint32_t pidx = row * a.prow + z;
+    float f[19];
+    const uint8_t cls = a.cls[idx];
+    if (AA == AA_EVEN) {
+#define X(s, ex, ey, ez, o) f[s] = __ldg(a.pown[o] + pidx);
+        D3Q19_DIRS(X)
+#undef X
+    } else {
+#define X(s, ex, ey, ez, o) f[s] = __ldg(a.ppull[s] + pidx);
+        D3Q19_DIRS(X)
+#undef X
+    }
+    if (cls == NODE_SOLID || cls == NODE_SOLID_WRITE) return;
+    uint32_t fl = 0;
+    int oxm = 0, oxp = 0, oym = 0, oyp = 0, ozm = 0, ozp = 0;
+    bool pressure = false;
+    uint32_t slot = 0;
+#define OFF(ex, ey, ez)                                                                        \
+    ((ex > 0 ? oxm : (ex < 0 ? oxp : 0)) + (ey > 0 ? oym : (ey < 0 ? oyp : 0)) +               \
+     (ez > 0 ? ozm : (ez < 0 ? ozp : 0)))
+#define WRAPS(ex, ey, ez)                                                                      \
+    (fl & ((ex > 0 ? FL_AT_X0 : (ex < 0 ? FL_AT_X1 : 0u)) | (ey > 0 ? FL_AT_Y0 : (ey < 0 ? FL_AT_Y1 : 0u)) | \
+           (ez > 0 ? FL_AT_Z0 : (ez < 0 ? FL_AT_Z1 : 0u))))
+    if (cls == NODE_SPECIAL) {
+        fl = a.flags[idx];
+        if (AA == AA_ODD) {
+            const int sx = a.ny * (int)a.prow, sy = (int)a.prow;
+            oxm = (fl & FL_AT_X0) ? (a.nx - 1) * sx : -sx;
+            oxp = (fl & FL_AT_X1) ? -(a.nx - 1) * sx : sx;
+            oym = (fl & FL_AT_Y0) ? (a.ny - 1) * sy : -sy;
+            oyp = (fl & FL_AT_Y1) ? -(a.ny - 1) * sy : sy;
+            ozm = (fl & FL_AT_Z0) ? (a.nz - 1) : -1;
+            ozp = (fl & FL_AT_Z1) ? -(a.nz - 1) : 1;
+#define X(s, ex, ey, ez, o)                                                                    \
+    if (s > 0) {                                                                               \
+        if ((fl >> s) & 1u) f[s] = __ldg(a.pown[o] + pidx);                                    \
+        else if (WRAPS(ex, ey, ez)) f[s] = __ldg(a.pown[s] + (pidx + OFF(ex, ey, ez)));        \
+    }
+            D3Q19_DIRS(X)
+#undef X
+        }
+        if (a.has_bc) {
+            const uint32_t bc = (fl >> FL_BC_SHIFT) & FL_BC_MASK;
+            if (bc) {
+                const int face = (int)bc - 1;
+                const int type = a.P.bc_type[face];
+                if (type == 1) {                  // :274-281  F = feq(rho_bc, v_prev)
+                    float u0 = 0.f, u1 = 0.f, u2 = 0.f;
+                    slot = vbc_slot(a, face, idx);
+                    if (!(fl & FL_PIN_SOLID)) {
+                        u0 = a.vbc[3 * (size_t)slot + 0];
+                        u1 = a.vbc[3 * (size_t)slot + 1];
+                        u2 = a.vbc[3 * (size_t)slot + 2];
+                    }
+                    feq_all(f, a.P.bc_rho[face], u0, u1, u2);
+                    pressure = true;
+                } else if (type == 2) {           // :283-288  F = feq(1, bc_vel)
+                    feq_all(f, 1.0f, a.P.bc_vel[face][0], a.P.bc_vel[face][1], a.P.bc_vel[face][2]);
+                }
+            }
+        }
+    }
+    float rho, ux, uy, uz;
+    float frc[3];
+    macro_force<FORCE>(a, idx, frc);
+    macro(f, frc, FORCE != 0, rho, ux, uy, uz);
+    if (MODE == MODE_EXTRACT) {
+        write_user_fields<MODE>(a, idx, f, rho, ux, uy, uz);
+        return;
+    }
+    if (pressure) {
+        a.vbc[3 * (size_t)slot + 0] = ux;
+        a.vbc[3 * (size_t)slot + 1] = uy;
+        a.vbc[3 * (size_t)slot + 2] = uz;
+    }
+    if (FORCE == 3) local_force<FORCE>(a, idx, frc);
+    collide(f, a.P, frc, FORCE != 0, rho, ux, uy, uz);
+    if (AA == AA_EVEN) {
+#pragma unroll
+        for (int s = 0; s < 19; ++s) a.pout[s][pidx] = f[s];
+        return;
+    }
+    // ODD: back into the pulled locations (pown and pout are the same buffer)
+    a.pout[0][pidx] = f[0];
+    if (cls != NODE_SPECIAL) {
+#define X(s, ex, ey, ez, o) if (s > 0) const_cast<float *>(a.ppull[s])[pidx] = f[o];
+        D3Q19_DIRS(X)
+#undef X
+    } else {
+#define X(s, ex, ey, ez, o)                                                                    \
+    if (s > 0) {                                                                               \
+        if ((fl >> s) & 1u) a.pout[o][pidx] = f[o];                                            \
+        else if (WRAPS(ex, ey, ez)) a.pout[s][pidx + OFF(ex, ey, ez)] = f[o];                  \
+        else const_cast<float *>(a.ppull[s])[pidx] = f[o];                                     \
+    }
+        D3Q19_DIRS(X)
+#undef X
+    }
+#undef WRAPS
+#undef OFF
+}
+
 // ---------------------------------------------------------------------------------------------
 // sparse storage: compacted fluid list + 18-neighbour pull table
 // ---------------------------------------------------------------------------------------------
@@ -406,6 +522,13 @@ static void launch_dense_t(const StepArgs &a, int block, cudaStream_t st) {
     const unsigned rg = (a.row_count + by - 1) / by;
     const unsigned gy = rg < 32768u ? rg : 32768u;
     dim3 grid((a.nz + bx - 1) / bx, gy, (rg + gy - 1) / gy);
+    if (a.aa != AA_OFF && MODE != MODE_COLLIDE) {
+        if (a.aa == AA_ODD)
+            k_dense_aa<FORCE, MODE == MODE_COLLIDE ? MODE_STEP : MODE, AA_ODD><<<grid, blk, 0, st>>>(a);
+        else
+            k_dense_aa<FORCE, MODE == MODE_COLLIDE ? MODE_STEP : MODE, AA_EVEN><<<grid, blk, 0, st>>>(a);
+        return;
+    }
     if (a.spec)
         k_dense<FORCE, MODE, true><<<grid, blk, 0, st>>>(a);
     else

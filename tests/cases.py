@@ -50,10 +50,12 @@ class Case:
 
     # ---- CUDA solver -----------------------------------------------------------------------
     def make_solver(self, sparse=False, strict=False):
-        """sparse: False (dense), True (compact list, two buffers), "aa" (compact list, in place)"""
+        """sparse: False (dense), True (compact list, two buffers), "aa" (compact list, in place),
+        "daa" (dense, in place)"""
         from taichi_lbm3d_b200 import LB3D_Solver_Single_Phase
-        lb = LB3D_Solver_Single_Phase(*self.shape, sparse_storage=bool(sparse), strict=strict,
-                                      tau_mode=self.tau_mode, in_place=(sparse == "aa"), guo_mode=self.guo_mode)
+        lb = LB3D_Solver_Single_Phase(*self.shape, sparse_storage=sparse in (True, "aa"), strict=strict,
+                                      tau_mode=self.tau_mode, in_place=sparse in ("aa", "daa"),
+                                      guo_mode=self.guo_mode)
         lb.solid.from_numpy(self.solid)
         for face, kind, val in self.bc:
             getattr(lb, (FACE_SETTERS_RHO if kind == "rho" else FACE_SETTERS_VEL)[face])(val)

@@ -79,7 +79,7 @@ CASES = [cases.case_mixed_bc, cases.case_periodic_force, cases.case_all_faces, c
 
 
 @pytest.mark.parametrize("make", CASES)
-@pytest.mark.parametrize("sparse", [False, True, "aa"])
+@pytest.mark.parametrize("sparse", [False, True, "aa", "daa"])
 @pytest.mark.parametrize("steps", [1, 2, 25])
 def test_strict_bit_identical(cuda, make, sparse, steps):
     case = make()
@@ -89,7 +89,7 @@ def test_strict_bit_identical(cuda, make, sparse, steps):
 
 
 @pytest.mark.parametrize("make", CASES)
-@pytest.mark.parametrize("sparse", [False, True, "aa"])
+@pytest.mark.parametrize("sparse", [False, True, "aa", "daa"])
 def test_fast_parity_small(cuda, make, sparse):
     case = make()
     o, o0 = _oracle(case, 200)
@@ -208,7 +208,7 @@ def test_wide_table_blocks_bit_identical(cuda, sparse):
     _compare(lb, o, exact=True)
 
 
-@pytest.mark.parametrize("sparse", [False, True, "aa"])
+@pytest.mark.parametrize("sparse", [False, True, "aa", "daa"])
 def test_force_field_replaced_between_steps(cuda, sparse):
     """the per-node force array (cal_local_force override point :217-220) may change between
     steps (buoyancy follows the temperature field in the solute solver) and be switched off"""
@@ -271,6 +271,9 @@ def test_full_size_properties_256(cuda):
     lba = case.make_solver(sparse="aa")                  # in place == two buffers, bit for bit
     lba.run(100)
     assert np.array_equal(lba.v.to_numpy(), lbs.v.to_numpy())
+    lbda = case.make_solver(sparse="daa")                # dense in place == dense two buffers
+    lbda.run(100)
+    assert np.array_equal(lbda.v.to_numpy(), v) and np.array_equal(lbda.rho.to_numpy(), rho)
 
 
 def test_full_size_properties_config3(cuda):
@@ -340,7 +343,7 @@ EDGE_SHAPES = [(1, 4, 5), (2, 2, 2), (3, 1, 40), (5, 3, 33), (4, 6, 1)]
 
 
 @pytest.mark.parametrize("shape", EDGE_SHAPES)
-@pytest.mark.parametrize("sparse", [False, True, "aa"])
+@pytest.mark.parametrize("sparse", [False, True, "aa", "daa"])
 def test_degenerate_extents(cuda, shape, sparse):
     """extents of 1 or 2 make periodic_index wrap a node onto itself or onto the same neighbour
     twice (:247-257); rows shorter / longer than a warp; all against the oracle, bit for bit"""
@@ -354,7 +357,7 @@ def test_degenerate_extents(cuda, shape, sparse):
     _compare(lb, o, exact=True)
 
 
-@pytest.mark.parametrize("sparse", [False, True, "aa"])
+@pytest.mark.parametrize("sparse", [False, True, "aa", "daa"])
 def test_all_solid_and_single_fluid_node(cuda, sparse):
     """empty fluid set, and one fluid node enclosed by solid (every link bounces back)"""
     from taichi_lbm3d_b200.constants import W
@@ -372,7 +375,7 @@ def test_all_solid_and_single_fluid_node(cuda, sparse):
     lb.run(5)
     _compare(lb, o, exact=True)
     assert lb.num_fluid() == 1
-    if sparse:
+    if sparse in (True, "aa"):
         assert np.all(lb.neighbor_table() == -1)
     # mass of the enclosed node is conserved up to the reference's Guo mass sink (moment 0)
     assert abs(lb.F.to_numpy()[2, 2, 3].sum() - o.F[2, 2, 3].sum()) == 0.0
