@@ -810,9 +810,9 @@ static int launch_planes2(lbm2p_ctx *c, int kind, int x0, int x1, cudaStream_t s
 // Default: colour ; exchange(psi) ; main ; exchange(f*, records) on one stream.
 // LBM3D_2P_OVERLAP=1 (EXPERIMENTAL, off by default): boundary planes first, their exchange on a
 // highest-priority side stream while the interior planes are updated.  Bit-identical in the ring
-// of one and over NCCL on 2 B200 at 96x64x64, but the 2-GPU run at 256x256x256 did not finish
-// (suspected interaction of two NCCL groups per step with the saturating interior kernels), so it
-// is not enabled:
+// of one and over NCCL on 2 B200, +13 % at 2 x 128 x 256^2 as the first solver of a process, but it
+// hangs at that size when other slab solvers / communicators were used earlier in the same
+// process (scripts/multi_gpu_check_2p.py), so it is not enabled:
 //   main stream  colour(interior) . wait XA' . colour(boundary) . main(interior) . wait XB . main(boundary) ...
 //   side stream                                  XB = exchange(psi)                XA = exchange(f*, records)
 // (XA' = the exchange of the previous step; the colour pass of interior planes only reads records
@@ -848,8 +848,11 @@ int lbm2p_run_slab(lbm2p_ctx *c, int nsteps, void *cuda_stream) {
         return 0;
     }
     bool xa_pending = false;
+    static const int sync_every = getenv("LBM3D_2P_SYNC_EVERY") ? atoi(getenv("LBM3D_2P_SYNC_EVERY")) : 0;
     for (int it = 0; it < nsteps; ++it) {
         int r = 0;
+        // optional bound on how far the host runs ahead of the two streams
+        if (sync_every > 0 && it > 0 && it % sync_every == 0) CU2(c, cudaStreamSynchronize(c->comm_stream));
         if (!c->colour_valid) {
             r = launch_planes2(c, 0, 2, nx - 2, st);                       // colour, interior planes
             if (r) return r;
