@@ -97,6 +97,31 @@ def test_fast_parity_small(cuda, make, sparse):
     _compare(lb, o, False, case, 200)
 
 
+GOLDEN = {"mixed_bc": cases.case_mixed_bc, "all_faces": cases.case_all_faces,
+          "periodic_force": cases.case_periodic_force, "force_field": cases.case_force_field,
+          "other_copy": cases.case_other_copy}
+
+
+@pytest.mark.parametrize("name", sorted(GOLDEN))
+@pytest.mark.parametrize("sparse", [False, True, "aa", "daa"])
+def test_committed_golden_vectors(cuda, name, sparse):
+    """verification arithmetic against the committed fixtures (tests/golden/sp_*.npz): start state
+    and result after `steps` steps, bit for bit, without running the oracle"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "sp_%s.npz" % name))
+    case = GOLDEN[name]()
+    assert np.array_equal(case.solid, g["solid"])
+    lb = case.make_solver(sparse=sparse, strict=True)
+    lb.F.from_numpy(g["F0"])
+    lb.rho.from_numpy(g["rho0"])
+    lb.v.from_numpy(g["v0"])
+    lb.run(int(g["steps"]))
+    fl = case.solid == 0
+    assert np.array_equal(lb.F.to_numpy()[fl], g["F"][fl])
+    assert np.array_equal(lb.rho.to_numpy()[fl], g["rho"][fl])
+    assert np.array_equal(lb.v.to_numpy()[fl], g["v"][fl])
+
+
 def test_step_by_step_equals_run(cuda):
     """step() x n, with field reads in between, equals run(n) (state machine, :477-481)."""
     case = cases.case_mixed_bc()

@@ -36,6 +36,21 @@ def test_strict_bit_identical(cuda, make, steps, sparse):
     assert np.array_equal(lb.psi.to_numpy()[~fl], case.psi[~fl])
 
 
+@pytest.mark.parametrize("make", CASES)
+@pytest.mark.parametrize("sparse", [False, True])
+def test_committed_golden_vectors(cuda, make, sparse):
+    """verification arithmetic against the committed fixtures (tests/golden/tp_*.npz)"""
+    import os
+    case = make()
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "tp_%s.npz" % case.name))
+    assert np.array_equal(case.solid, g["solid"]) and np.array_equal(case.psi, g["psi0"])
+    lb = case.make_solver(strict=True, sparse=sparse)
+    lb.run(int(g["steps"]))
+    fl = case.solid == 0
+    for n in FIELDS:
+        assert np.array_equal(getattr(lb, n).to_numpy()[fl], g[n][fl]), n
+
+
 def _yardstick(o32, o64, name, fl):
     """max(1e-5 relative, 2 x the fp32 oracle's own distance to its fp64 form): interface
     dynamics amplify fp32 round-off (the oracle built with -ffast-math drifts 1e-4 in psi from

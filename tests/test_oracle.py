@@ -71,11 +71,12 @@ def test_numpy_and_c_forms_bit_identical(make):
     assert np.array_equal(a64.F, b64.F) and np.array_equal(a64.v, b64.v)
 
 
-@pytest.mark.parametrize("name", ["mixed_bc", "all_faces", "periodic_force"])
+@pytest.mark.parametrize("name", ["mixed_bc", "all_faces", "periodic_force", "force_field", "other_copy"])
 def test_golden_vectors(name):
     g = np.load(os.path.join(GOLD, "sp_%s.npz" % name))
     case = {"mixed_bc": cases.case_mixed_bc, "all_faces": cases.case_all_faces,
-            "periodic_force": cases.case_periodic_force}[name]()
+            "periodic_force": cases.case_periodic_force, "force_field": cases.case_force_field,
+            "other_copy": cases.case_other_copy}[name]()
     assert np.array_equal(case.solid, g["solid"])
     o = case.make_oracle(RefSinglePhaseC)
     assert np.array_equal(o.F, g["F0"]) and np.array_equal(o.v, g["v0"])

@@ -21,6 +21,19 @@ def test_numpy_and_c_forms_bit_identical(make):
     assert np.isfinite(a.F).all()
 
 
+@pytest.mark.parametrize("make", [cases2p.case_drainage, cases2p.case_bcs, cases2p.case_periodic_bubble])
+def test_golden_vectors(make):
+    """committed fixtures (tests/golden/make_golden.py, NumPy oracle) pin both oracle forms"""
+    import os
+    case = make()
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "tp_%s.npz" % case.name))
+    assert np.array_equal(case.solid, g["solid"]) and np.array_equal(case.psi, g["psi0"])
+    o = case.make_oracle(RefTwoPhaseC)
+    o.run(int(g["steps"]))
+    for n in ("F", "rho", "v", "psi", "rho_r", "rho_b"):
+        assert np.array_equal(getattr(o, n), g[n]), n
+
+
 def test_pull_accumulation_matches_literal_push():
     case = cases2p.case_drainage((8, 7, 6))
     o = case.make_oracle(RefTwoPhase)
