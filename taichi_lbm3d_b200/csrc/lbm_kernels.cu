@@ -27,20 +27,6 @@
 namespace LBM_NS {
 using namespace d3q19;
 
-// Loads that must be ISSUED where they are written: volatile asm keeps ptxas from sinking an
-// index load down to its first use, which would chain the table look-ups into one DRAM
-// round trip per neighbour row instead of one for the whole table.
-__device__ __forceinline__ int32_t ld_early_s32(const int32_t *p) {
-    int32_t v;
-    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ uint32_t ld_early_u32(const uint32_t *p) {
-    uint32_t v;
-    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
-
 __device__ __forceinline__ uint32_t vbc_slot(const StepArgs &a, int face, uint32_t lin) {
     const uint32_t z = lin % (uint32_t)a.nz;
     const uint32_t t = lin / (uint32_t)a.nz;
@@ -474,10 +460,10 @@ __device__ __forceinline__ void sparse_node(const StepArgs &a, const SparseTable
             D3Q19_DIRS(X)
 #undef X
         }
-        return;
-    }
+    } else {
 #pragma unroll
-    for (int s = 0; s < 19; ++s) a.pout[s][i] = f[s];
+        for (int s = 0; s < 19; ++s) a.pout[s][i] = f[s];
+    }
 }
 
 // occupancy: 8 blocks (32 registers) per SM, except the in-place odd step, which keeps the 19
