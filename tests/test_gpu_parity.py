@@ -122,6 +122,30 @@ def test_committed_golden_vectors(cuda, name, sparse):
     assert np.array_equal(lb.v.to_numpy()[fl], g["v"][fl])
 
 
+@pytest.mark.parametrize("sparse", [False, True, "aa", "daa"])
+def test_reference_source_fixtures(cuda, sparse):
+    """tests/golden/ref_sp_*.npz: what the reference's own source computes (run through
+    tests/taichi_shim, tests/golden/make_reference_fixtures.py).  Verification arithmetic bit for
+    bit, production arithmetic within 1e-5, through the reference's own method names."""
+    from tests import refpin
+    for name in refpin.NAMES:
+        g = refpin.fixture(name)
+        fl = g["solid"] == 0
+        lb = refpin.make_solver(name, sparse=sparse, strict=True)
+        lb.step()
+        assert np.array_equal(lb.F.to_numpy()[fl], g["F1"][fl]) and np.array_equal(lb.v.to_numpy()[fl], g["v1"][fl])
+        for _ in range(int(g["steps"]) - 1):
+            lb.step()
+        for n in ("F", "rho", "v"):
+            assert np.array_equal(getattr(lb, n).to_numpy()[fl], g[n][fl]), (name, n)
+        assert abs(lb.get_max_v() - float(g["max_v"])) <= 2e-7 * float(g["max_v"]) + 1e-12
+        lbf = refpin.make_solver(name, sparse=sparse, strict=False)
+        lbf.run(int(g["steps"]))
+        assert rel_linf(lbf.F.to_numpy()[fl], g["F"][fl]) <= TOL and rel_linf(lbf.rho.to_numpy()[fl], g["rho"][fl]) <= TOL
+        dv = np.abs(lbf.v.to_numpy()[fl] - g["v"][fl]).max()
+        assert dv <= max(TOL * np.abs(g["v"][fl]).max(), 2e-7), (name, dv)
+
+
 def test_step_by_step_equals_run(cuda):
     """step() x n, with field reads in between, equals run(n) (state machine, :477-481)."""
     case = cases.case_mixed_bc()

@@ -1,0 +1,58 @@
+"""The oracle against THE REFERENCE'S OWN SOURCE (CPU, no GPU).
+
+tests/golden/ref_sp_*.npz were computed by /root/reference/Single_phase/
+LBM_3D_SinglePhase_Solver.py, imported unmodified and executed through the pure-Python Taichi
+stand-in tests/taichi_shim (tests/golden/make_reference_fixtures.py).  Both oracle forms must
+reproduce them BIT FOR BIT: F, rho, v after the first step and after the last, the relaxation
+rates, the fp32 inverse matrix and get_max_v.  Where /root/reference is mounted, the reference
+is run again and must reproduce the committed files."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle.cref import RefSinglePhaseC
+from oracle.ref_single_phase import RefSinglePhase
+from tests import refpin
+
+
+@pytest.mark.parametrize("name", refpin.NAMES)
+@pytest.mark.parametrize("cls", [RefSinglePhase, RefSinglePhaseC])
+def test_oracle_reproduces_reference_source(name, cls):
+    g = refpin.fixture(name)
+    o = refpin.make_oracle(cls, name)
+    assert np.array_equal(o.S, g["S"])                                   # init_simulation :126-131
+    assert np.array_equal(np.asarray(o.inv_M, np.float32), g["inv_M"])   # :83, :110
+    fl = g["solid"] == 0
+    o.step()
+    for n in ("F", "rho", "v"):
+        assert np.array_equal(getattr(o, n)[fl], g[n + "1"][fl]), (n, "after step 1")
+    for _ in range(int(g["steps"]) - 1):
+        o.step()
+    for n in ("F", "rho", "v", "f"):
+        assert np.array_equal(getattr(o, n)[fl], g[n][fl]), n
+    # solid nodes: rho = 1, v = 0 (:390-392), F keeps its initial w (:164-169)
+    assert np.array_equal(o.rho[~fl], g["rho"][~fl]) and np.array_equal(o.v[~fl], g["v"][~fl])
+    assert np.array_equal(o.F[~fl], g["F"][~fl])
+    vmax = np.sqrt((o.v.astype(np.float32) ** 2).sum(-1, dtype=np.float32)).max()
+    assert abs(float(vmax) - float(g["max_v"])) <= 1e-9 + 2e-7 * float(g["max_v"])
+
+
+@pytest.mark.skipif(not os.path.exists(refpin.mk.REF), reason="/root/reference is not mounted here")
+def test_fixtures_are_what_the_reference_computes():
+    mod = refpin.mk.load_reference()
+    for name in ("pressure_x", "lid_and_force"):
+        out = refpin.mk.run_reference(mod, name)
+        g = refpin.fixture(name)
+        for k in ("F", "rho", "v", "F1", "S", "inv_M"):
+            assert np.array_equal(out[k], g[k]), (name, k)
+
+
+def test_shim_is_not_reachable_from_the_product():
+    """the stand-in lives under tests/ and no product module imports taichi"""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hits = subprocess.run(["grep", "-rlE", r"^\s*(import|from) taichi\b", os.path.join(root, "taichi_lbm3d_b200"),
+                           os.path.join(root, "bench.py"), os.path.join(root, "__graft_entry__.py")],
+                          stdout=subprocess.PIPE).stdout.decode().split()
+    assert hits == []
