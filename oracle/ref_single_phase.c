@@ -4,8 +4,9 @@
  * and bench.py's cpu_baseline / --impl reference legs.  Never linked into, imported by
  * or called from the product library (taichi_lbm3d_b200/csrc).
  *
- * PARITY UNPINNED: the reference holds no golden vectors and Taichi cannot run in
- * this image; see oracle/ref_single_phase.py for the full statement.  This file is the
+ * PARITY PIN: the reference holds no golden vectors and Taichi cannot run in this image;
+ * the pin is the reference's own source executed through tests/taichi_shim, reproduced bit
+ * for bit (tests/test_reference_pin.py; full statement in oracle/ref_single_phase.py).  This file is the
  * same algorithm as that NumPy form, operation for operation (built with
  * -ffp-contract=off the two are bit-identical; tests/test_oracle.py checks it), kept
  * in the reference's own four-pass AoS structure so that, threaded with OpenMP, it

@@ -5,17 +5,22 @@ TEST INFRASTRUCTURE ONLY.  Nothing under ``oracle/`` is part of the product: onl
 legs may import it, and only as the checker.  The product path
 (``taichi_lbm3d_b200``) never imports this module and has no CPU fallback.
 
-PARITY UNPINNED.  The reference (yjhp1016/taichi_LBM3D) ships no tests, no golden
-vectors and no known-answer fixtures, and its runtime (Taichi) is not installable
-in this image, so this restatement cannot be pinned against reference outputs.  It
-follows ``Single_phase/LBM_3D_SinglePhase_Solver.py`` statement by statement and
-keeps the reference's four-pass structure (collide -> push-stream -> face BCs ->
-macro) and every quirk of the code (tau = niu/3 + 0.5, the /3 and /9 in the Guo
+PARITY PIN.  The reference (yjhp1016/taichi_LBM3D) ships no tests, no golden vectors
+and no known-answer fixtures, and its runtime (Taichi) is not installable in this
+image.  The pin is the reference's OWN SOURCE: ``Single_phase/LBM_3D_SinglePhase_Solver.py``
+is imported unmodified and executed through a pure-Python stand-in for the Taichi
+constructs it uses (``tests/taichi_shim``; ``tests/golden/make_reference_fixtures.py``
+writes ``tests/golden/ref_sp_*.npz``), and this restatement reproduces those outputs
+BIT FOR BIT (``tests/test_reference_pin.py``: pressure, velocity and periodic faces, body
+force, non-default viscosity).  What the stand-in cannot know is how real Taichi's LLVM
+backend reassociates or contracts under its default ``fast_math=True``; against real
+Taichi output a round-off tolerance would remain.  The restatement follows the reference
+statement by statement and keeps its four-pass structure (collide -> push-stream -> face
+BCs -> macro) and every quirk of the code (tau = niu/3 + 0.5, the /3 and /9 in the Guo
 term, equilibrium-overwrite boundary conditions, m3/m5/m7 = u rather than rho*u).
-The pins available are the invariants in tests/ (rest state, mass conservation,
-push == pull, analytic Poiseuille with the effective force f/9) and the
-bit-identity between this NumPy form, the pure-Python loop form below and the C
-form in ``ref_single_phase.c``.
+Further pins in tests/: rest state, mass conservation, push == pull, analytic Poiseuille
+with the effective force f/9, and the bit-identity between this NumPy form, the
+pure-Python loop form below and the C form in ``ref_single_phase.c``.
 
 Evaluation order.  Taichi's default ``fast_math=True`` leaves the summation order
 of ``M @ F`` and ``.sum()`` unspecified; here every reduction runs in ascending

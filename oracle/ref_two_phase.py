@@ -1,8 +1,12 @@
 """CPU restatement (oracle) of the reference two-phase colour-gradient step.
 
 TEST INFRASTRUCTURE ONLY (see oracle/ref_single_phase.py: only tests/, smoke() and bench.py's
-CPU legs may use anything under oracle/).  PARITY UNPINNED: the reference has no tests or
-golden vectors and Taichi cannot run in this image.
+CPU legs may use anything under oracle/).  PARITY PIN: the reference has no tests or golden
+vectors and Taichi cannot run in this image; the kernels of the reference script itself are
+executed through tests/taichi_shim with only its hand-edited parameter lines replaced
+(tests/golden/make_reference_fixtures.py -> tests/golden/ref_tp_*.npz) and this restatement
+matches them to fp32 round-off (tests/test_reference_pin.py; not bit for bit, because the
+script accumulates rho_r / rho_b with order-dependent float atomics, :365-372).
 
 Follows ``2phase/lbm_solver_3d_2phase.py`` (the dense script; ``..._sparse.py`` differs only in
 allocation) statement by statement; line numbers below cite that file.  The script is a

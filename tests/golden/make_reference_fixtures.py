@@ -73,7 +73,88 @@ def run_reference(mod, name):
     return out
 
 
+# ---- two-phase script ---------------------------------------------------------------------------
+# 2phase/lbm_solver_3d_2phase.py is a flat script: module-level parameters that its users edit by
+# hand, kernels, then a driver that reads the (missing) 131^3 input files and loops 80001 times.
+# Here the kernel part (everything above the driver) is executed through the shim with ONLY the
+# hand-edited parameter lines replaced -- lattice extents and, per case, fluid / BC parameters --
+# and the driver's loop body (:626-632) is called from here.
+REF2P = "/root/reference/2phase/lbm_solver_3d_2phase.py"
+
+CASES2P = {
+    # name -> (shape, solid fraction, seed, parameter-line overrides, steps)
+    "drainage": ((6, 5, 4), 0.25, 3, {"niu_l": "0.05", "niu_g": "0.2"}, 4),
+    "pressure_and_psi_faces": ((5, 5, 5), 0.2, 8, {
+        "fx,fy,fz": "0.0,0.0,0.0",
+        "bc_x_left, rho_bcxl, vx_bcxl, vy_bcxl, vz_bcxl": "1, 1.0, 0.0e-5, 0.0, 0.0",
+        "bc_x_right, rho_bcxr, vx_bcxr, vy_bcxr, vz_bcxr": "1, 0.995, 0.0, 0.0, 0.0",
+        "bc_z_right, rho_bczr, vx_bczr, vy_bczr, vz_bczr": "2, 1.0, 0.0, 0.0, 0.0",
+        "bc_psi_y_right, psi_y_right": "1, 1.0"}, 3),
+    "periodic_bubble": ((6, 6, 6), 0.0, 1, {"bc_psi_x_left, psi_x_left": "0, -1.0", "fx,fy,fz": "1e-5,0.0,0.0",
+                                            "niu_l": "0.05", "niu_g": "0.2"}, 3),
+}
+
+
+def case2p_inputs(name):
+    shape, frac, seed, _, _ = CASES2P[name]
+    solid = (np.random.default_rng(seed).random(shape) < frac).astype(np.int8)
+    if name == "periodic_bubble":
+        x, y, z = np.meshgrid(*[np.arange(n) for n in shape], indexing='ij')
+        psi = np.where((x - 2.5) ** 2 + (y - 2.5) ** 2 + (z - 2.5) ** 2 < 4.5, -1.0, 1.0).astype(np.float32)
+    else:
+        psi = np.ones(shape, np.float32)
+        psi[:2] = -1.0
+    return solid, psi
+
+
+def run_reference_two_phase(name):
+    import re
+    shape, _, _, overrides, steps = CASES2P[name]
+    src = open(REF2P).read()
+    head = src[:src.index("time_init = time.time()")]
+    lines = dict(overrides)
+    lines["nx,ny,nz"] = "%d,%d,%d" % shape
+    for lhs, rhs in lines.items():
+        head, n = re.subn(r"^%s\s*=.*$" % re.escape(lhs), "%s = %s" % (lhs, rhs), head, count=1, flags=re.M)
+        assert n == 1, lhs
+    shim = os.path.join(ROOT, "tests", "taichi_shim")
+    sys.path.insert(0, shim)
+    try:
+        for m in ("taichi", "pyevtk", "pyevtk.hl"):
+            sys.modules.pop(m, None)
+        ns = {"__name__": "lbm_solver_3d_2phase"}
+        exec(compile(head, REF2P, "exec"), ns)
+    finally:
+        sys.path.remove(shim)
+    solid, psi = case2p_inputs(name)
+    ns["solid"].from_numpy(solid)
+    ns["psi"].from_numpy(psi)
+    ns["static_init"]()
+    ns["init"]()
+    for _ in range(steps):                  # the driver's loop body, :626-632
+        ns["colission"]()
+        ns["streaming1"]()
+        ns["Boundary_condition"]()
+        ns["streaming3"]()
+        ns["Boundary_condition_psi"]()
+    out = {"solid": solid, "psi0": psi, "steps": steps}
+    for n in ("F", "rho", "v", "psi", "rho_r", "rho_b"):
+        out[n] = ns[n].to_numpy()
+    for n in ("fx", "fy", "fz", "niu_l", "niu_g", "psi_solid", "CapA"):
+        out[n] = np.float64(ns[n])
+    return out
+
+
 def main():
+    if "--two-phase-only" not in sys.argv:
+        main_single()
+    for name in CASES2P:
+        out = run_reference_two_phase(name)
+        np.savez_compressed(os.path.join(HERE, "ref_tp_%s.npz" % name), **out)
+        print("two-phase", name, "steps", out["steps"], "psi range", float(out["psi"].min()), float(out["psi"].max()))
+
+
+def main_single():
     mod = load_reference()
     for name in CASES:
         out = run_reference(mod, name)

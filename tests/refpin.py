@@ -43,3 +43,39 @@ def make_solver(name, sparse=False, strict=True):
         getattr(lb, fn)(arg)
     lb.init_simulation()
     return lb
+
+
+# ---- two-phase script (2phase/lbm_solver_3d_2phase.py through the shim) -------------------------
+NAMES2P = sorted(mk.CASES2P)
+FIELDS2P = ("F", "rho", "v", "psi", "rho_r", "rho_b")
+_SPEC2P = {
+    "drainage": dict(flow_bc=(), psi_bc=((0, -1.0),), force=(5e-5, -2e-5, 0.0), niu_l=0.05, niu_g=0.2),
+    "pressure_and_psi_faces": dict(flow_bc=[(0, 1, 1.0), (1, 1, 0.995), (5, 2, 1.0)], psi_bc=[(0, -1.0), (3, 1.0)],
+                                   force=(0.0, 0.0, 0.0), niu_l=0.1, niu_g=0.1),
+    "periodic_bubble": dict(flow_bc=(), psi_bc=(), force=(1e-5, 0.0, 0.0), niu_l=0.05, niu_g=0.2),
+}
+
+
+def fixture2p(name):
+    return np.load(os.path.join(GOLD, "ref_tp_%s.npz" % name))
+
+
+def case2p(name):
+    """the fixture's inputs as a tests/cases2p.Case2P (the parameter lines the generator replaced)"""
+    from tests import cases2p
+    g = fixture2p(name)
+    return cases2p.Case2P(name, g["solid"], g["psi0"], **_SPEC2P[name])
+
+
+def check2p(get, g, what, production=False):
+    """The reference accumulates rho_r / rho_b with float atomics (order undefined, here the shim's
+    loop order) and the shim keeps some f32 locals in f64, so the comparison is to fp32 round-off:
+    5e-7 relative on every field, v to 3e-7 of the population scale (it is a difference of
+    populations divided by rho).  Production arithmetic (factored transforms, FMA): the
+    north_star bar of 1e-5 relative, v to 3e-6 of the population scale."""
+    fl = g["solid"] == 0
+    rel, vrel = (1e-5, 3e-6) if production else (5e-7, 3e-7)
+    for n in FIELDS2P:
+        a, b = np.asarray(get(n))[fl].astype(np.float64), g[n][fl].astype(np.float64)
+        tol = vrel * float(np.abs(g["F"][fl]).max()) if n == "v" else rel * float(np.abs(b).max())
+        assert float(np.abs(a - b).max()) <= tol, (what, n, float(np.abs(a - b).max()), tol)

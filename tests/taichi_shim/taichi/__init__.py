@@ -30,6 +30,8 @@ f64 = np.float64
 i32 = np.int32
 i8 = np.int8
 ijk = "ijk"
+ijkl = "ijkl"
+i = "i"
 cpu = "cpu"
 gpu = "gpu"
 
@@ -74,6 +76,9 @@ class Vec(np.ndarray):
 
     def norm(self):
         return np.sqrt(self.dot(self))
+
+    def norm_sqr(self):
+        return self.dot(self)
 
     def sum(self):          # noqa: A003  ascending order
         acc = self[0]
@@ -168,8 +173,11 @@ class _Field:
             return ()
         if isinstance(key, np.ndarray):
             return tuple(int(k) for k in key)
-        if isinstance(key, tuple):
-            return tuple(int(k) for k in key)
+        if isinstance(key, tuple):          # F[ip, s]: a vector index followed by scalars
+            out = []
+            for k in key:
+                out.extend(int(q) for q in k) if isinstance(k, np.ndarray) and k.ndim == 1 else out.append(int(k))
+            return tuple(out)
         return (int(key),)
 
     def __getitem__(self, key):

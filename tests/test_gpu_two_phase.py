@@ -51,6 +51,20 @@ def test_committed_golden_vectors(cuda, make, sparse):
         assert np.array_equal(getattr(lb, n).to_numpy()[fl], g[n][fl]), n
 
 
+@pytest.mark.parametrize("sparse", [False, True])
+@pytest.mark.parametrize("strict", [True, False])
+def test_reference_script_fixtures(cuda, sparse, strict):
+    """tests/golden/ref_tp_*.npz: what the reference's own two-phase script computes (its kernels run
+    through tests/taichi_shim); fp32 round-off tolerance because the script's colour accumulation
+    is order-dependent (tests/refpin.py: check2p)"""
+    from tests import refpin
+    for name in refpin.NAMES2P:
+        g = refpin.fixture2p(name)
+        lb = refpin.case2p(name).make_solver(strict=strict, sparse=sparse)
+        lb.run(int(g["steps"]))
+        refpin.check2p(lambda n: getattr(lb, n).to_numpy(), g, name, production=not strict)
+
+
 def _yardstick(o32, o64, name, fl):
     """max(1e-5 relative, 2 x the fp32 oracle's own distance to its fp64 form): interface
     dynamics amplify fp32 round-off (the oracle built with -ffast-math drifts 1e-4 in psi from

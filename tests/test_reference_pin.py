@@ -48,6 +48,20 @@ def test_fixtures_are_what_the_reference_computes():
             assert np.array_equal(out[k], g[k]), (name, k)
 
 
+@pytest.mark.parametrize("name", refpin.NAMES2P)
+def test_two_phase_oracle_matches_reference_script(name):
+    """tests/golden/ref_tp_*.npz: 2phase/lbm_solver_3d_2phase.py, its kernels executed through the
+    shim with only the hand-edited parameter lines replaced (make_reference_fixtures.py)"""
+    from oracle.cref import RefTwoPhaseC
+    from oracle.ref_two_phase import RefTwoPhase
+    g = refpin.fixture2p(name)
+    for cls in (RefTwoPhase, RefTwoPhaseC):
+        o = refpin.case2p(name).make_oracle(cls)
+        for _ in range(int(g["steps"])):
+            o.step()
+        refpin.check2p(lambda n: getattr(o, n), g, cls.__name__)
+
+
 def test_shim_is_not_reachable_from_the_product():
     """the stand-in lives under tests/ and no product module imports taichi"""
     import subprocess
