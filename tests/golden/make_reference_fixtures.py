@@ -31,6 +31,9 @@ CASES = {
                                       ("set_bc_rho_y0", 1.0), ("set_bc_vel_y1", [0.0, -0.01, 0.01]),
                                       ("set_bc_rho_z0", 1.02), ("set_bc_vel_z1", [0.0, 0.0, 0.03])], 3),
     "periodic_force": ((4, 6, 5), 0.3, 11, [("set_force", [1e-5, 2e-5, -1e-5])], 4),
+    # one whole 3^3 block solid: never activated in the reference's sparse mode (reads give 0)
+    "solid_block": ((6, 6, 6), 0.15, 13, [("set_bc_rho_x0", 1.0), ("set_bc_rho_x1", 0.995),
+                                         ("set_force", [0.0, 1e-5, 0.0])], 2),
 }
 
 
@@ -52,13 +55,16 @@ def load_reference():
 
 def case_solid(name):
     shape, frac, seed, _, _ = CASES[name]
-    return (np.random.default_rng(seed).random(shape) < frac).astype(np.int8)
+    solid = (np.random.default_rng(seed).random(shape) < frac).astype(np.int8)
+    if name == "solid_block":
+        solid[3:6, 3:6, 3:6] = 1
+    return solid
 
 
-def run_reference(mod, name):
+def run_reference(mod, name, sparse_storage=False):
     shape, _, _, setup, steps = CASES[name]
     solid = case_solid(name)
-    lb = mod.LB3D_Solver_Single_Phase(nx=shape[0], ny=shape[1], nz=shape[2])
+    lb = mod.LB3D_Solver_Single_Phase(nx=shape[0], ny=shape[1], nz=shape[2], sparse_storage=sparse_storage)
     lb.solid.from_numpy(solid)
     for fn, arg in setup:
         getattr(lb, fn)(arg)
@@ -70,6 +76,13 @@ def run_reference(mod, name):
             out.update(F1=lb.F.to_numpy(), rho1=lb.rho.to_numpy(), v1=lb.v.to_numpy())
     out.update(F=lb.F.to_numpy(), rho=lb.rho.to_numpy(), v=lb.v.to_numpy(), f=lb.f.to_numpy(),
                max_v=np.float32(lb.get_max_v()), S=np.asarray(lb.S_dig[None]), inv_M=np.asarray(lb.inv_M[None]))
+    if sparse_storage:
+        # pointer/dense SNode fields have the extent 3*(n//3+1) (:43-44); the reference itself
+        # slices them back to the lattice (export_VTK :469-474)
+        nx, ny, nz = shape
+        for k in ("F", "rho", "v", "f", "F1", "rho1", "v1"):
+            out[k] = out[k][:nx, :ny, :nz]
+        out["active_blocks"] = lb.rho.active.copy()
     return out
 
 
@@ -158,8 +171,14 @@ def main_single():
     mod = load_reference()
     for name in CASES:
         out = run_reference(mod, name)
+        # the same case with sparse_storage=True (pointer SNode tree of 3^3 blocks, :36-44)
+        sp = run_reference(mod, name, sparse_storage=True)
+        for k in ("F", "rho", "v"):
+            out[k + "_sparse"] = sp[k]
+        out["active_blocks"] = sp["active_blocks"]
         np.savez_compressed(os.path.join(HERE, "ref_sp_%s.npz" % name), **out)
-        print(name, "steps", out["steps"], "max_v", float(out["max_v"]), "F dtype", out["F"].dtype)
+        print(name, "steps", out["steps"], "max_v", float(out["max_v"]), "F dtype", out["F"].dtype,
+              "active blocks", int(sp["active_blocks"].sum()), "of", sp["active_blocks"].size)
 
 
 if __name__ == "__main__":

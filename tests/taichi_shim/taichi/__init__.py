@@ -19,7 +19,12 @@ Semantics implemented (and only these):
   * Vector.dot, Matrix @ Vector: sums in ascending index order -- Taichi unrolls them the same
     way, but its LLVM backend may reassociate / contract under fast_math, so a comparison with
     real Taichi output would still need a round-off tolerance.
-The pointer / dense SNode tree (sparse_storage=True) is not modelled.
+  * ti.root.pointer(ijk, n).dense(ijk, b).place(fields): fields of extent n*b per axis that share
+    one activity mask per pointer cell; a WRITE (also through an element view) activates the
+    block, reads of inactive cells give 0, struct-fors visit the cells of active blocks only --
+    the semantics the reference's sparse_storage=True mode relies on (:36-44, :164, :225).
+    Reads outside a dense field's extent give 0 (Taichi leaves them undefined; the reference
+    guards every such read with i<nx, :225, :262, :376).
 """
 import itertools
 
@@ -65,7 +70,29 @@ def _coerce(a, b):
 
 
 class Vec(np.ndarray):
-    """ti.Vector value / view of one field element."""
+    """ti.Vector value / view of one field element (a view of an SNode-placed field activates
+    its block when it is written through)."""
+    _touch = None
+
+    def __setitem__(self, key, value):
+        if self._touch is not None:
+            self._touch()
+        np.ndarray.__setitem__(self, key, value)
+
+    def __iadd__(self, o):
+        if self._touch is not None:
+            self._touch()
+        return np.ndarray.__iadd__(self, np.asarray(o).astype(self.dtype, copy=False))
+
+    def __isub__(self, o):
+        if self._touch is not None:
+            self._touch()
+        return np.ndarray.__isub__(self, np.asarray(o).astype(self.dtype, copy=False))
+
+    def __itruediv__(self, o):
+        if self._touch is not None:
+            self._touch()
+        return np.ndarray.__itruediv__(self, np.asarray(o).astype(self.dtype, copy=False))
 
     def dot(self, other):
         a, b = _coerce(self, other)
@@ -158,14 +185,18 @@ def Matrix(vals):  # noqa: N802
 
 class _Field:
     def __init__(self, dtype, shape, elem=()):
-        if shape is None:
-            raise NotImplementedError("taichi shim: SNode-placed fields (sparse_storage=True) are not modelled")
-        if isinstance(shape, int):
-            shape = (shape,)
-        self.shape = tuple(shape)
         self.elem = tuple(elem)
-        self.data = np.zeros(self.shape + self.elem, dtype)
         self.dtype = dtype
+        self.block = None             # SNode-placed: cells per pointer cell, activity mask (shared)
+        self.active = None
+        self.shape = None
+        self.data = None
+        if shape is not None:
+            self._allocate((shape,) if isinstance(shape, int) else tuple(shape))
+
+    def _allocate(self, shape):
+        self.shape = tuple(shape)
+        self.data = np.zeros(self.shape + self.elem, self.dtype)
 
     @staticmethod
     def _idx(key):
@@ -180,21 +211,39 @@ class _Field:
             return tuple(out)
         return (int(key),)
 
+    def _inside(self, idx):
+        return all(0 <= i < n for i, n in zip(idx, self.shape))
+
+    def _activate(self, idx):
+        if self.active is not None:
+            self.active[tuple(i // b for i, b in zip(idx, self.block))] = True
+
     def __getitem__(self, key):
         if self.shape == () and not self.elem:
             return self.data              # 0-d view: ti.atomic_max(fld[None], x) can write through it
-        v = self.data[self._idx(key)]
+        idx = self._idx(key)
+        if not self._inside(idx[:len(self.shape)]):
+            return np.zeros(self.elem, self.dtype).view(Vec) if self.elem else self.dtype(0)
+        v = self.data[idx]
         if len(self.elem) == 1:
-            return v.view(Vec)
+            v = v.view(Vec)
+            if self.active is not None:
+                v._touch = lambda: self._activate(idx)
+            return v
         if len(self.elem) == 2:
             return v.view(Mat)
         return v                      # scalar (np.float32 / np.int8 ...)
 
     def __setitem__(self, key, value):
-        self.data[self._idx(key)] = np.asarray(value).astype(self.dtype, copy=False)
+        idx = self._idx(key)
+        self._activate(idx[:len(self.shape)])
+        self.data[idx] = np.asarray(value).astype(self.dtype, copy=False)
 
-    def __iter__(self):               # struct-for: every index, C order
-        return itertools.product(*[range(n) for n in self.shape])
+    def __iter__(self):               # struct-for: every index (of the active blocks), C order
+        if self.active is None:
+            return itertools.product(*[range(n) for n in self.shape])
+        return (idx for idx in itertools.product(*[range(n) for n in self.shape])
+                if self.active[tuple(i // b for i, b in zip(idx, self.block))])
 
     def from_numpy(self, arr):
         self.data[...] = np.asarray(arr).astype(self.dtype).reshape(self.data.shape)
@@ -238,9 +287,30 @@ def atomic_max(target, value):
         target[...] = value
 
 
-class _Root:
-    def pointer(self, *a, **k):
-        raise NotImplementedError("taichi shim: the pointer SNode tree (sparse_storage=True) is not modelled")
+class _SNode:
+    """pointer / dense cells along ijk: just enough of the SNode tree for
+    ti.root.pointer(ti.ijk, n).dense(ti.ijk, b).place(...)"""
+
+    def __init__(self, cells=(), block=None):
+        self.cells, self.block = tuple(cells), block
+
+    def pointer(self, axes, dims):
+        if self.cells:
+            raise NotImplementedError("taichi shim: one pointer level only")
+        return _SNode(dims)
+
+    def dense(self, axes, dims):
+        if not self.cells or self.block is not None:
+            raise NotImplementedError("taichi shim: dense directly under one pointer level only")
+        return _SNode(self.cells, tuple(dims))
+
+    def place(self, *fields):
+        if self.block is None:
+            raise NotImplementedError("taichi shim: place under pointer().dense() only")
+        active = np.zeros(self.cells, bool)          # activity belongs to the pointer cells: shared
+        for f in fields:
+            f._allocate(tuple(c * b for c, b in zip(self.cells, self.block)))
+            f.block, f.active = self.block, active
 
 
-root = _Root()
+root = _SNode()

@@ -38,6 +38,25 @@ def test_oracle_reproduces_reference_source(name, cls):
     assert abs(float(vmax) - float(g["max_v"])) <= 1e-9 + 2e-7 * float(g["max_v"])
 
 
+@pytest.mark.parametrize("name", refpin.NAMES)
+def test_reference_sparse_storage_semantics(name):
+    """sparse_storage=True of the reference (pointer SNode tree of 3^3 blocks, :36-44, modelled by
+    the shim): on fluid nodes it computes bit for bit what its dense mode computes; solid cells
+    inside an activated block read rho = 1, v = 0 (:390-392) and keep F = 0 (init :164 skips them).
+    The CUDA build returns the dense convention (rho = 1, v = 0, F = w) on solid nodes in both
+    modes, so parity is asserted on fluid nodes (SURVEY 8a': 6)."""
+    g = refpin.fixture(name)
+    fl = g["solid"] == 0
+    for k in ("F", "rho", "v"):
+        assert np.array_equal(g[k + "_sparse"][fl], g[k][fl]), k
+    nx, ny, nz = g["solid"].shape
+    blk = np.repeat(np.repeat(np.repeat(g["active_blocks"], 3, 0), 3, 1), 3, 2)[:nx, :ny, :nz]
+    assert blk[fl].all()                                   # every fluid cell lives in an active block
+    solid_active = ~fl & blk
+    assert np.all(g["rho_sparse"][solid_active] == 1.0) and np.all(g["v_sparse"][solid_active] == 0.0)
+    assert np.all(g["F_sparse"][~fl] == 0.0) and np.all(g["rho_sparse"][~fl & ~blk] == 0.0)
+
+
 @pytest.mark.skipif(not os.path.exists(refpin.mk.REF), reason="/root/reference is not mounted here")
 def test_fixtures_are_what_the_reference_computes():
     mod = refpin.mk.load_reference()
