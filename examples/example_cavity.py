@@ -1,43 +1,28 @@
-# Reference: Single_phase/example_cavity.py.  Differences: the two Taichi lines
-# (`import taichi as ti`, `ti.init(...)`) are gone and the 50^3 geometry file is generated
-# when it is not in the working directory (the reference ships it as geo_cavity.dat).
+"""Lid-driven cavity, the case of the reference's Single_phase/example_cavity.py: 50^3 box from
+geo_cavity.dat, lid velocity (0, 0, 0.1) on the x-right face, 2000 steps, VTK every 1000.
+
+A reference case script itself runs against this package after deleting its two Taichi lines
+(`import taichi as ti`, `ti.init(...)`): examples/LBM_3D_SinglePhase_Solver.py re-exports the
+class under the module name those scripts import."""
 import os
-import time
 
 import LBM_3D_SinglePhase_Solver as lb3dsp
+from _progress import Progress
 
-time_init = time.time()
-time_now = time.time()
-time_pre = time.time()
-
-if not os.path.exists('./geo_cavity.dat'):
+GEOMETRY = "./geo_cavity.dat"
+if not os.path.exists(GEOMETRY):          # the reference ships this file; generate it when absent
     from taichi_lbm3d_b200 import geometry
-    geometry.save_geometry_text('./geo_cavity.dat', geometry.cavity(50, 50, 50))
+    geometry.save_geometry_text(GEOMETRY, geometry.cavity(50, 50, 50))
 
-lb3d = lb3dsp.LB3D_Solver_Single_Phase(nx=50, ny=50, nz=50, sparse_storage=False)
+solver = lb3dsp.LB3D_Solver_Single_Phase(nx=50, ny=50, nz=50, sparse_storage=False)
+solver.init_geo(GEOMETRY)
+solver.set_bc_vel_x1([0.0, 0.0, 0.1])
+solver.init_simulation()
 
-lb3d.init_geo('./geo_cavity.dat')
-lb3d.set_bc_vel_x1([0.0, 0.0, 0.1])
-lb3d.init_simulation()
-
-for iter in range(2000 + 1):
-    lb3d.step()
-
-    if (iter % 500 == 0):
-
-        time_pre = time_now
-        time_now = time.time()
-        diff_time = int(time_now - time_pre)
-        elap_time = int(time_now - time_init)
-        m_diff, s_diff = divmod(diff_time, 60)
-        h_diff, m_diff = divmod(m_diff, 60)
-        m_elap, s_elap = divmod(elap_time, 60)
-        h_elap, m_elap = divmod(m_elap, 60)
-
-        max_v = lb3d.get_max_v()
-
-        print('----------Time between two outputs is %dh %dm %ds; elapsed time is %dh %dm %ds----------------------' % (h_diff, m_diff, s_diff, h_elap, m_elap, s_elap))
-        print('The %dth iteration, Max Force = %f,  force_scale = %f\n\n ' % (iter, max_v, 0.0))
-
-        if (iter % 1000 == 0):
-            lb3d.export_VTK(iter)
+progress = Progress()
+for step in range(2001):
+    solver.step()
+    if step % 500 == 0:
+        progress.report(step, max_v=solver.get_max_v())
+    if step % 1000 == 0:
+        solver.export_VTK(step)           # ./LB_SingelPhase_<step>.vtr

@@ -6,11 +6,13 @@
 # the reference mount (.MISSING_LARGE_BLOBS); when absent, a seeded sphere-pack stand-in and a
 # phase field with the non-wetting phase in the first 13 planes are used.
 import os
-import time
+import sys
 
 import numpy as np
 
-from taichi_lbm3d_b200 import LB3D_Solver_Two_Phase, geometry
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from taichi_lbm3d_b200 import LB3D_Solver_Two_Phase, geometry  # noqa: E402
+from _progress import Progress  # noqa: E402
 
 nx = ny = nz = 131
 lb = LB3D_Solver_Two_Phase(nx, ny, nz, sparse_storage=True)     # what ..._2phase_sparse.py does
@@ -31,21 +33,11 @@ lb.fx, lb.fy, lb.fz = 5.0e-5, -2e-5, 0.0
 lb.bc_psi_x_left, lb.psi_x_left = 1, -1.0
 lb.init_simulation()
 
-time_init = time_now = time.time()
-for iter in range(80000 + 1):
+progress = Progress()
+for step in range(80001):
     lb.step()
-
-    if (iter % 500 == 0):
-        time_pre, time_now = time_now, time.time()
-        diff_time, elap_time = int(time_now - time_pre), int(time_now - time_init)
-        m_diff, s_diff = divmod(diff_time, 60)
-        h_diff, m_diff = divmod(m_diff, 60)
-        m_elap, s_elap = divmod(elap_time, 60)
-        h_elap, m_elap = divmod(m_elap, 60)
-        print('----------Time between two outputs is %dh %dm %ds; elapsed time is %dh %dm %ds----------------------'
-              % (h_diff, m_diff, s_diff, h_elap, m_elap, s_elap))
-        print('The %dth iteration, max |v| = %g, non-wetting saturation = %.4f\n\n '
-              % (iter, lb.get_max_v(), float((lb.psi.to_numpy()[lb.solid.to_numpy() == 0] < 0).mean())))
-
-        if (iter % 10000 == 0):
-            lb.export_VTK(iter)             # ./structured<iter>.vtr: Solid, rho, phase, velocity
+    if step % 500 == 0:
+        fluid = lb.solid.to_numpy() == 0
+        progress.report(step, max_v=lb.get_max_v(), non_wetting_saturation=float((lb.psi.to_numpy()[fluid] < 0).mean()))
+    if step % 10000 == 0:
+        lb.export_VTK(step)               # ./structured<step>.vtr: Solid, rho, phase, velocity
