@@ -140,7 +140,8 @@ def run_reference(args):
         "data": "synthetic",
         "config": {"workload": "lid-driven cavity %d^3 dense, D3Q19 MRT single phase (BASELINE config 2 shape)" % n,
                    "note": "Taichi is not installable in this image; this is the oracle's C/OpenMP "
-                           "restatement of the reference's four-pass AoS step on the host cores"},
+                           "restatement of the reference's four-pass AoS step on the host cores (its strict "
+                           "build reproduces the reference source bit for bit, tests/test_reference_pin.py)"},
         "cpu_baseline": {"value": mlups, "unit": "MLUPS", "cores": cores, "kind": "port",
                          "sample": "%d steps of the %d^3 cavity (%d fluid nodes)" % (args.steps, n, nfl)},
         "e2e": {"value": mlups, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -351,7 +352,9 @@ def main():
             v, dtc, nflc = cpu_reference_run(nb, sb, 1)
             line["cpu_baseline"] = {"value": v, "unit": "MLUPS", "cores": cores, "kind": "port",
                                     "sample": "%d steps of a %d^3 cavity (same BCs), C/OpenMP restatement of the "
-                                              "reference's 4-pass step; Taichi unavailable" % (sb, nb)}
+                                              "reference's 4-pass step (its strict build reproduces the reference "
+                                              "source bit for bit, tests/test_reference_pin.py); Taichi unavailable"
+                                              % (sb, nb)}
         except Exception as ex:  # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "unit": "MLUPS", "cores": os.cpu_count(), "kind": "port",
                                     "sample": "failed: %s" % ex}
