@@ -320,6 +320,68 @@ def _two_phase_slab_class():
     return _Slab
 
 
+class StagedHaloExchanger:
+    """The two exchanges of a two-phase step over torch.distributed point-to-point ops.
+
+    `backend` provides, for stage 0 (populations + colour records) and stage 1 (psi):
+        pack(stage, side) -> tensor        side 0: the first owned plane (goes to the left rank)
+                                           side 1: the last owned plane (goes to the right rank)
+        unpack(stage, side, tensor)        side 0: left ghost plane <- what the left rank packed(1)
+                                           side 1: right ghost plane <- what the right rank packed(0)
+        recv_buffer(stage, side) -> tensor
+    `dist` is torch.distributed (None or world 1: the ring closes on itself)."""
+
+    def __init__(self, part, backend, dist=None):
+        self.part, self.backend, self.dist = part, backend, dist
+
+    def exchange(self, stage):
+        p, b = self.part, self.backend
+        to_left = b.pack(stage, 0)
+        to_right = b.pack(stage, 1)
+        if p.world == 1 or self.dist is None:
+            b.unpack(stage, 0, to_right)
+            b.unpack(stage, 1, to_left)
+            return
+        dist = self.dist
+        from_left, from_right = b.recv_buffer(stage, 0), b.recv_buffer(stage, 1)
+        # posting order matters when left == right (two ranks): pairs match in order
+        ops = [dist.P2POp(dist.isend, to_right, p.right), dist.P2POp(dist.isend, to_left, p.left),
+               dist.P2POp(dist.irecv, from_left, p.left), dist.P2POp(dist.irecv, from_right, p.right)]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        b.unpack(stage, 0, from_left)
+        b.unpack(stage, 1, from_right)
+
+
+class _Cuda2PBackend:
+    """pack / unpack through the C ABI (lbm2p_halo_pack / lbm2p_halo_unpack), torch staging buffers"""
+
+    def __init__(self, slab, torch):
+        self.slab, self.torch = slab, torch
+        lib, ctx = slab._lib, slab._ctx
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.count = [int(lib.lbm2p_halo_floats(ctx, 0)), int(lib.lbm2p_halo_floats(ctx, 1))]
+        self.send = [torch.empty(self.count[0], dtype=torch.float32, device=dev) for _ in range(2)]
+        self.recv = [torch.empty(self.count[0], dtype=torch.float32, device=dev) for _ in range(2)]
+
+    def _stream(self):
+        return ctypes.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+
+    def pack(self, stage, side):
+        s = self.slab
+        s._ck(s._lib.lbm2p_halo_pack(s._ctx, stage, side, ctypes.c_void_p(self.send[side].data_ptr()), self._stream()),
+              "lbm2p_halo_pack")
+        return self.send[side][:self.count[stage]]
+
+    def unpack(self, stage, side, tensor):
+        s = self.slab
+        s._ck(s._lib.lbm2p_halo_unpack(s._ctx, stage, side, ctypes.c_void_p(tensor.data_ptr()), self._stream()),
+              "lbm2p_halo_unpack")
+
+    def recv_buffer(self, stage, side):
+        return self.recv[side][:self.count[stage]]
+
+
 class TwoPhaseSlabSolver:
     """Two-phase colour-gradient solver over `world_size` GPUs (x-slabs).  The attributes of
     LB3D_Solver_Two_Phase (niu_l, CapA, bc_psi_x_left, ...) are set on ``.local``; geometry and
@@ -359,11 +421,8 @@ class TwoPhaseSlabSolver:
         loc.init_simulation()
         lib, ctx = loc._lib, loc._ctx
         self._started = False
-        dev = self.torch.device("cuda", self.torch.cuda.current_device())
-        n0 = int(lib.lbm2p_halo_floats(ctx, 0))
-        self._send = [self.torch.empty(n0, dtype=self.torch.float32, device=dev) for _ in range(2)]
-        self._recv = [self.torch.empty(n0, dtype=self.torch.float32, device=dev) for _ in range(2)]
-        self._count = [n0, int(lib.lbm2p_halo_floats(ctx, 1))]
+        self.backend = _Cuda2PBackend(loc, self.torch)
+        self.halo = StagedHaloExchanger(self.part, self.backend, self.dist)
         if self.transport == "native":
             ident = (ctypes.c_char * 128)()
             if self.part.world > 1:
@@ -386,23 +445,7 @@ class TwoPhaseSlabSolver:
         return loc._ck(loc._lib.lbm2p_slab_stage(loc._ctx, stage, self._stream()), "lbm2p_slab_stage")
 
     def _exchange(self, stage):
-        loc, p = self.local, self.part
-        lib, ctx, n = loc._lib, loc._ctx, self._count[stage]
-        for side in (0, 1):
-            loc._ck(lib.lbm2p_halo_pack(ctx, stage, side, ctypes.c_void_p(self._send[side].data_ptr()),
-                                        self._stream()), "lbm2p_halo_pack")
-        if p.world == 1 or self.dist is None:
-            src = [self._send[1], self._send[0]]          # ring of one slab
-        else:
-            dist = self.dist
-            ops = [dist.P2POp(dist.isend, self._send[1][:n], p.right), dist.P2POp(dist.isend, self._send[0][:n], p.left),
-                   dist.P2POp(dist.irecv, self._recv[0][:n], p.left), dist.P2POp(dist.irecv, self._recv[1][:n], p.right)]
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
-            src = self._recv
-        for side in (0, 1):
-            loc._ck(lib.lbm2p_halo_unpack(ctx, stage, side, ctypes.c_void_p(src[side].data_ptr()), self._stream()),
-                    "lbm2p_halo_unpack")
+        self.halo.exchange(stage)
 
     def step(self):
         self.run(1)

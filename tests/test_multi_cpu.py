@@ -97,3 +97,67 @@ def test_halo_exchange_over_gloo_matches_single_domain(world, tmp_path):
     assert np.array_equal(F[fl], ref.F[fl])
     assert np.array_equal(rho[fl], ref.rho[fl])
     assert np.array_equal(v[fl], ref.v[fl])
+
+
+# ---- two-phase: the staged exchange (two exchanges per step) over gloo --------------------------
+class _TagBackend:
+    """stand-in for one rank's two-phase slab: packs tensors that say who sent what, and keeps
+    what it is asked to unpack"""
+
+    def __init__(self, rank):
+        import torch
+        self.torch, self.rank, self.got = torch, rank, {}
+        self.n = [15 * 6, 6]              # stage 0: 15 floats per face node, stage 1: 1
+
+    def pack(self, stage, side):
+        return self.torch.full((self.n[stage],), float(self.rank * 100 + stage * 10 + side))
+
+    def unpack(self, stage, side, tensor):
+        assert tensor.numel() == self.n[stage]
+        vals = set(tensor.tolist())
+        assert len(vals) == 1
+        self.got[(stage, side)] = vals.pop()
+
+    def recv_buffer(self, stage, side):
+        return self.torch.empty(self.n[stage])
+
+
+def _worker_staged(rank, world, port, out_dir):
+    import json
+    import torch.distributed as dist
+    from taichi_lbm3d_b200.multi_gpu import SlabPartition, StagedHaloExchanger
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        part = SlabPartition(12, world, rank)
+        b = _TagBackend(rank)
+        halo = StagedHaloExchanger(part, b, dist)
+        for stage in (0, 1, 0, 1):        # the schedule of TwoPhaseSlabSolver.run
+            halo.exchange(stage)
+        with open(os.path.join(out_dir, "staged%d.json" % rank), "w") as fh:
+            json.dump({"%d,%d" % k: v for k, v in b.got.items()}, fh)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_staged_exchange_routes_planes_to_the_right_ghosts(world, tmp_path):
+    """left ghost <- what the LEFT rank packed for its right side (side 1), right ghost <- what the
+    RIGHT rank packed for its left side (side 0), for both stages, also when left == right
+    (two ranks) and in the ring of one"""
+    import json
+    import torch.multiprocessing as mp
+    from taichi_lbm3d_b200.multi_gpu import SlabPartition, StagedHaloExchanger
+    if world == 1:
+        b = _TagBackend(0)
+        halo = StagedHaloExchanger(SlabPartition(12, 1, 0), b, None)
+        halo.exchange(0)
+        halo.exchange(1)
+        got = [{"%d,%d" % k: v for k, v in b.got.items()}]
+    else:
+        mp.spawn(_worker_staged, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+        got = [json.load(open(os.path.join(str(tmp_path), "staged%d.json" % r))) for r in range(world)]
+    for r in range(world):
+        left, right = (r - 1) % world, (r + 1) % world
+        for stage in (0, 1):
+            assert got[r]["%d,0" % stage] == left * 100 + stage * 10 + 1
+            assert got[r]["%d,1" % stage] == right * 100 + stage * 10 + 0
