@@ -93,10 +93,12 @@ def run_reference(mod, name, sparse_storage=False):
 # hand-edited parameter lines replaced -- lattice extents and, per case, fluid / BC parameters --
 # and the driver's loop body (:626-632) is called from here.
 REF2P = "/root/reference/2phase/lbm_solver_3d_2phase.py"
+REF2P_SPARSE = "/root/reference/2phase/lbm_solver_3d_2phase_sparse.py"     # same kernels, pointer SNode fields
 
 CASES2P = {
     # name -> (shape, solid fraction, seed, parameter-line overrides, steps)
-    "drainage": ((6, 5, 4), 0.25, 3, {"niu_l": "0.05", "niu_g": "0.2"}, 4),
+    # (the dense script's default force; the sparse script's own default differs: fy = 0)
+    "drainage": ((6, 5, 4), 0.25, 3, {"niu_l": "0.05", "niu_g": "0.2", "fx,fy,fz": "5.0e-5,-2e-5,0.0"}, 4),
     "pressure_and_psi_faces": ((5, 5, 5), 0.2, 8, {
         "fx,fy,fz": "0.0,0.0,0.0",
         "bc_x_left, rho_bcxl, vx_bcxl, vy_bcxl, vz_bcxl": "1, 1.0, 0.0e-5, 0.0, 0.0",
@@ -120,10 +122,10 @@ def case2p_inputs(name):
     return solid, psi
 
 
-def run_reference_two_phase(name):
+def run_reference_two_phase(name, script=REF2P):
     import re
     shape, _, _, overrides, steps = CASES2P[name]
-    src = open(REF2P).read()
+    src = open(script).read()
     head = src[:src.index("time_init = time.time()")]
     lines = dict(overrides)
     lines["nx,ny,nz"] = "%d,%d,%d" % shape
@@ -136,7 +138,7 @@ def run_reference_two_phase(name):
         for m in ("taichi", "pyevtk", "pyevtk.hl"):
             sys.modules.pop(m, None)
         ns = {"__name__": "lbm_solver_3d_2phase"}
-        exec(compile(head, REF2P, "exec"), ns)
+        exec(compile(head, script, "exec"), ns)
     finally:
         sys.path.remove(shim)
     solid, psi = case2p_inputs(name)
@@ -151,8 +153,9 @@ def run_reference_two_phase(name):
         ns["streaming3"]()
         ns["Boundary_condition_psi"]()
     out = {"solid": solid, "psi0": psi, "steps": steps}
+    nx, ny, nz = shape
     for n in ("F", "rho", "v", "psi", "rho_r", "rho_b"):
-        out[n] = ns[n].to_numpy()
+        out[n] = ns[n].to_numpy()[:nx, :ny, :nz]        # SNode-placed fields have the extent 3*(n//3+1)
     for n in ("fx", "fy", "fz", "niu_l", "niu_g", "psi_solid", "CapA"):
         out[n] = np.float64(ns[n])
     return out
@@ -163,6 +166,9 @@ def main():
         main_single()
     for name in CASES2P:
         out = run_reference_two_phase(name)
+        sp = run_reference_two_phase(name, REF2P_SPARSE)
+        for n in ("F", "rho", "v", "psi", "rho_r", "rho_b"):
+            out[n + "_sparse"] = sp[n]
         np.savez_compressed(os.path.join(HERE, "ref_tp_%s.npz" % name), **out)
         print("two-phase", name, "steps", out["steps"], "psi range", float(out["psi"].min()), float(out["psi"].max()))
 

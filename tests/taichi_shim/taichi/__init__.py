@@ -288,29 +288,29 @@ def atomic_max(target, value):
 
 
 class _SNode:
-    """pointer / dense cells along ijk: just enough of the SNode tree for
-    ti.root.pointer(ti.ijk, n).dense(ti.ijk, b).place(...)"""
+    """pointer / dense cells along ijk(l): just enough of the SNode tree for
+    ti.root.pointer(axes, n).dense(axes, b).place(...).  The activity mask belongs to the
+    POINTER node: every field placed below it (through any of its dense children) shares it."""
 
-    def __init__(self, cells=(), block=None):
-        self.cells, self.block = tuple(cells), block
+    def __init__(self, cells=(), block=None, active=None):
+        self.cells, self.block, self.active = tuple(cells), block, active
 
     def pointer(self, axes, dims):
         if self.cells:
             raise NotImplementedError("taichi shim: one pointer level only")
-        return _SNode(dims)
+        return _SNode(dims, None, np.zeros(tuple(dims), bool))
 
     def dense(self, axes, dims):
         if not self.cells or self.block is not None:
             raise NotImplementedError("taichi shim: dense directly under one pointer level only")
-        return _SNode(self.cells, tuple(dims))
+        return _SNode(self.cells, tuple(dims), self.active)
 
     def place(self, *fields):
         if self.block is None:
             raise NotImplementedError("taichi shim: place under pointer().dense() only")
-        active = np.zeros(self.cells, bool)          # activity belongs to the pointer cells: shared
         for f in fields:
             f._allocate(tuple(c * b for c, b in zip(self.cells, self.block)))
-            f.block, f.active = self.block, active
+            f.block, f.active = self.block, self.active
 
 
 root = _SNode()

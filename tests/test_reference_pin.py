@@ -81,6 +81,16 @@ def test_two_phase_oracle_matches_reference_script(name):
         refpin.check2p(lambda n: getattr(o, n), g, cls.__name__)
 
 
+@pytest.mark.parametrize("name", refpin.NAMES2P)
+def test_two_phase_sparse_script_equals_dense_script(name):
+    """2phase/lbm_solver_3d_2phase_sparse.py (pointer SNode fields, same kernels) computes on fluid
+    nodes what the dense script computes -- the premise of serving both with one CUDA path"""
+    g = refpin.fixture2p(name)
+    fl = g["solid"] == 0
+    for n in refpin.FIELDS2P:
+        assert np.array_equal(g[n + "_sparse"][fl], g[n][fl]), n
+
+
 def test_shim_is_not_reachable_from_the_product():
     """the stand-in lives under tests/ and no product module imports taichi"""
     import subprocess
