@@ -37,20 +37,57 @@ CASES = {
 }
 
 
-def load_reference():
-    """the reference module with taichi / pyevtk resolved to the shim"""
+REF_OTHER = "/root/reference/Phase_change"      # the class's other copy: tau = 3 niu + 1/2, un-scaled Guo term
+
+
+def load_reference(directory=REF):
+    """the reference module (from `directory`) with taichi / pyevtk resolved to the shim"""
     shim = os.path.join(ROOT, "tests", "taichi_shim")
     sys.path.insert(0, shim)
-    sys.path.insert(0, REF)
+    sys.path.insert(0, directory)
     try:
         for m in ("taichi", "pyevtk", "pyevtk.hl", "LBM_3D_SinglePhase_Solver"):
             sys.modules.pop(m, None)
         mod = importlib.import_module("LBM_3D_SinglePhase_Solver")
-        assert mod.__file__.startswith(REF), mod.__file__
+        assert mod.__file__.startswith(directory), mod.__file__
         return mod
     finally:
-        sys.path.remove(REF)
+        sys.path.remove(directory)
         sys.path.remove(shim)
+
+
+def local_force_field(shape):
+    """a per-node force for the cal_local_force hook (:217-220)"""
+    rng = np.random.default_rng(29)
+    return (1e-5 * rng.standard_normal(shape + (3,))).astype(np.float32)
+
+
+def run_reference_local_force(mod, name):
+    """the reference's extension point as its users exercise it (Phase_change/
+    LBM_3D_SinglePhase_Solute_Solver.py:185-190): a SUBCLASS overriding the @ti.func
+    cal_local_force(i,j,k); here it returns a per-node vector.  fx is set non-zero only to switch
+    the class's force_flag on (:137-140), the hook ignores it."""
+    import taichi as ti          # the shim (load_reference left it in sys.modules)
+    shape, _, _, setup, steps = CASES[name]
+    ff = local_force_field(shape)
+
+    class WithLocalForce(mod.LB3D_Solver_Single_Phase):
+        @ti.func
+        def cal_local_force(self, i, j, k):
+            return ti.Vector([ff[i, j, k, 0], ff[i, j, k, 1], ff[i, j, k, 2]])
+
+    solid = case_solid(name)
+    lb = WithLocalForce(nx=shape[0], ny=shape[1], nz=shape[2])
+    lb.solid.from_numpy(solid)
+    for fn, arg in setup:
+        if fn != "set_force":
+            getattr(lb, fn)(arg)
+    lb.set_force([1e-30, 0.0, 0.0])
+    lb.init_simulation()
+    for _ in range(steps):
+        lb.step()
+    return {"solid": solid, "steps": steps, "force_field": ff, "F": lb.F.to_numpy(), "rho": lb.rho.to_numpy(),
+            "v": lb.v.to_numpy()}
 
 
 def case_solid(name):
@@ -174,7 +211,16 @@ def main():
 
 
 def main_single():
+    other = load_reference(REF_OTHER)
+    for name in ("lid_and_force", "periodic_force"):
+        out = run_reference(other, name)
+        np.savez_compressed(os.path.join(HERE, "ref_sp_other_copy_%s.npz" % name), **out)
+        print("other copy", name, "max_v", float(out["max_v"]))
     mod = load_reference()
+    for name in ("pressure_x", "periodic_force"):
+        out = run_reference_local_force(mod, name)
+        np.savez_compressed(os.path.join(HERE, "ref_sp_local_force_%s.npz" % name), **out)
+        print("cal_local_force override", name, "max |v|", float(np.abs(out["v"]).max()))
     for name in CASES:
         out = run_reference(mod, name)
         # the same case with sparse_storage=True (pointer SNode tree of 3^3 blocks, :36-44)

@@ -38,6 +38,47 @@ def test_oracle_reproduces_reference_source(name, cls):
     assert abs(float(vmax) - float(g["max_v"])) <= 1e-9 + 2e-7 * float(g["max_v"])
 
 
+@pytest.mark.parametrize("name", ["lid_and_force", "periodic_force"])
+@pytest.mark.parametrize("cls", [RefSinglePhase, RefSinglePhaseC])
+def test_other_copy_of_the_class(name, cls):
+    """Phase_change/LBM_3D_SinglePhase_Solver.py (tau = 3 niu + 1/2 :126, Guo term not divided :235),
+    run unmodified through the shim, is what tau_mode="textbook", guo_mode="unscaled" compute"""
+    g = np.load(os.path.join(refpin.GOLD, "ref_sp_other_copy_%s.npz" % name))
+    o = refpin.make_oracle(cls, name, tau_mode="textbook", guo_mode="unscaled")
+    assert np.array_equal(o.S, g["S"])
+    for _ in range(int(g["steps"])):
+        o.step()
+    fl = g["solid"] == 0
+    for n in ("F", "rho", "v"):
+        assert np.array_equal(getattr(o, n)[fl], g[n][fl]), n
+
+
+@pytest.mark.parametrize("name", ["pressure_x", "periodic_force"])
+@pytest.mark.parametrize("cls", [RefSinglePhase, RefSinglePhaseC])
+def test_cal_local_force_override_is_the_force_array(name, cls):
+    """the reference's extension point, a subclass overriding the @ti.func cal_local_force(i,j,k)
+    (:217-220; used by colission :231 and streaming3 :385), returning a per-node vector: bit for
+    bit what set_force_field computes (lbm_set_force_field in the C ABI)"""
+    g = np.load(os.path.join(refpin.GOLD, "ref_sp_local_force_%s.npz" % name))
+    shape, _, _, setup, _ = refpin.mk.CASES[name]
+    o = cls(*shape)
+    o.set_solid(g["solid"])
+    for fn, arg in setup:
+        if fn.startswith("set_bc_rho_"):
+            o.set_bc_rho(refpin.FACE[fn[-2:]], arg)
+        elif fn.startswith("set_bc_vel_"):
+            o.set_bc_vel(refpin.FACE[fn[-2:]], arg)
+        elif fn != "set_force":
+            getattr(o, fn)(arg)
+    o.set_force_field(g["force_field"])
+    o.init_simulation()
+    for _ in range(int(g["steps"])):
+        o.step()
+    fl = g["solid"] == 0
+    for n in ("F", "rho", "v"):
+        assert np.array_equal(getattr(o, n)[fl], g[n][fl]), n
+
+
 @pytest.mark.parametrize("name", refpin.NAMES)
 def test_reference_sparse_storage_semantics(name):
     """sparse_storage=True of the reference (pointer SNode tree of 3^3 blocks, :36-44, modelled by
