@@ -354,7 +354,7 @@ class LB3D_Solver_Single_Phase:
                 raise ValueError("solid must have shape %s" % ((self.nx, self.ny, self.nz),))
             if self._ctx is not None:
                 raise _lib.LbmError("geometry is fixed at init_simulation()")
-            self._solid_host = (a > 0).astype(np.int8)      # init_geo :175
+            self._solid_host = (a > 0).view(np.int8)        # init_geo :175 (bool viewed as 0/1 bytes: one pass)
             return
         if name == "f":
             return      # scratch in the reference: colission overwrites it before any read (:240)

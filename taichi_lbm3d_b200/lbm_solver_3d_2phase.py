@@ -217,7 +217,7 @@ class LB3D_Solver_Two_Phase:
         if a.shape != (self.nx, self.ny, self.nz):
             raise ValueError("%s must have shape %s" % (name, (self.nx, self.ny, self.nz)))
         if name == "solid":
-            self._solid_host = (a > 0).astype(np.int8)
+            self._solid_host = (a > 0).view(np.int8)
         elif name == "psi":
             self._psi_host = np.ascontiguousarray(a.astype(np.float32))
         else:

@@ -183,7 +183,7 @@ class SlabSolver:
 
     # ---- setup -------------------------------------------------------------------------------
     def set_solid(self, global_solid):
-        self._global_solid = (np.asarray(global_solid) > 0).astype(np.int8)
+        self._global_solid = (np.asarray(global_solid) > 0).view(np.int8)
         self.local.solid.from_numpy(self.part.local_solid(self._global_solid))
 
     def set_local_solid(self, local_solid_with_ghosts):
