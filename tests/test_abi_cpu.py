@@ -194,3 +194,42 @@ def test_create_rejects_bad_and_oversized_lattices():
     # NULL contexts are refused, not dereferenced
     assert lib.lbm_step(None, 1, None) == -1 and lib.lbm_init(None) == -1 and lib.lbm_launch_count(None) == -1
     assert lib.lbm2p_step(None, 1, None) == -1
+
+
+def test_headers_are_plain_c_and_a_c_host_links(tmp_path):
+    """include/*.h compile as C99 (no C++-isms, no torch types) and a plain C program links against
+    liblbm3d_b200.so; without a GPU its lbm_create fails with the library's own message"""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    from taichi_lbm3d_b200 import _lib
+    _lib.load()
+    libdir = os.path.dirname(_lib.library_path())
+    src = tmp_path / "host.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "lbm3d.h"
+#include "lbm3d_2phase.h"
+int main(void) {
+    lbm_config cfg = {4, 4, 4, 0, 0, 0, 0, 0};
+    lbm_ctx *ctx = NULL;
+    int rc = lbm_create(&cfg, &ctx);
+    printf("abi %d rc %d msg %s\n", lbm_abi_version(), rc, rc ? lbm_last_error(NULL) : "ok");
+    if (ctx) lbm_destroy(ctx);
+    lbm2p_config cfg2 = {4, 4, 4, 0, 0, LBM2P_SPARSE};
+    lbm2p_ctx *c2 = NULL;
+    rc = lbm2p_create(&cfg2, &c2);
+    if (c2) lbm2p_destroy(c2);
+    return 0;
+}
+''')
+    exe = tmp_path / "host"
+    subprocess.run([gcc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                    "-o", str(exe), "-L", libdir, "-llbm3d_b200", "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], stdout=subprocess.PIPE, check=True).stdout.decode()
+    assert out.startswith("abi 1 rc ")
+    import torch
+    if not torch.cuda.is_available():
+        assert "no CPU fallback" in out
