@@ -65,3 +65,87 @@ class OracleSlab:
 
     def owned(self, name):
         return self.part.owned(getattr(self.o, name))
+
+
+# ---------------------------------------------------------------------------------------------
+# two-phase: CPU stand-in for one rank's slab behind StagedHaloExchanger
+# ---------------------------------------------------------------------------------------------
+class _SlabTwoPhase:
+    """oracle/ref_two_phase.RefTwoPhase whose colission() stops before the colour accumulation
+    (:365-372), so that the neighbours' g_r, g_b can arrive in between"""
+
+    def __new__(cls, *args, **kw):
+        from oracle.ref_two_phase import RefTwoPhase
+
+        class Split(RefTwoPhase):
+            def _accumulate_colour(self):
+                pass
+
+            def accumulate_now(self):
+                RefTwoPhase._accumulate_colour(self)
+
+        return Split(*args, **kw)
+
+
+class OracleSlab2P:
+    """One rank's slab of the two-phase solver on the CPU: the NumPy oracle on the local lattice
+    (owned planes + one ghost plane either side; np.roll wraps the two ghost planes onto each other,
+    which never reaches an owned node), stepped in the three stages of the CUDA schedule
+    (include/lbm3d_2phase.h) and exchanging what those stages need: stage 0 the post-collision f
+    and the recoloured g_r, g_b of the boundary plane (the CUDA path sends 5 populations and the
+    24-byte colour record instead), stage 1 psi.  x faces must be periodic here."""
+
+    def __init__(self, part, case):
+        assert all(face >= 2 for face, _, _ in case.flow_bc) and all(face >= 2 for face, _ in case.psi_bc), \
+            "x faces must be periodic in the CPU slab test"
+        self.part = part
+        o = _SlabTwoPhase(part.local_nx, case.shape[1], case.shape[2])
+        o.set_solid(part.local_solid(case.solid))
+        o.set_psi(np.ascontiguousarray(np.take(case.psi, part.local_planes(), axis=0)))
+        o.fx, o.fy, o.fz = case.force
+        o.niu_l, o.niu_g, o.CapA, o.psi_solid = case.niu_l, case.niu_g, case.CapA, case.psi_solid
+        o.bc_type = [0] * 6
+        for face, t, rho in case.flow_bc:
+            o.bc_type[face] = t
+            o.bc_rho[face] = rho
+        o.bc_psi_type = [0] * 6
+        for face, val in case.psi_bc:
+            o.bc_psi_type[face] = 1
+            o.bc_psi_val[face] = val
+        o.init_simulation()
+        self.o = o
+
+    # ---- backend interface of StagedHaloExchanger -------------------------------------------------
+    def _fields(self, stage):
+        o = self.o
+        return (o.f, o.g_r, o.g_b) if stage == 0 else (o.psi[..., None],)
+
+    def pack(self, stage, side):
+        plane = 1 if side == 0 else self.o.nx - 2
+        return torch.from_numpy(np.concatenate([a[plane].reshape(-1) for a in self._fields(stage)]).astype(np.float32))
+
+    def unpack(self, stage, side, tensor):
+        plane = 0 if side == 0 else self.o.nx - 1
+        flat, pos = tensor.numpy(), 0
+        for a in self._fields(stage):
+            n = a[plane].size
+            a[plane] = flat[pos:pos + n].reshape(a[plane].shape)
+            pos += n
+
+    def recv_buffer(self, stage, side):
+        return torch.empty(sum(a[1].size for a in self._fields(stage)), dtype=torch.float32)
+
+    # ---- the three stages --------------------------------------------------------------------------
+    def stage(self, k):
+        o = self.o
+        if k in (0, 2):                   # collision of the next step: f*, g_r, g_b (needs ghost psi)
+            o.colission()
+        else:                             # colour accumulation, stream, BCs, macro, psi (needs ghost f*, g)
+            o.accumulate_now()
+            o.streaming1()
+            o.Boundary_condition()
+            o.streaming3()
+            o.Boundary_condition_psi()
+
+    def owned(self, name):
+        return self.part.owned(getattr(self.o, name))

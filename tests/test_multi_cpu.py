@@ -161,3 +161,59 @@ def test_staged_exchange_routes_planes_to_the_right_ghosts(world, tmp_path):
         for stage in (0, 1):
             assert got[r]["%d,0" % stage] == left * 100 + stage * 10 + 1
             assert got[r]["%d,1" % stage] == right * 100 + stage * 10 + 0
+
+
+def _case2p():
+    from tests import cases2p
+    shape = (11, 6, 7)
+    solid = (np.random.default_rng(19).random(shape) < 0.25).astype(np.int8)
+    psi = np.ones(shape, np.float32)
+    psi[:, :2] = -1.0
+    # constant psi on the y-left face, pressure faces in z, x periodic (crosses the cuts)
+    return cases2p.Case2P("slabs2p", solid, psi, flow_bc=[(4, 1, 1.0), (5, 1, 0.995)], psi_bc=[(2, -1.0)],
+                          force=(3e-5, -1e-5, 0.0))
+
+
+def _worker_2p(rank, world, port, steps, out_dir):
+    import torch.distributed as dist
+    from taichi_lbm3d_b200.multi_gpu import SlabPartition, StagedHaloExchanger
+    from tests.slab_oracle import OracleSlab2P
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        case = _case2p()
+        part = SlabPartition(case.shape[0], world, rank)
+        slab = OracleSlab2P(part, case)
+        halo = StagedHaloExchanger(part, slab, dist)
+        # the schedule of TwoPhaseSlabSolver.run / lbm2p_run_slab
+        slab.stage(0)
+        halo.exchange(0)
+        for _ in range(steps - 1):
+            slab.stage(1)
+            halo.exchange(1)
+            slab.stage(2)
+            halo.exchange(0)
+        slab.stage(1)                     # close the last step (what the getters do on demand)
+        np.savez(os.path.join(out_dir, "tp_rank%d.npz" % rank),
+                 **{n: slab.owned(n) for n in ("F", "rho", "v", "psi", "rho_r", "rho_b")})
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_two_phase_staged_exchange_over_gloo_matches_single_domain(world, tmp_path):
+    """the two-exchange schedule of the two-phase slabs (psi after the colour stage; populations and
+    colour data after the collision), driven by the PRODUCT's partition and exchanger over gloo with
+    the NumPy oracle as the stepper: bit-identical to the single-domain oracle"""
+    import torch.multiprocessing as mp
+    from oracle.ref_two_phase import RefTwoPhase
+    steps = 4
+    mp.spawn(_worker_2p, args=(world, _free_port(), steps, str(tmp_path)), nprocs=world, join=True)
+    case = _case2p()
+    ref = case.make_oracle(RefTwoPhase)
+    for _ in range(steps):
+        ref.step()
+    fl = case.solid == 0
+    parts = [np.load(os.path.join(str(tmp_path), "tp_rank%d.npz" % r)) for r in range(world)]
+    for n in ("F", "rho", "v", "psi", "rho_r", "rho_b"):
+        got = np.concatenate([p[n] for p in parts], axis=0)
+        assert np.array_equal(got[fl], getattr(ref, n)[fl]), n
