@@ -132,6 +132,34 @@ def test_two_phase_sparse_script_equals_dense_script(name):
         assert np.array_equal(g[n + "_sparse"][fl], g[n][fl]), n
 
 
+@pytest.mark.skipif(not os.path.exists(refpin.mk.REF), reason="/root/reference is not mounted here")
+def test_init_geo_of_the_reference_reads_what_our_loader_reads(tmp_path):
+    """init_geo :173-177 (np.loadtxt, >0 -> 1, Fortran-order reshape) through the shim, against
+    taichi_lbm3d_b200.geometry.load_geometry on the same text file, and on .npy / .raw copies"""
+    from taichi_lbm3d_b200 import geometry
+    rng = np.random.default_rng(3)
+    shape = (4, 3, 5)
+    vals = rng.integers(0, 3, size=shape[0] * shape[1] * shape[2])          # 0, 1 and a stray 2
+    path = str(tmp_path / "geo.dat")
+    np.savetxt(path, vals, fmt="%d")
+    mod = refpin.mk.load_reference()
+    lb = mod.LB3D_Solver_Single_Phase(nx=shape[0], ny=shape[1], nz=shape[2])
+    lb.init_geo(path)
+    want = lb.solid.to_numpy()
+    got = geometry.load_geometry(path, *shape)
+    assert got.dtype == np.int8 and np.array_equal(got, want)
+    raw = str(tmp_path / "geo.raw")
+    vals.astype(np.uint8).tofile(raw)
+    assert np.array_equal(geometry.load_geometry(raw, *shape), want)
+    npy = str(tmp_path / "geo.npy")
+    np.save(npy, want)
+    assert np.array_equal(geometry.load_geometry(npy, *shape), want)
+    txt = str(tmp_path / "geo2.dat")
+    geometry.save_geometry_text(txt, want)                                    # the generator's format
+    lb.init_geo(txt)
+    assert np.array_equal(lb.solid.to_numpy(), want)
+
+
 def test_shim_is_not_reachable_from_the_product():
     """the stand-in lives under tests/ and no product module imports taichi"""
     import subprocess
