@@ -160,6 +160,39 @@ def test_init_geo_of_the_reference_reads_what_our_loader_reads(tmp_path):
     assert np.array_equal(lb.solid.to_numpy(), want)
 
 
+@pytest.mark.skipif(not os.path.exists(refpin.mk.REF2P), reason="/root/reference is not mounted here")
+def test_two_phase_init_geo_reads_what_our_class_reads(tmp_path):
+    """init_geo(filename, filename2) of the two-phase script (:194-202: geometry >0 -> 1, phase as
+    floats, both reshaped in Fortran order) against LB3D_Solver_Two_Phase.init_geo"""
+    import re
+    import sys
+    from taichi_lbm3d_b200 import LB3D_Solver_Two_Phase
+    shape = (4, 3, 5)
+    rng = np.random.default_rng(5)
+    n = shape[0] * shape[1] * shape[2]
+    geo, pha = str(tmp_path / "img.txt"), str(tmp_path / "phase.dat")
+    np.savetxt(geo, rng.integers(0, 3, size=n), fmt="%d")
+    np.savetxt(pha, rng.choice([-1.0, 1.0], size=n), fmt="%.1f")
+    src = open(refpin.mk.REF2P).read()
+    head = src[:src.index("time_init = time.time()")]
+    head = re.sub(r"^nx,ny,nz\s*=.*$", "nx,ny,nz = %d,%d,%d" % shape, head, count=1, flags=re.M)
+    shim = os.path.join(os.path.dirname(os.path.abspath(__file__)), "taichi_shim")
+    sys.path.insert(0, shim)
+    try:
+        for m in ("taichi", "pyevtk", "pyevtk.hl"):
+            sys.modules.pop(m, None)
+        ns = {"__name__": "lbm_solver_3d_2phase"}
+        exec(compile(head, refpin.mk.REF2P, "exec"), ns)
+    finally:
+        sys.path.remove(shim)
+        sys.modules.pop("taichi", None)
+    solid_ref, phase_ref = ns["init_geo"](geo, pha)
+    lb = LB3D_Solver_Two_Phase(*shape)
+    solid, phase = lb.init_geo(geo, pha)
+    assert np.array_equal(solid, solid_ref) and np.array_equal(phase, phase_ref.astype(np.float32))
+    assert np.array_equal(lb.solid.to_numpy(), solid_ref) and np.array_equal(lb.psi.to_numpy(), phase_ref.astype(np.float32))
+
+
 def test_shim_is_not_reachable_from_the_product():
     """the stand-in lives under tests/ and no product module imports taichi"""
     import subprocess
