@@ -31,6 +31,8 @@ CASES = {
                                       ("set_bc_rho_y0", 1.0), ("set_bc_vel_y1", [0.0, -0.01, 0.01]),
                                       ("set_bc_rho_z0", 1.02), ("set_bc_vel_z1", [0.0, 0.0, 0.03])], 3),
     "periodic_force": ((4, 6, 5), 0.3, 11, [("set_force", [1e-5, 2e-5, -1e-5])], 4),
+    # example_cavity.py in small (the reference's geo_cavity generator: walls on x0, y0, y1, z0, z1; lid on x1)
+    "cavity8": ((8, 8, 8), 0.0, 0, [("set_bc_vel_x1", [0.0, 0.0, 0.1])], 25),
     # one whole 3^3 block solid: never activated in the reference's sparse mode (reads give 0)
     "solid_block": ((6, 6, 6), 0.15, 13, [("set_bc_rho_x0", 1.0), ("set_bc_rho_x1", 0.995),
                                          ("set_force", [0.0, 1e-5, 0.0])], 2),
@@ -95,6 +97,9 @@ def case_solid(name):
     solid = (np.random.default_rng(seed).random(shape) < frac).astype(np.int8)
     if name == "solid_block":
         solid[3:6, 3:6, 3:6] = 1
+    if name == "cavity8":
+        from taichi_lbm3d_b200.geometry import cavity
+        solid = cavity(*shape)
     return solid
 
 
