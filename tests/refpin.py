@@ -32,15 +32,20 @@ def make_oracle(cls, name, **kw):
     return o
 
 
-def make_solver(name, sparse=False, strict=True):
-    """the CUDA class, driven with the reference's own method names"""
+def make_solver(name, sparse=False, strict=True, force_field=None, **kw):
+    """the CUDA class, driven with the reference's own method names (kw: tau_mode / guo_mode of the
+    class's other copy; force_field: the array form of a cal_local_force override, which replaces
+    the case's set_force)"""
     from taichi_lbm3d_b200 import LB3D_Solver_Single_Phase
     shape, _, _, setup, _ = mk.CASES[name]
     lb = LB3D_Solver_Single_Phase(*shape, sparse_storage=sparse in (True, "aa"), strict=strict,
-                                  in_place=sparse in ("aa", "daa"))
+                                  in_place=sparse in ("aa", "daa"), **kw)
     lb.solid.from_numpy(fixture(name)["solid"])
     for fn, arg in setup:
-        getattr(lb, fn)(arg)
+        if force_field is None or fn != "set_force":
+            getattr(lb, fn)(arg)
+    if force_field is not None:
+        lb.set_force_field(force_field)
     lb.init_simulation()
     return lb
 

@@ -146,6 +146,29 @@ def test_reference_source_fixtures(cuda, sparse):
         assert dv <= max(TOL * np.abs(g["v"][fl]).max(), 2e-7), (name, dv)
 
 
+@pytest.mark.parametrize("sparse", [False, True])
+def test_reference_other_copy_and_force_hook_fixtures(cuda, sparse):
+    """tests/golden/ref_sp_other_copy_*.npz (Phase_change/LBM_3D_SinglePhase_Solver.py through the shim:
+    tau = 3 niu + 1/2, un-scaled Guo term) and ref_sp_local_force_*.npz (a subclass overriding the
+    cal_local_force hook): verification arithmetic bit for bit"""
+    import os
+    from tests import refpin
+    for name in ("lid_and_force", "periodic_force"):
+        g = np.load(os.path.join(refpin.GOLD, "ref_sp_other_copy_%s.npz" % name))
+        fl = g["solid"] == 0
+        lb = refpin.make_solver(name, sparse=sparse, strict=True, tau_mode="textbook", guo_mode="unscaled")
+        lb.run(int(g["steps"]))
+        for n in ("F", "rho", "v"):
+            assert np.array_equal(getattr(lb, n).to_numpy()[fl], g[n][fl]), ("other copy", name, n)
+    for name in ("pressure_x", "periodic_force"):
+        g = np.load(os.path.join(refpin.GOLD, "ref_sp_local_force_%s.npz" % name))
+        fl = g["solid"] == 0
+        lb = refpin.make_solver(name, sparse=sparse, strict=True, force_field=g["force_field"])
+        lb.run(int(g["steps"]))
+        for n in ("F", "rho", "v"):
+            assert np.array_equal(getattr(lb, n).to_numpy()[fl], g[n][fl]), ("force hook", name, n)
+
+
 def test_step_by_step_equals_run(cuda):
     """step() x n, with field reads in between, equals run(n) (state machine, :477-481)."""
     case = cases.case_mixed_bc()
