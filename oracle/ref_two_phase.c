@@ -1,7 +1,7 @@
 /* CPU restatement (oracle) of the reference two-phase colour-gradient step, in C.
  *
- * TEST INFRASTRUCTURE ONLY; parity pin: the reference script run through tests/taichi_shim, matched
- * to fp32 round-off (tests/test_reference_pin.py) -- see oracle/ref_two_phase.py, whose operations
+ * TEST INFRASTRUCTURE ONLY; parity pin: the reference script run through tests/taichi_shim (bit for
+ * bit up to the order of its float atomics, tests/test_reference_pin.py) -- see oracle/ref_two_phase.py, whose operations
  * this file repeats one for one (the -ffp-contract=off build is bit-identical to the NumPy
  * form; tests/test_oracle_two_phase.py).  Line numbers cite
  * /root/reference/2phase/lbm_solver_3d_2phase.py.

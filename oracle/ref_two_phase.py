@@ -4,9 +4,11 @@ TEST INFRASTRUCTURE ONLY (see oracle/ref_single_phase.py: only tests/, smoke() a
 CPU legs may use anything under oracle/).  PARITY PIN: the reference has no tests or golden
 vectors and Taichi cannot run in this image; the kernels of the reference script itself are
 executed through tests/taichi_shim with only its hand-edited parameter lines replaced
-(tests/golden/make_reference_fixtures.py -> tests/golden/ref_tp_*.npz) and this restatement
-matches them to fp32 round-off (tests/test_reference_pin.py; not bit for bit, because the
-script accumulates rho_r / rho_b with order-dependent float atomics, :365-372).
+(tests/golden/make_reference_fixtures.py -> tests/golden/ref_tp_*.npz).  The script accumulates
+rho_r / rho_b with float atomics whose order is open (:365-372): with them executed in node
+order (accumulate_colour_in_push_order, what the shim's sequential run does) this restatement
+reproduces the script BIT FOR BIT; in its own deterministic order (_accumulate_colour, the
+order of the CUDA path) it differs by that summation order only (tests/test_reference_pin.py).
 
 Follows ``2phase/lbm_solver_3d_2phase.py`` (the dense script; ``..._sparse.py`` differs only in
 allocation) statement by statement; line numbers below cite that file.  The script is a
@@ -248,6 +250,14 @@ class RefTwoPhase:
                 nb_fluid = np.roll(fluid, (ex, ey, ez), axis=(0, 1, 2))
                 contrib = np.where(nb_fluid, from_nb, g[..., LR[s]])
                 acc[fluid] = acc[fluid] + contrib[fluid]
+
+    def accumulate_colour_in_push_order(self):
+        """:365-372 with the float atomics executed one after the other in node order (what a
+        sequential run of the script does): drop-in for _accumulate_colour; tiny cases only"""
+        rr, rb = self.push_colour_loops()
+        fl = self.solid == 0
+        self.rhor[fl] = self.rhor[fl] + rr[fl]
+        self.rhob[fl] = self.rhob[fl] + rb[fl]
 
     def push_colour_loops(self):
         """:365-372 literally (sequential node order); tiny cases only.  Returns (rhor, rhob)."""

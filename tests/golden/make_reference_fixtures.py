@@ -183,6 +183,11 @@ def run_reference_two_phase(name, script=REF2P):
         exec(compile(head, script, "exec"), ns)
     finally:
         sys.path.remove(shim)
+    # Taichi embeds the Python-scope floats a kernel reads (wl, wg, lg0, l1, ..., psi_solid, CapA) as f32
+    # constants; the script computes them in Python floats first (:100-108), so: one rounding, here
+    for k, val in list(ns.items()):
+        if isinstance(val, float):
+            ns[k] = np.float32(val)
     solid, psi = case2p_inputs(name)
     ns["solid"].from_numpy(solid)
     ns["psi"].from_numpy(psi)
@@ -199,7 +204,7 @@ def run_reference_two_phase(name, script=REF2P):
     for n in ("F", "rho", "v", "psi", "rho_r", "rho_b"):
         out[n] = ns[n].to_numpy()[:nx, :ny, :nz]        # SNode-placed fields have the extent 3*(n//3+1)
     for n in ("fx", "fy", "fz", "niu_l", "niu_g", "psi_solid", "CapA"):
-        out[n] = np.float64(ns[n])
+        out[n] = np.float32(ns[n])
     return out
 
 
