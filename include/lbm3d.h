@@ -53,6 +53,8 @@ typedef struct {
     int32_t sparse;       /* 0: direct-addressed dense lattice (:31-35);
                              1: compacted fluid-node list + 18-neighbour table, replaces the
                                 pointer/dense SNode tree (:36-44); two population buffers (A-B);
+                                at most 2^30 fluid nodes per context (split larger domains
+                                into x-slabs);
                              2: the same list stepped IN PLACE on one buffer (AA pattern): odd
                                 steps pull through the table and store back into the pulled
                                 locations, even steps are purely local -- half the memory and
