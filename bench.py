@@ -4,20 +4,28 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
-A bench "step" is ONE lattice time step (one fused kernel launch per GPU) over the whole
-workload.  N=1 workload: BASELINE config 2, the dense 256^3 lid-driven cavity
-(Single_phase/example_cavity.py scaled up; lid vz=0.1 on the x1 face).  N>1: x-slabs of
-256 planes per GPU ((256 N) x 256 x 256 cavity, weak scaling), five populations per face
-exchanged per step.
+A bench "step" is ONE lattice time step over the whole workload.
+
+Headline (`value`, `e2e`, `roofline`): BASELINE config 2, the dense 256^3 lid-driven cavity
+(Single_phase/example_cavity.py scaled up; lid vz=0.1 on the x1 face) on one GPU; on N GPUs the
+(256 N) x 256 x 256 cavity in x-slabs of 256 planes (weak scaling), five populations per face and
+direction exchanged per step.
+
+Sub-records on the same JSON line (the other BASELINE configs under the same clock):
+  strong_1024  config 5: the 1024^3 cavity split into x-slabs over the N ranks (N = 1: one
+               GPU, stepped in place on one population buffer); strong scaling
+  sparse_512   config 3: 512^3 periodic sphere pack at ~20 % porosity, compact fluid list (N = 1 only)
+  two_phase    config 4: colour-gradient drainage at 131^3 (dense and sparse storage) plus a 256^3
+               droplet box and a 384^3 pack, against the declared 176-byte roofline (N = 1 only)
 
 value   fluid-node updates per second / 1e6 with the state resident in HBM (CUDA events).
-e2e     the same metric for the whole user-level job through the Python class / C ABI with
-        HOST buffers: geometry upload (pinned host -> device) + init_simulation + K x step()
-        + rho, v and max_v back to the host, all inside the timed region.
+e2e     the same metric for the user-level job through the Python class / C ABI with HOST
+        buffers: geometry upload (pinned host -> device) + init_simulation + K x step() + rho, v and
+        max_v back to the host, all inside the timed region.
 roofline  algorithmic bytes (152 B per fluid-node update, BASELINE.json) / kernel time,
         against the measured copy bandwidth in MEASURED_PEAKS.json.
-cpu_baseline  the oracle (C/OpenMP restatement of the reference's four-pass step; Taichi
-        is not installable here) on the host cores, bounded sample.
+cpu_baseline / --impl reference   the oracle (C/OpenMP restatement of the reference's four-pass
+        step; Taichi is not installable here) on all host cores, same workload, bounded steps.
 """
 import argparse
 import json
@@ -30,8 +38,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 B_PER_LUP = 152.0          # 19 fp32 read + 19 fp32 written (BASELINE.json north_star)
-SLAB = 256                 # planes per GPU
-NY = NZ = 256
+B_PER_LUP_2P = 176.0       # + rho_r, rho_b read+write (16) + psi read+write (8): SURVEY 8d / DESIGN 4b
+SLAB = 256                 # planes per GPU (headline)
 LID = [0.0, 0.0, 0.1]
 
 
@@ -50,6 +58,35 @@ def profiled_traffic(workload):
             return json.load(fh).get(workload)
     except Exception:  # noqa: BLE001
         return None
+
+
+def headline_config(gnx, ny, nz, n_gpus):
+    """`config` of the JSON line: a function of the workload only, so both arms print the same"""
+    return {"workload": "lid-driven cavity %dx%dx%d, lid vz=0.1 on x1 (BASELINE config 2%s); D3Q19 MRT single "
+                        "phase, dense storage" % (gnx, ny, nz, "" if n_gpus == 1 else
+                                                  ", x-slabs of %d planes per GPU" % (gnx // n_gpus)),
+            "fluid_nodes": cavity_fluid_nodes(gnx, ny, nz),
+            "l2_policy": "inputs_exceed_l2 (%.2f GB of populations per GPU vs 126 MB L2)"
+                         % (2 * 19 * 4 * float(gnx // n_gpus) * ny * nz / 1e9),
+            "parallelism": "x-slabs x%d" % n_gpus}
+
+
+def cavity_fluid_nodes(nx, ny, nz):
+    return (nx - 1) * (ny - 2) * (nz - 2)
+
+
+def cavity_planes(gnx, ny, nz, planes):
+    """planes (global x indices, may repeat / wrap) of geometry.cavity(gnx, ny, nz)"""
+    import numpy as np
+    g = np.zeros((len(planes), ny, nz), np.int8)
+    g[:, 0, :] = 1
+    g[:, -1, :] = 1
+    g[:, :, 0] = 1
+    g[:, :, -1] = 1
+    for i, x in enumerate(planes):
+        if x % gnx == 0:
+            g[i] = 1
+    return g
 
 
 class ClockSampler(threading.Thread):
@@ -88,7 +125,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.02)
+            time.sleep(0.005)
 
     def stop(self):
         self._stop_evt.set()
@@ -100,18 +137,33 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_run(n, steps, warmup, threads=None):
-    """The oracle's C/OpenMP four-pass step (stand-in for ti.init(arch=ti.cpu)) on an n^3 cavity."""
+# reference arm / cpu_baseline: the oracle's C/OpenMP four-pass step on the host cores
+# ---------------------------------------------------------------------------------------------
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm uses every core it is given"""
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    try:        # libgomp may be loaded already (it read the environment then): tell it directly
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(cores)
+    except Exception:  # noqa: BLE001
+        pass
+    return cores
+
+
+def cpu_reference_run(gnx, ny, nz, steps, warmup):
+    """(gnx, ny, nz) cavity with the lid on x1 through oracle/ref_single_phase.c (-O3 build)"""
     import numpy as np
     from oracle.cref import RefSinglePhaseC
     from taichi_lbm3d_b200.geometry import cavity
-    if threads:
-        os.environ["OMP_NUM_THREADS"] = str(threads)
-    o = RefSinglePhaseC(n, n, n, kind="fast")
-    o.set_solid(cavity(n, n, n))
+    o = RefSinglePhaseC(gnx, ny, nz, kind="fast")
+    o.set_solid(cavity(gnx, ny, nz))
     o.set_bc_vel(1, LID)
     o.init_simulation()
-    nfl = int((o.solid == 0).sum())
+    nfl = int((o.solid == 0).sum(dtype=np.int64))
     if warmup:
         o.run(warmup)
     t0 = time.perf_counter()
@@ -120,30 +172,58 @@ def cpu_reference_run(n, steps, warmup, threads=None):
     return nfl * steps / dt / 1e6, dt, nfl
 
 
+def host_mem_available():
+    try:
+        with open("/proc/meminfo") as fh:
+            for line in fh:
+                if line.startswith("MemAvailable:"):
+                    return int(line.split()[1]) * 1024
+    except Exception:  # noqa: BLE001
+        pass
+    return 16 << 30
+
+
+def cpu_arm(gnx, ny, nz, steps, warmup, budget_s):
+    """The CPU arm on the SAME domain as the GPU arm, steps bounded so that it ends within
+    `budget_s`; shrinks the domain (labelled) only when the host cannot hold it."""
+    cores = use_all_host_threads()
+    cal, _, _ = cpu_reference_run(64, 64, 64, 3, 1)
+    note = None
+    need = lambda x: 200.0 * x * ny * nz          # noqa: E731  (f, F AoS + rho, v, solid, slack)
+    x = gnx
+    while x > 64 and need(x) > 0.6 * host_mem_available():
+        x //= 2
+    if x != gnx:
+        note = "host memory holds only %dx%dx%d of the %dx%dx%d domain" % (x, ny, nz, gnx, ny, nz)
+    per_step = float(x) * ny * nz / (cal * 1e6)
+    k = int(max(3, min(steps, (budget_s - warmup * per_step) / per_step)))
+    w = int(max(1, min(warmup, 2)))
+    if k != steps:
+        note = (note + "; " if note else "") + "%d of the %d steps (time bound; MLUPS does not depend on it)" % (k, steps)
+    mlups, dt, nfl = cpu_reference_run(x, ny, nz, k, w)
+    sample = "%d steps of the %dx%dx%d cavity (%d fluid nodes), %d OpenMP threads" % (k, x, ny, nz, nfl, cores)
+    if note:
+        sample += " [" + note + "]"
+    return mlups, dt / k * 1e3, cores, sample
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    cores = os.cpu_count() or 1
-    # calibrate on a small cube, then pick the largest cube <= 256 that keeps the run bounded
-    mlups_cal, _, _ = cpu_reference_run(64, 2, 1)
-    budget_s = 150.0
-    total_steps = args.steps + args.warmup
-    n = 256
-    while n > 64 and (n ** 3) * total_steps / (mlups_cal * 1e6) > budget_s:
-        n -= 32
-    mlups, dt, nfl = cpu_reference_run(n, args.steps, args.warmup)
+    n_gpus = args.gpus
+    gnx, ny, nz = SLAB * n_gpus, SLAB, SLAB
+    mlups, ms_per_step, cores, sample = cpu_arm(gnx, ny, nz, args.steps, args.warmup, 150.0)
     line = {
-        "impl": "reference", "metric": "mlups", "value": mlups, "unit": "MLUPS", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "impl": "reference", "metric": "mlups", "value": mlups, "unit": "MLUPS", "n_gpus": n_gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "lid-driven cavity %d^3 dense, D3Q19 MRT single phase (BASELINE config 2 shape)" % n,
-                   "note": "Taichi is not installable in this image; this is the oracle's C/OpenMP "
-                           "restatement of the reference's four-pass AoS step on the host cores (its strict "
-                           "build reproduces the reference source bit for bit, tests/test_reference_pin.py)"},
-        "cpu_baseline": {"value": mlups, "unit": "MLUPS", "cores": cores, "kind": "port",
-                         "sample": "%d steps of the %d^3 cavity (%d fluid nodes)" % (args.steps, n, nfl)},
+        "config": headline_config(gnx, ny, nz, n_gpus),
+        "note": "Taichi is not installable in this image; this is the oracle's C/OpenMP restatement of the "
+                "reference's four-pass AoS step on the host cores (its strict build reproduces the reference "
+                "source bit for bit, tests/test_reference_pin.py)",
+        "cpu_baseline": {"value": mlups, "unit": "MLUPS", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": mlups, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -152,6 +232,184 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+class Env:
+    """process-group plumbing shared by the headline and the sub-records"""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            self.dist = dist
+
+    def barrier(self):
+        if self.dist:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        if not self.dist:
+            return x
+        t = self.torch.tensor([x], device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, x):
+        if not self.dist:
+            return x
+        t = self.torch.tensor([x], device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t)
+        return float(t.item())
+
+    def timed(self, stepper, steps, warmup, sample_clocks=False):
+        """W untimed steps, then K steps between CUDA events on the launching stream, barrier +
+        synchronize on both sides, max over ranks.  Returns (ms, launches over all ranks, clocks)."""
+        torch = self.torch
+        stepper.run(warmup)
+        self.barrier()
+        sampler = ClockSampler(self.local_rank) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        l0 = stepper.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record()
+        stepper.run(steps)
+        e1.record()
+        self.barrier()
+        ms = self.max_over_ranks(e0.elapsed_time(e1))
+        clocks = sampler.stop() if sampler else None
+        launches = int(self.sum_over_ranks(stepper.launch_count - l0))
+        return ms, launches, clocks
+
+
+def make_cavity_solver(env, gnx, ny, nz, in_place=False, pinned=None):
+    """the lid-driven cavity on this process group: one GPU -> the class itself, N GPUs -> SlabSolver
+    with every rank uploading only its own planes (+ the two ghost planes)"""
+    if env.world == 1:
+        from taichi_lbm3d_b200 import LB3D_Solver_Single_Phase
+        lb = LB3D_Solver_Single_Phase(gnx, ny, nz, in_place=in_place)
+        lb.solid.from_numpy(pinned if pinned is not None else cavity_planes(gnx, ny, nz, range(gnx)))
+    else:
+        from taichi_lbm3d_b200.multi_gpu import SlabSolver
+        lb = SlabSolver(gnx, ny, nz)
+        lb.set_local_solid(pinned if pinned is not None else cavity_planes(gnx, ny, nz, lb.part.local_planes()))
+    lb.set_bc_vel_x1(LID)
+    lb.init_simulation()
+    return lb
+
+
+def roofline(nfl_per_gpu, steps, ms, bytes_per_update, kernel, traffic=None):
+    peak, peak_src = measured_peak()
+    achieved = bytes_per_update * nfl_per_gpu * steps / (ms * 1e-3) / 1e9        # GB/s per GPU
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "peak_source": peak_src, "bytes_per_update": bytes_per_update,
+            "kernel": kernel, "frac_of_nominal_8TBps": achieved / 8000.0}
+
+
+def sub_strong_1024(env, args):
+    """BASELINE config 5: the 1024^3 cavity, x-slabs over the ranks (one GPU: in place, one buffer)"""
+    n = args.domain or 1024
+    steps, warm = max(3, min(args.steps, 20)), 3
+    lb = make_cavity_solver(env, n, n, n, in_place=(env.world == 1))
+    ms, launches, _ = env.timed(lb, steps, warm)
+    max_v = lb.get_max_v()
+    del lb
+    env.torch.cuda.empty_cache()
+    nfl = cavity_fluid_nodes(n, n, n)
+    out = {"workload": "lid-driven cavity %d^3 (BASELINE config 5), dense storage, %s"
+                       % (n, "one GPU stepped in place (AA pattern, one population buffer)" if env.world == 1
+                          else "x-slabs over %d GPUs, two buffers, 5+5 populations per cut over NCCL" % env.world),
+           "scaling": "strong", "n_gpus": env.world, "fluid_nodes": nfl, "steps": steps, "warmup": warm,
+           "ms_per_step": ms / steps, "mlups": nfl * steps / (ms * 1e-3) / 1e6, "gpu_launches": launches,
+           "max_v": max_v,
+           "roofline": roofline(nfl / env.world, steps, ms, B_PER_LUP,
+                                "k_dense_aa" if env.world == 1 else "k_dense")}
+    return out
+
+
+def sub_sparse_512(env, args):
+    """BASELINE config 3: periodic sphere pack, compact fluid list, body force"""
+    import numpy as np
+    from taichi_lbm3d_b200 import LB3D_Solver_Single_Phase
+    from taichi_lbm3d_b200.geometry import sphere_pack
+    n = 512
+    solid = sphere_pack(n, n, n, 0.80, 8.0, 16.0, seed=512, periodic=True)
+    nfl = int((solid == 0).sum(dtype=np.int64))
+    lb = LB3D_Solver_Single_Phase(n, n, n, sparse_storage=True)
+    lb.solid.from_numpy(solid)
+    lb.set_force([1e-6, 0.0, 0.0])
+    lb.init_simulation()
+    steps, warm = max(3, args.steps), max(3, min(args.warmup, 10))
+    ms, launches, _ = env.timed(lb, steps, warm)
+    max_v = lb.get_max_v()
+    del lb
+    env.torch.cuda.empty_cache()
+    return {"workload": "periodic sphere pack 512^3, seed 512, radii U[8,16], porosity %.4f, body force fx=1e-6, "
+                        "all faces periodic (BASELINE config 3), sparse storage (compact fluid list)"
+                        % (nfl / float(n) ** 3),
+            "fluid_nodes": nfl, "steps": steps, "warmup": warm, "ms_per_step": ms / steps,
+            "mlups": nfl * steps / (ms * 1e-3) / 1e6, "gpu_launches": launches, "max_v": max_v,
+            "roofline": roofline(nfl, steps, ms, B_PER_LUP, "k_sparse", profiled_traffic("porous512_sparse"))}
+
+
+def sub_two_phase(env, args):
+    """BASELINE config 4 (drainage, 131^3 stand-in geometry, both storages) and two larger boxes"""
+    import numpy as np
+    from taichi_lbm3d_b200 import LB3D_Solver_Two_Phase
+    from taichi_lbm3d_b200.geometry import ftb131_standin, sphere_pack
+    steps, warm = max(3, args.steps), max(3, min(args.warmup, 10))
+
+    def run(name, solid, psi, sparse, traffic_key=None):
+        lb = LB3D_Solver_Two_Phase(*solid.shape, sparse_storage=sparse)
+        lb.solid.from_numpy(solid)
+        lb.psi.from_numpy(psi)
+        lb.niu_l, lb.niu_g, lb.CapA, lb.psi_solid = 0.05, 0.2, 0.005, 0.7
+        lb.init_simulation()
+        ms, launches, _ = env.timed(lb, steps, warm)
+        psi_now = lb.psi.to_numpy()[solid == 0]
+        nfl = int((solid == 0).sum(dtype=np.int64))
+        del lb
+        env.torch.cuda.empty_cache()
+        return {"workload": name, "fluid_nodes": nfl, "steps": steps, "warmup": warm, "ms_per_step": ms / steps,
+                "mlups": nfl * steps / (ms * 1e-3) / 1e6, "launches_per_step": launches / steps,
+                "psi_range": [float(psi_now.min()), float(psi_now.max())],
+                "roofline": roofline(nfl, steps, ms, B_PER_LUP_2P, "k2p_main + k2p_colour",
+                                     profiled_traffic(traffic_key) if traffic_key else None)}
+
+    out = []
+    solid = ftb131_standin()
+    psi = np.ones(solid.shape, np.float32)
+    psi[:13] = -1.0
+    text = "colour-gradient drainage 131^3 (BASELINE config 4: niu_l=0.05, niu_g=0.2, CapA=0.005, " \
+           "psi_solid=0.7; sphere-pack stand-in for the missing ftb131 files), %s storage"
+    out.append(run(text % "dense", solid, psi, False))
+    out.append(run(text % "sparse", solid, psi, True))
+    n = 256
+    x, y, z = np.meshgrid(*[np.arange(n, dtype=np.float32)] * 3, indexing='ij', sparse=True)
+    r2 = (x - n / 2) ** 2 + (y - n / 2) ** 2 + (z - n / 2) ** 2
+    out.append(run("droplet (radius 64) in a periodic 256^3 box, config 4 fluid parameters, dense storage",
+                   np.zeros((n, n, n), np.int8), np.where(r2 < (n / 4) ** 2, -1.0, 1.0).astype(np.float32), False,
+                   "two_phase_droplet256_dense"))
+    n = 384
+    solid = sphere_pack(n, n, n, 0.80, 6.0, 12.0, seed=n, periodic=True)
+    psi = np.ones(solid.shape, np.float32)
+    psi[:n // 4] = -1.0
+    out.append(run("drainage in a periodic 384^3 sphere pack (porosity 0.2), config 4 fluid parameters, sparse storage",
+                   solid, psi, True, "two_phase_porous384_sparse"))
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -159,208 +417,121 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sparse", action="store_true", help="use the compacted fluid-list storage")
-    ap.add_argument("--size", type=int, default=SLAB, help="cube edge / planes per GPU (default 256)")
+    ap.add_argument("--size", type=int, default=SLAB, help="cube edge / planes per GPU of the headline (default 256)")
     ap.add_argument("--domain", type=int, default=0,
-                    help="fixed GLOBAL cube edge split into x-slabs over the ranks (strong scaling, BASELINE "
-                         "config 5: --domain 1024); default 0 = weak scaling with --size planes per GPU")
-    ap.add_argument("--workload", default="cavity", choices=["cavity", "porous"],
-                    help="cavity: BASELINE config 2 (headline); porous: config 3, periodic sphere pack at "
-                         "~20%% porosity, body force fx=1e-6 (use with --sparse)")
+                    help="edge of the strong-scaling cube (sub-record strong_1024; default 1024)")
+    ap.add_argument("--subs", default="auto",
+                    help="comma list of sub-records (strong_1024,sparse_512,two_phase), 'none', or 'auto' = all "
+                         "on one GPU, strong_1024 on N > 1")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         return run_reference(args)
 
     import numpy as np
-    import torch
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    n_gpus = world
-
-    from taichi_lbm3d_b200.geometry import cavity, sphere_pack
+    env = Env()
+    torch = env.torch
+    world, rank, n_gpus = env.world, env.rank, env.world
     n = args.size
     ny = nz = n
     gnx = n * n_gpus
-    if args.domain:
-        gnx = ny = nz = args.domain
-        n = (gnx + n_gpus - 1) // n_gpus
-    if os.environ.get("LBM3D_BENCH_SHAPE") and n_gpus == 1:      # tuning experiments: "nx,ny,nz"
-        gnx, ny, nz = (int(t) for t in os.environ["LBM3D_BENCH_SHAPE"].split(","))
-        n = gnx
-    porous = args.workload == "porous"
-    if porous:
-        r0 = max(3.0, 8.0 * n / 512.0)
-        solid = sphere_pack(gnx, ny, nz, 0.80, r0, 2 * r0, seed=n, periodic=True)
-    else:
-        solid = cavity(gnx, ny, nz)
-    nfl_total = int((solid == 0).sum())
+    nfl_total = cavity_fluid_nodes(gnx, ny, nz)
 
-    def configure(lb):
-        if porous:
-            lb.set_force([1e-6, 0.0, 0.0])
-        else:
-            lb.set_bc_vel_x1(LID)
-
-    if world == 1:
-        from taichi_lbm3d_b200 import LB3D_Solver_Single_Phase
-        lb = LB3D_Solver_Single_Phase(gnx, ny, nz, sparse_storage=args.sparse)
-        lb.solid.from_numpy(solid)
-        configure(lb)
-        lb.init_simulation()
-        stepper = lb
-    else:
-        from taichi_lbm3d_b200.multi_gpu import SlabSolver
-        lb = SlabSolver(gnx, ny, nz, sparse_storage=args.sparse)
-        lb.set_solid(solid)
-        configure(lb)
-        lb.init_simulation()
-        stepper = lb
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident timing --------------------------------------------------------------
-    stepper.run(args.warmup)
-    barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    l0 = stepper.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    stepper.run(args.steps)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    clocks = sampler.stop()
-    launches = stepper.launch_count - l0
-    if world > 1:
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        lt = torch.tensor([launches], device="cuda")
-        dist.all_reduce(lt)
-        launches = int(lt.item())
+    # ---- device-resident timing ---------------------------------------------------------------
+    lb = make_cavity_solver(env, gnx, ny, nz)
+    ms, launches, clocks = env.timed(lb, args.steps, args.warmup, sample_clocks=True)
     mlups = nfl_total * args.steps / (ms * 1e-3) / 1e6
-    max_v = stepper.get_max_v()
-
-    # ---- end to end through the public API with host buffers ---------------------------------
-    # the whole user-level job: host geometry in (pinned), init_simulation (table / flag build),
-    # K x step(), rho, v and max_v back into pinned host buffers; wall clock between barriers,
-    # max over ranks
-    del lb, stepper
+    max_v = lb.get_max_v()
+    del lb
     torch.cuda.empty_cache()
-    from taichi_lbm3d_b200 import LB3D_Solver_Single_Phase
-    from taichi_lbm3d_b200.multi_gpu import SlabPartition, SlabSolver
-    own = SlabPartition(gnx, world, rank).own
-    pinned = torch.from_numpy(solid).pin_memory()
-    rho_pin = torch.empty((own, ny, nz), dtype=torch.float32, pin_memory=True)
-    v_pin = torch.empty((own, ny, nz, 3), dtype=torch.float32, pin_memory=True)
-    barrier()
+
+    # ---- end to end through the public API with host buffers -----------------------------------
+    # the user-level job: host geometry in (pinned), init_simulation (flag / table build), K x step(),
+    # rho, v and max_v back into pinned host buffers; wall clock between barriers, max over ranks.
+    # At N > 1 every rank handles only its own slab; the process-wide NCCL communicator exists
+    # already (like the CUDA context, it is created once per process, not per solver).
+    from taichi_lbm3d_b200.multi_gpu import SlabPartition
+    part = SlabPartition(gnx, world, rank)
+    planes = range(gnx) if world == 1 else part.local_planes()
+    pinned = torch.from_numpy(cavity_planes(gnx, ny, nz, planes)).pin_memory()
+    rho_pin = torch.empty((part.own, ny, nz), dtype=torch.float32, pin_memory=True)
+    v_pin = torch.empty((part.own, ny, nz, 3), dtype=torch.float32, pin_memory=True)
+    env.barrier()
     t0 = time.perf_counter()
+    lb2 = make_cavity_solver(env, gnx, ny, nz, pinned=pinned.numpy())     # H2D + flag build
+    t_init = time.perf_counter() - t0
+    for _ in range(args.steps):                      # the reference scripts' loop: one call per step
+        lb2.step()
+    torch.cuda.synchronize()
+    t_steps = time.perf_counter() - t0 - t_init
     if world == 1:
-        lb2 = LB3D_Solver_Single_Phase(gnx, ny, nz, sparse_storage=args.sparse)
-        lb2.solid.from_numpy(pinned.numpy())            # host geometry in
-        configure(lb2)
-        lb2.init_simulation()                           # H2D + table build
-        t_init = time.perf_counter() - t0
-        for _ in range(args.steps):                     # the reference scripts' loop: one call per step
-            lb2.step()
-        lb2.synchronize()
-        t_steps = time.perf_counter() - t0 - t_init
-        rho_h = lb2.rho.to_numpy(out=rho_pin.numpy())   # D2H results into pinned host buffers
+        rho_h = lb2.rho.to_numpy(out=rho_pin.numpy())                     # D2H into pinned host buffers
         v_h = lb2.v.to_numpy(out=v_pin.numpy())
-        h2d = solid.nbytes
     else:
-        lb2 = SlabSolver(gnx, ny, nz, sparse_storage=args.sparse)
-        lb2.set_solid(pinned.numpy())
-        configure(lb2)
-        lb2.init_simulation()
-        t_init = time.perf_counter() - t0
-        for _ in range(args.steps):
-            lb2.step()
-        torch.cuda.synchronize()
-        t_steps = time.perf_counter() - t0 - t_init
         rho_pin.numpy()[...] = lb2.local_field("rho")
         v_pin.numpy()[...] = lb2.local_field("v")
         rho_h, v_h = rho_pin.numpy(), v_pin.numpy()
-        h2d = (own + 2) * ny * nz
     mv = lb2.get_max_v()
-    barrier()
-    dt = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
+    env.barrier()
+    dt = env.max_over_ranks(time.perf_counter() - t0)
     e2e = {"value": nfl_total * args.steps / dt / 1e6, "unit": "MLUPS",
-           "h2d_bytes_per_step": h2d * n_gpus / args.steps,
-           "d2h_bytes_per_step": (rho_h.nbytes + v_h.nbytes + 4) * n_gpus / args.steps,
+           "h2d_bytes_per_step": env.sum_over_ranks(pinned.numel()) / args.steps,
+           "d2h_bytes_per_step": env.sum_over_ranks(rho_h.nbytes + v_h.nbytes + 4) / args.steps,
            "job": "geometry upload + init_simulation + %d x step() + rho, v, max_v to host%s"
-                  % (args.steps, "" if world == 1 else " (every rank its slab; includes creating the NCCL communicator)"),
+                  % (args.steps, "" if world == 1 else " (every rank its own slab)"),
            "seconds": dt, "seconds_init": t_init, "seconds_steps": t_steps,
            "seconds_readback": dt - t_init - t_steps, "max_v": mv}
     del lb2
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configs under the same clock -----------------------------------------
+    subs = args.subs
+    if subs == "auto":
+        subs = "strong_1024,sparse_512,two_phase" if world == 1 else "strong_1024"
+    extra = {}
+    for name in [s for s in subs.split(",") if s and s != "none"]:
+        fn = {"strong_1024": sub_strong_1024, "sparse_512": sub_sparse_512, "two_phase": sub_two_phase}[name]
+        if world > 1 and name != "strong_1024":
+            continue
+        try:
+            extra[name] = fn(env, args)
+        except Exception as ex:  # noqa: BLE001  (a sub-record must not take the headline down)
+            if world > 1:
+                raise                   # the other ranks are inside collectives: fail together
+            extra[name] = {"error": "%s: %s" % (type(ex).__name__, ex)}
+            torch.cuda.empty_cache()
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        if env.dist:
+            env.dist.destroy_process_group()
         return 0
 
-    peak, peak_src = measured_peak()
-    achieved = B_PER_LUP * (nfl_total / n_gpus) * args.steps / (ms * 1e-3) / 1e9    # GB/s per GPU
-    workload = "%s%d_%s" % (args.workload, n, "sparse" if args.sparse else "dense")
-    wl_text = ("periodic sphere pack %dx%dx%d at porosity %.3f, body force fx=1e-6 (BASELINE config 3 shape)"
-               % (gnx, ny, nz, nfl_total / float(gnx * ny * nz))) if porous else \
-        ("lid-driven cavity %dx%dx%d, lid vz=0.1 on x1 (BASELINE config 2%s)"
-         % (gnx, ny, nz, "" if n_gpus == 1 else ", x-slabs of %d planes per GPU" % n))
     line = {
         "metric": "mlups", "value": mlups, "unit": "MLUPS", "n_gpus": n_gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "strong" if args.domain else "weak", "vs_baseline": mlups / 900.0 if n_gpus == 1 else None,
+        "scaling": "weak", "vs_baseline": mlups / 900.0 if n_gpus == 1 else None,
+        "vs_baseline_note": "900 MLUPS: README.md:5 of the reference, one A100, grid size unstated",
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s; D3Q19 MRT single phase, %s" % (wl_text, "sparse storage (compact fluid list)"
-                                                                    if args.sparse else "dense storage"),
-                   "fluid_nodes": nfl_total, "l2_policy": "inputs_exceed_l2 (%.2f GB of populations per GPU vs 126 MB L2)"
-                   % (2 * 19 * 4 * float(n) * ny * nz / 1e9),
-                   "vs_baseline_note": "900 MLUPS: README.md:5, one A100, grid size unstated",
-                   "parallelism": "x-slabs x%d" % n_gpus, "max_v": max_v},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": profiled_traffic(workload), "peak_source": peak_src,
-                     "bytes_per_update": B_PER_LUP, "kernel": "k_sparse" if args.sparse else "k_dense",
-                     "frac_of_nominal_8TBps": achieved / 8000.0},
-        "clocks": clocks, "gpu_launches": launches,
+        "config": headline_config(gnx, ny, nz, n_gpus),
+        "max_v": max_v,
+        "roofline": roofline(nfl_total / n_gpus, args.steps, ms, B_PER_LUP, "k_dense",
+                             profiled_traffic("cavity%d_dense" % n)),
+        "clocks": clocks, "gpu_launches": launches, "e2e": e2e,
     }
-    if e2e is not None:
-        line["e2e"] = e2e
+    line.update(extra)
     if not args.no_cpu_baseline and n_gpus == 1:
         try:
-            cores = os.cpu_count() or 1
-            # bounded sample: about 12 s of host time on a 128^3 cavity, sized from a 64^3 probe
-            cal, _, _ = cpu_reference_run(64, 2, 1)
-            nb = 128
-            sb = int(max(5, min(400, 12.0 * cal * 1e6 / nb ** 3)))
-            v, dtc, nflc = cpu_reference_run(nb, sb, 1)
+            v, _, cores, sample = cpu_arm(gnx, ny, nz, args.steps, args.warmup, 15.0)
             line["cpu_baseline"] = {"value": v, "unit": "MLUPS", "cores": cores, "kind": "port",
-                                    "sample": "%d steps of a %d^3 cavity (same BCs), C/OpenMP restatement of the "
-                                              "reference's 4-pass step (its strict build reproduces the reference "
-                                              "source bit for bit, tests/test_reference_pin.py); Taichi unavailable"
-                                              % (sb, nb)}
+                                    "sample": sample + "; C/OpenMP restatement of the reference's 4-pass step "
+                                    "(its strict build reproduces the reference source bit for bit, "
+                                    "tests/test_reference_pin.py); Taichi unavailable"}
         except Exception as ex:  # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "unit": "MLUPS", "cores": os.cpu_count(), "kind": "port",
                                     "sample": "failed: %s" % ex}
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    if env.dist:
+        env.dist.destroy_process_group()
     return 0
 
 

@@ -275,20 +275,52 @@ class LB3D_Solver_Single_Phase:
                                        np.ascontiguousarray(v[0:self.nx, 0:self.ny, 0:self.nz, 2]))})
 
     # ---- checkpoint / restart (the reference cannot resume: its VTK dumps lack populations) ----
-    def save_checkpoint(self, path):
-        """state of the run (F, rho, v) + geometry as a compressed .npz"""
-        np.savez_compressed(path, nx=self.nx, ny=self.ny, nz=self.nz, solid=self._solid_host,
-                            F=self.F.to_numpy(), rho=self.rho.to_numpy(), v=self.v.to_numpy())
+    @staticmethod
+    def _ckpt_path(path):
+        path = str(path)
+        return path if path.endswith(".npz") else path + ".npz"      # what np.savez appends
 
-    def load_checkpoint(self, path):
-        """restore F, rho, v saved by save_checkpoint (after init_simulation(), same geometry)"""
-        d = np.load(path)
+    def _case_settings(self):
+        """everything besides the state that decides how the run continues"""
+        bcs = []
+        for face in range(6):
+            t, rho, vel = self._bc_tuple(face)
+            bcs.append([float(t), float(rho)] + [float(c) for c in vel])
+        return {"niu": float(self.niu), "force": [float(self.fx), float(self.fy), float(self.fz)],
+                "tau_mode": self.tau_mode, "guo_mode": self.guo_mode, "bc": bcs}
+
+    def save_checkpoint(self, path):
+        """state of the run (F, rho, v), geometry, per-node force and the case settings (viscosity,
+        force, BCs, tau/guo mode) as a compressed .npz (``.npz`` is appended if missing)"""
+        import json
+        extra = {} if self._force_field is None else {"force_field": self._force_field}
+        np.savez_compressed(self._ckpt_path(path), nx=self.nx, ny=self.ny, nz=self.nz, solid=self._solid_host,
+                            F=self.F.to_numpy(), rho=self.rho.to_numpy(), v=self.v.to_numpy(),
+                            settings=np.array(json.dumps(self._case_settings())), **extra)
+
+    def load_checkpoint(self, path, strict_settings=True):
+        """restore F, rho, v (and the per-node force) saved by save_checkpoint, after
+        init_simulation() on the same geometry.  The case settings stored with the state must equal
+        this solver's (a restart with other setters would silently continue a different case);
+        ``strict_settings=False`` only warns."""
+        import json
+        d = np.load(self._ckpt_path(path))
         if (int(d["nx"]), int(d["ny"]), int(d["nz"])) != (self.nx, self.ny, self.nz) or \
                 not np.array_equal(d["solid"], self._solid_host):
             raise ValueError("checkpoint was written for a different lattice")
+        if "settings" in d.files:
+            saved, mine = json.loads(str(d["settings"])), self._case_settings()
+            if saved != mine:
+                msg = "checkpoint settings differ from this solver's: saved %s, now %s" % (saved, mine)
+                if strict_settings:
+                    raise ValueError(msg)
+                import warnings
+                warnings.warn(msg)
         self.F.from_numpy(d["F"])
         self.rho.from_numpy(d["rho"])
         self.v.from_numpy(d["v"])
+        if "force_field" in d.files:
+            self.set_force_field(d["force_field"])
 
     # ---- sparse-storage tables (bit-exact compaction checks) ---------------------------------
     def num_fluid(self):
@@ -352,8 +384,11 @@ class LB3D_Solver_Single_Phase:
             a = np.asarray(arr)
             if a.shape != (self.nx, self.ny, self.nz):
                 raise ValueError("solid must have shape %s" % ((self.nx, self.ny, self.nz),))
+            # the reference allows init_geo(A); init_simulation(); ...; init_geo(B); init_simulation():
+            # a new geometry makes the running context stale, the next init_simulation() rebuilds it
             if self._ctx is not None:
-                raise _lib.LbmError("geometry is fixed at init_simulation()")
+                self._lib.lbm_destroy(self._ctx)
+                self._ctx = None
             self._solid_host = (a > 0).view(np.int8)        # init_geo :175 (bool viewed as 0/1 bytes: one pass)
             return
         if name == "f":

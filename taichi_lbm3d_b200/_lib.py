@@ -121,20 +121,30 @@ def library_path():
 
 
 def load():
-    """Load (building first if the sources are newer and nvcc exists) the CUDA library."""
+    """Load the CUDA library, (re)building it first when it is missing or older than its sources
+    (csrc/, include/*.h) and nvcc exists.  LBM3D_LIB selects a differently tuned build of the same
+    sources (python -m taichi_lbm3d_b200.build --tag NAME --flags "-D..."), used as it is."""
     global _lib
     if _lib is not None:
         return _lib
-    # LBM3D_LIB: a differently tuned build of the same sources (python -m taichi_lbm3d_b200.build
-    # --tag NAME --flags "-D..."), for A/B timing on the GPU box
-    path = os.environ.get("LBM3D_LIB") or _build.LIB
-    if not os.path.exists(path):
+    path = os.environ.get("LBM3D_LIB")
+    if path:
+        if not os.path.exists(path):
+            raise ImportError("taichi_lbm3d_b200: LBM3D_LIB=%s does not exist" % path)
+    else:
+        path = _build.LIB
         try:
-            _build.build()
+            # every rank of a multi-GPU job comes through here: one builder at a time
+            with _build.build_lock():
+                if _build.needs_build() and (_build.have_nvcc() or not os.path.exists(path)):
+                    _build.build()
         except Exception as e:  # noqa: BLE001
-            raise ImportError(
-                "taichi_lbm3d_b200: %s is missing and could not be built (%s). Run "
-                "`python -m taichi_lbm3d_b200.build`; there is no CPU fallback." % (path, e))
+            if not os.path.exists(path):
+                raise ImportError(
+                    "taichi_lbm3d_b200: %s is missing and could not be built (%s). Run "
+                    "`python -m taichi_lbm3d_b200.build`; there is no CPU fallback." % (path, e))
+            raise ImportError("taichi_lbm3d_b200: %s is older than its sources and the rebuild failed: %s"
+                              % (path, e))
     lib = ctypes.CDLL(path)
     for table in (SIGNATURES, SIGNATURES_2P):
         for name, (res, args) in table.items():

@@ -42,14 +42,57 @@ def _nvcc():
 def _sources():
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
     deps.append(os.path.join(HERE, "..", "include", "lbm3d.h"))
+    deps.append(os.path.join(HERE, "..", "include", "lbm3d_2phase.h"))
     return [d for d in deps if os.path.isfile(d)]
+
+
+def have_nvcc():
+    try:
+        _nvcc()
+        return True
+    except RuntimeError:
+        return False
+
+
+class build_lock:
+    """Exclusive lock file around needs_build()/build(): the ranks of a multi-GPU job all call
+    _lib.load(), and only one of them may write lib/obj/*.o and link."""
+
+    def __enter__(self):
+        import fcntl
+        os.makedirs(LIBDIR, exist_ok=True)
+        self._fh = open(os.path.join(LIBDIR, ".build.lock"), "w")
+        fcntl.flock(self._fh, fcntl.LOCK_EX)
+        return self
+
+    def __exit__(self, *exc):
+        import fcntl
+        fcntl.flock(self._fh, fcntl.LOCK_UN)
+        self._fh.close()
+        return False
+
+
+def _source_hash():
+    """content hash of every source the library is built from (mtimes do not survive the copy to
+    a GPU box, contents do)"""
+    import hashlib
+    h = hashlib.sha256()
+    for path in sorted(_sources()):
+        h.update(os.path.basename(path).encode())
+        with open(path, "rb") as fh:
+            h.update(fh.read())
+    h.update(os.environ.get("LBM3D_NVCC_FLAGS", "").encode())
+    return h.hexdigest()
 
 
 def needs_build():
     if not os.path.exists(LIB):
         return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(s) > t for s in _sources())
+    try:
+        with open(LIB + ".srchash") as fh:
+            return fh.read().strip() != _source_hash()
+    except OSError:
+        return True
 
 
 def build(force=False, verbose=False, tag=None, flags=None):
@@ -97,6 +140,8 @@ def build(force=False, verbose=False, tag=None, flags=None):
     if r.returncode != 0:
         raise RuntimeError("link failed: %s\n%s" % (" ".join(cmd), r.stdout.decode(errors="replace")))
     os.replace(tmp, LIB)
+    with open(LIB + ".srchash", "w") as fh:
+        fh.write(_source_hash())
     return LIB
 
 

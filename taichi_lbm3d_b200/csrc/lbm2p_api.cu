@@ -203,6 +203,8 @@ void fill2(const lbm2p_ctx *c, Step2Args &A, const float *fin, float *fout) {
     }
     a.row_first = c->row_first;
     a.row_count = c->row_count;
+    a.row_split = 0xFFFFFFFFu; a.row_skip = 0;
+    a.nb1 = 0xFFFFFFFFu; a.first2 = 0; a.count2 = 0;
     a.halo_x = c->halo ? 1 : 0;
     a.prow = c->prow;
     a.spec = c->spec;
@@ -364,7 +366,6 @@ int lbm2p_destroy(lbm2p_ctx *c) {
     CTX2(c);
     cudaSetDevice(c->cfg.device);
     cudaDeviceSynchronize();
-    if (c->comm && g_nccl.ok) g_nccl.CommDestroy(c->comm);
     for (int i = 0; i < 2; ++i) { cudaFree(c->d_send[i]); cudaFree(c->d_recv[i]); }
     if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
     for (cudaEvent_t ev : {c->ev_cb, c->ev_xb, c->ev_mb, c->ev_xa})
@@ -767,7 +768,7 @@ int lbm2p_comm_init(lbm2p_ctx *c, const void *id128, int world, int rank) {
         if (!load_nccl(err)) FAIL2(c, -2, "%s", err.c_str());
         NcclId id;
         memcpy(&id, id128, sizeof id);
-        NC2(c, g_nccl.CommInitRank(&c->comm, world, id, rank));
+        NC2(c, shared_comm(world, rank, id, &c->comm));
     }
     c->comm_world = world;
     c->comm_rank = rank;
@@ -1021,17 +1022,8 @@ int lbm2p_get_max_v(lbm2p_ctx *c, float *out) {
     if (!out) FAIL2(c, -1, "null destination");
     int r = sync2(c, true, false);
     if (r) return r;
-    const int init_bits = 0x80000000;
-    CU2(c, cudaMemcpyAsync(c->d_scalar, &init_bits, sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    k_max_v<<<148 * 8, 256, 0, c->stream>>>(c->d_v, c->N, c->d_scalar);
-    CU2(c, cudaGetLastError());
+    CU2(c, max_v_reduce(c->d_v, c->N, c->d_scalar, c->stream, out));
     c->launches++;
-    int bits = 0;
-    CU2(c, cudaMemcpyAsync(&bits, c->d_scalar, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CU2(c, cudaStreamSynchronize(c->stream));
-    float v;
-    memcpy(&v, &bits, sizeof v);
-    *out = bits < 0 ? -1e10f : v;
     return 0;
 }
 

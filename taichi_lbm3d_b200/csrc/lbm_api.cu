@@ -96,7 +96,7 @@ struct lbm_ctx {
     void *comm = nullptr;            // ncclComm_t
     int comm_world = 1, comm_rank = 0;
     cudaStream_t comm_stream = nullptr;
-    cudaEvent_t ev_boundary = nullptr, ev_comm = nullptr;
+    cudaEvent_t ev_boundary = nullptr, ev_comm = nullptr, ev_interior = nullptr;
     float *d_send[2] = {nullptr, nullptr}, *d_recv[2] = {nullptr, nullptr};
 };
 
@@ -187,6 +187,8 @@ void fill_args(const lbm_ctx *c, StepArgs &a) {
     a.count = c->own_count;
     a.row_first = c->row_first;
     a.row_count = c->row_count;
+    a.row_split = 0xFFFFFFFFu; a.row_skip = 0;
+    a.nb1 = 0xFFFFFFFFu; a.first2 = 0; a.count2 = 0;
     a.prow = c->prow;
     a.spec = c->spec;
     a.nx = c->cfg.nx; a.ny = c->cfg.ny; a.nz = c->cfg.nz;
@@ -385,6 +387,70 @@ int exchange_impl(lbm_ctx *c, int which, cudaStream_t st) {
     return halo_unpack_impl(c, 1, which, from_right, st);
 }
 
+// the same exchange with one pack launch and one unpack launch for both sides (native slab loop)
+int exchange_merged(lbm_ctx *c, int which, cudaStream_t st) {
+    static const HaloDirs kR = {{1, 7, 9, 11, 13}}, kL = {{2, 8, 10, 12, 14}};
+    float *buf = c->d_f[which ? c->cur ^ 1 : c->cur];
+    StepArgs a;
+    fill_args(c, a);
+    if (c->cfg.sparse) a.nz = 0;
+    const uint32_t *pf = c->plane_first, *pc = c->plane_count;
+    const uint32_t most = pc[1] > pc[2] ? pc[1] : pc[2], most_g = pc[0] > pc[3] ? pc[0] : pc[3];
+    if (most) {
+        set_buffers(c, a, buf, nullptr);
+        HaloSide s0{pf[1], pf[1], pc[1], kL, c->d_send[0]}, s1{pf[2], pf[2], pc[2], kR, c->d_send[1]};
+        k_halo_pack2<<<dim3(nblocks(most, 256), 2), 256, 0, st>>>(a, s0, s1);
+        CU(c, cudaGetLastError());
+        c->launches++;
+    }
+    float *from_left = c->d_send[1], *from_right = c->d_send[0];   // ring of one slab
+    if (c->comm_world > 1) {
+        const int left = (c->comm_rank + c->comm_world - 1) % c->comm_world;
+        const int right = (c->comm_rank + 1) % c->comm_world;
+        NC(c, g_nccl.GroupStart());
+        // posting order matters when left == right (two ranks): pairs match in order
+        NC(c, g_nccl.Send(c->d_send[1], (size_t)5 * pc[2], 7, right, c->comm, st));
+        NC(c, g_nccl.Send(c->d_send[0], (size_t)5 * pc[1], 7, left, c->comm, st));
+        NC(c, g_nccl.Recv(c->d_recv[0], (size_t)5 * pc[0], 7, left, c->comm, st));
+        NC(c, g_nccl.Recv(c->d_recv[1], (size_t)5 * pc[3], 7, right, c->comm, st));
+        NC(c, g_nccl.GroupEnd());
+        from_left = c->d_recv[0];
+        from_right = c->d_recv[1];
+    }
+    if (most_g) {
+        set_buffers(c, a, nullptr, buf);
+        // the left ghost receives what the left neighbour sent to its right (e_x = +1) and v.v.
+        HaloSide g0{pf[0], pf[0], pc[0], kR, from_left}, g1{pf[3], pf[3], pc[3], kL, from_right};
+        k_halo_unpack2<<<dim3(nblocks(most_g, 256), 2), 256, 0, st>>>(a, g0, g1);
+        CU(c, cudaGetLastError());
+        c->launches++;
+    }
+    return LBM_OK;
+}
+
+// first and last owned plane of a slab in one launch (buffer cur -> cur ^ 1)
+int launch_boundary_planes(lbm_ctx *c, cudaStream_t st) {
+    const int own = c->cfg.nx - 2;
+    StepArgs a;
+    fill_args(c, a);
+    set_buffers(c, a, c->d_f[c->cur], c->d_f[c->cur ^ 1]);
+    if (!c->cfg.sparse) {
+        const uint32_t ny = (uint32_t)c->cfg.ny;
+        a.row_first = ny;
+        a.row_count = 2 * ny;
+        a.row_split = ny;
+        a.row_skip = ny * (uint32_t)(own - 2);
+    } else {
+        a.first = c->plane_rank[1];
+        a.count = c->plane_rank[2] - a.first;
+        a.first2 = c->plane_rank[own];
+        a.count2 = c->plane_rank[own + 1] - a.first2;
+        if (a.count2 == 0) a.first2 = a.first;
+        a.nb1 = a.count ? (a.first + a.count + 255u) / 256u - a.first / 256u : 0u;
+    }
+    return launch(c, MODE_STEP, a, st);
+}
+
 }  // namespace
 
 extern "C" {
@@ -441,10 +507,10 @@ int lbm_destroy(lbm_ctx *ctx) {
     CTX_CHECK(ctx);
     cudaSetDevice(ctx->cfg.device);
     cudaDeviceSynchronize();
-    if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
     if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
     if (ctx->ev_boundary) cudaEventDestroy(ctx->ev_boundary);
     if (ctx->ev_comm) cudaEventDestroy(ctx->ev_comm);
+    if (ctx->ev_interior) cudaEventDestroy(ctx->ev_interior);
     for (int i = 0; i < 2; ++i) { cudaFree(ctx->d_send[i]); cudaFree(ctx->d_recv[i]); }
     free_device(ctx);
     delete ctx;
@@ -832,19 +898,8 @@ int lbm_get_max_v(lbm_ctx *c, float *out) {
     if (!out) FAIL(c, LBM_ERR_INVALID, "null destination");
     int r = sync_fields(c, false);
     if (r) return r;
-    const float seed = -1e10f;        // :395
-    // atomicMax on the int image orders non-negative floats; start below every one of them
-    const int init_bits = 0x80000000;
-    CU(c, cudaMemcpyAsync(c->d_scalar, &init_bits, sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    k_max_v<<<148 * 8, 256, 0, c->stream>>>(c->d_v, c->N, c->d_scalar);
-    CU(c, cudaGetLastError());
+    CU(c, max_v_reduce(c->d_v, c->N, c->d_scalar, c->stream, out));
     c->launches++;
-    int bits = 0;
-    CU(c, cudaMemcpyAsync(&bits, c->d_scalar, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
-    float v;
-    memcpy(&v, &bits, sizeof v);
-    *out = bits < 0 ? seed : v;
     return LBM_OK;
 }
 
@@ -966,7 +1021,7 @@ int lbm_comm_init(lbm_ctx *c, const void *id128, int world, int rank) {
         if (!load_nccl(err)) FAIL(c, LBM_ERR_CUDA, "%s", err.c_str());
         NcclId id;
         memcpy(&id, id128, sizeof id);
-        NC(c, g_nccl.CommInitRank(&c->comm, world, id, rank));
+        NC(c, shared_comm(world, rank, id, &c->comm));
     }
     c->comm_world = world;
     c->comm_rank = rank;
@@ -980,6 +1035,7 @@ int lbm_comm_init(lbm_ctx *c, const void *id128, int world, int rank) {
     }
     if (!c->ev_boundary) CU(c, cudaEventCreateWithFlags(&c->ev_boundary, cudaEventDisableTiming));
     if (!c->ev_comm) CU(c, cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming));
+    if (!c->ev_interior) CU(c, cudaEventCreateWithFlags(&c->ev_interior, cudaEventDisableTiming));
     const uint32_t sc[2] = {c->plane_count[1], c->plane_count[2]}, rc[2] = {c->plane_count[0], c->plane_count[3]};
     for (int i = 0; i < 2; ++i) {
         if (!c->d_send[i]) CU(c, cudaMalloc(&c->d_send[i], (size_t)5 * (sc[i] ? sc[i] : 1) * sizeof(float)));
@@ -1020,21 +1076,34 @@ int lbm_run_slab(lbm_ctx *c, int nsteps, int overlap, void *cuda_stream) {
             if (r) return r;
             continue;
         }
-        // boundary planes -> exchange on the side stream || interior planes -> join
-        int r = lbm_step_planes(c, 1, 2, st);
+        // Two streams, no per-step join.  Step n reads buffer cur, writes cur ^ 1:
+        //   main stream  interior(n)  = planes 2..own-1; reads planes 1..own of cur, never a ghost
+        //                plane: needs interior(n-1) (stream order) and boundary(n-1) (ev_boundary)
+        //   side stream  boundary(n)  = planes 1 and own in ONE launch; needs interior(n-1)
+        //                (ev_interior) and the ghost planes filled by exchange(n-1) (stream order);
+        //                then exchange(n): pack (one launch) ; ncclSend/Recv ; unpack (one launch)
+        // so consecutive interior kernels run back to back while the side stream (highest
+        // priority) has a whole step of slack for the boundary planes and the exchange.
+        if (it == 0) {
+            CU(c, cudaEventRecord(c->ev_interior, st));          // everything enqueued on st so far
+            CU(c, cudaEventRecord(c->ev_boundary, st));
+        }
+        CU(c, cudaStreamWaitEvent(st, c->ev_boundary, 0));       // boundary(n-1)
+        int r = lbm_step_planes(c, 2, own, st);                  // interior(n)
         if (r) return r;
-        r = lbm_step_planes(c, own, own + 1, st);
+        CU(c, cudaStreamWaitEvent(c->comm_stream, c->ev_interior, 0));   // interior(n-1)
+        CU(c, cudaEventRecord(c->ev_interior, st));              // interior(n)
+        r = launch_boundary_planes(c, c->comm_stream);           // boundary(n)
         if (r) return r;
-        CU(c, cudaEventRecord(c->ev_boundary, st));
-        CU(c, cudaStreamWaitEvent(c->comm_stream, c->ev_boundary, 0));
-        r = exchange_impl(c, 1, c->comm_stream);
+        CU(c, cudaEventRecord(c->ev_boundary, c->comm_stream));
+        r = exchange_merged(c, 1, c->comm_stream);               // ghost planes of buffer cur ^ 1
         if (r) return r;
-        CU(c, cudaEventRecord(c->ev_comm, c->comm_stream));
-        r = lbm_step_planes(c, 2, own, st);
-        if (r) return r;
-        CU(c, cudaStreamWaitEvent(st, c->ev_comm, 0));
         c->cur ^= 1;
         c->ffm_pending = false;
+    }
+    if (overlap) {                                               // st continues after both streams
+        CU(c, cudaEventRecord(c->ev_comm, c->comm_stream));
+        CU(c, cudaStreamWaitEvent(st, c->ev_comm, 0));
     }
     c->macro_valid = false;
     c->F_valid = false;

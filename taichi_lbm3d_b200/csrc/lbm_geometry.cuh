@@ -2,6 +2,8 @@
 // C-ABI layers (each translation unit gets its own copy: everything is in an anonymous
 // namespace).  Reference: Single_phase/LBM_3D_SinglePhase_Solver.py (line numbers below).
 #pragma once
+#include <cmath>
+#include <cstring>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -166,17 +168,47 @@ __global__ void k_binarize(int8_t *s, size_t n) {
     if (i < n) s[i] = s[i] > 0 ? 1 : 0;       // init_geo :175  in_dat[in_dat>0] = 1
 }
 
-// cal_max_v :399-402  (norm evaluated without FMA contraction so every mode agrees)
+// cal_max_v :399-402  (norm evaluated without FMA contraction so every mode agrees).
+// out[0]: int image of the maximum (atomicMax on it orders non-negative floats), out[1]: set when
+// any |v| is NaN -- fmaxf would drop it silently and a diverged run would report a finite speed.
 __global__ void k_max_v(const float *__restrict__ v, size_t n, float *out) {
     float best = -1e10f;
+    bool bad = false;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (size_t)gridDim.x * blockDim.x) {
         const float x = v[3 * i], y = v[3 * i + 1], z = v[3 * i + 2];
         const float nr = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+        bad |= nr != nr;
         best = fmaxf(best, nr);
     }
     for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
-    if ((threadIdx.x & 31) == 0 && best >= 0.f) atomicMax((int *)out, __float_as_int(best));
+    bad = __any_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0) {
+        if (best >= 0.f) atomicMax((int *)out, __float_as_int(best));
+        if (bad) atomicOr((int *)out + 1, 1);
+    }
+}
+
+// host side of cal_max_v, shared by both solvers: reduction on `st`, result (NaN if any node is)
+inline cudaError_t max_v_reduce(const float *d_v, size_t n, float *d_scalar2, cudaStream_t st, float *result) {
+    static int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+    }
+    const int init[2] = {(int)0x80000000, 0};       // below every non-negative float; no NaN seen
+    cudaError_t e = cudaMemcpyAsync(d_scalar2, init, sizeof init, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return e;
+    k_max_v<<<n_sm * 8, 256, 0, st>>>(d_v, n, d_scalar2);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    int got[2] = {0, 0};
+    if ((e = cudaMemcpyAsync(got, d_scalar2, sizeof got, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+    float v;
+    memcpy(&v, &got[0], sizeof v);
+    *result = got[1] ? nanf("") : (got[0] < 0 ? -1e10f : v);     // seed :395
+    return cudaSuccess;
 }
 
 inline unsigned nblocks(size_t n, int b) { return (unsigned)((n + b - 1) / b); }
@@ -200,6 +232,27 @@ __global__ void k_halo_unpack(StepArgs a, uint32_t row0, uint32_t first, uint32_
     const uint32_t e = a.nz ? (row0 + i / (uint32_t)a.nz) * a.prow + i % (uint32_t)a.nz : first + i;
 #pragma unroll
     for (int q = 0; q < 5; ++q) a.pout[d.s[q]][e] = src[(size_t)q * count + i];
+}
+
+// both sides of a slab in ONE launch (blockIdx.y = side): the native slab loop packs the e_x = -1
+// populations of the first owned plane and the e_x = +1 populations of the last owned plane
+// together, and fills both ghost planes together
+struct HaloSide { uint32_t row0, first, count; HaloDirs d; float *buf; };
+__global__ void k_halo_pack2(StepArgs a, HaloSide s0, HaloSide s1) {
+    const HaloSide &h = blockIdx.y == 0 ? s0 : s1;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= h.count) return;
+    const uint32_t e = a.nz ? (h.row0 + i / (uint32_t)a.nz) * a.prow + i % (uint32_t)a.nz : h.first + i;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) h.buf[(size_t)q * h.count + i] = a.pown[h.d.s[q]][e];
+}
+__global__ void k_halo_unpack2(StepArgs a, HaloSide s0, HaloSide s1) {
+    const HaloSide &h = blockIdx.y == 0 ? s0 : s1;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= h.count) return;
+    const uint32_t e = a.nz ? (h.row0 + i / (uint32_t)a.nz) * a.prow + i % (uint32_t)a.nz : h.first + i;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) a.pout[h.d.s[q]][e] = h.buf[(size_t)q * h.count + i];
 }
 
 // exact inverse of M (:64-83) as rationals; every non-zero entry rounds to the same f32 as

@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(256) k_dense(const StepArgs a) {
     const uint32_t z = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t r = (blockIdx.z * gridDim.y + blockIdx.y) * blockDim.y + threadIdx.y;
     if (z >= (uint32_t)a.nz || r >= a.row_count) return;
-    const uint32_t row = a.row_first + r;
+    const uint32_t row = a.row_first + r + (r >= a.row_split ? a.row_skip : 0u);
     const uint32_t idx = row * (uint32_t)a.nz + z;      // node (flags, rho, v, F)
     const uint32_t pidx = row * a.prow + z;             // element inside a population plane
     float f[19];
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(256) k_dense_aa(const StepArgs a) {
     const uint32_t z = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t r = (blockIdx.z * gridDim.y + blockIdx.y) * blockDim.y + threadIdx.y;
     if (z >= (uint32_t)a.nz || r >= a.row_count) return;
-    const uint32_t row = a.row_first + r;
+    const uint32_t row = a.row_first + r + (r >= a.row_split ? a.row_skip : 0u);
     const uint32_t idx = row * (uint32_t)a.nz + z;
     const uint32_t pidx = row * a.prow + z;
     float f[19];
@@ -379,8 +379,8 @@ __global__ void __launch_bounds__(256) k_dense_aa(const StepArgs a) {
 // `parity`), BC, macro, collide, store
 template <int FORCE, int MODE, bool COMP, int AA>
 __device__ __forceinline__ void sparse_node(const StepArgs &a, const SparseTable &s_tab, uint64_t *s_bar,
-                                            uint32_t parity, uint32_t i) {
-    const bool active = i >= a.first && i < a.first + a.count;
+                                            uint32_t parity, uint32_t i, uint32_t first, uint32_t count) {
+    const bool active = i >= first && i < first + count;
     float f[19];
     uint32_t fl = 0;
     // half-way bounce-back (:267-268): a direction whose pull source is solid takes the node's
@@ -474,7 +474,13 @@ k_sparse(const StepArgs a) {
     constexpr bool TABLE = COMP && MODE != MODE_COLLIDE && AA != AA_EVEN;   // phase 1 needed
     __shared__ SparseTable s_tab;
     __shared__ uint64_t s_bar;
-    const uint32_t blk = blockIdx.x + a.first / SPARSE_BLOCK;
+    uint32_t first = a.first, count = a.count, b = blockIdx.x;
+    if (b >= a.nb1) {                // second range of a two-range launch (StepArgs::nb1)
+        b -= a.nb1;
+        first = a.first2;
+        count = a.count2;
+    }
+    const uint32_t blk = b + first / SPARSE_BLOCK;
     if (TABLE) {
         if (threadIdx.x == 0) mbar_init(&s_bar, 1);
         __syncthreads();
@@ -483,7 +489,7 @@ k_sparse(const StepArgs a) {
             if (MODE == MODE_STEP && a.prefetch_dist) {
                 // ask L2 for the table slice of the block one wave ahead
                 const uint32_t pb = blk * SPARSE_BLOCK + a.prefetch_dist;
-                if (pb + SPARSE_BLOCK <= a.first + a.count) {
+                if (pb + SPARSE_BLOCK <= first + count) {
 #pragma unroll
                     for (int k = 0; k < 8; ++k)
                         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.rb16[k] + pb), "r"(SPARSE_BLOCK * 2u) : "memory");
@@ -492,7 +498,7 @@ k_sparse(const StepArgs a) {
             }
         }
     }
-    sparse_node<FORCE, MODE, COMP, AA>(a, s_tab, &s_bar, 0u, blk * SPARSE_BLOCK + threadIdx.x);
+    sparse_node<FORCE, MODE, COMP, AA>(a, s_tab, &s_bar, 0u, blk * SPARSE_BLOCK + threadIdx.x, first, count);
 }
 
 template <int FORCE, int MODE>
@@ -526,7 +532,9 @@ static void launch_sparse_t(const StepArgs &a, int block, cudaStream_t st) {
     (void)block;
     block = SPARSE_BLOCK;
     const unsigned b0 = a.first / SPARSE_BLOCK, b1 = (a.first + a.count + SPARSE_BLOCK - 1) / SPARSE_BLOCK;
-    const unsigned grid = b1 - b0;
+    unsigned grid = b1 - b0;
+    if (a.nb1 != 0xFFFFFFFFu)        // two ranges: nb1 blocks of the first, then the second
+        grid = a.nb1 + ((a.first2 + a.count2 + SPARSE_BLOCK - 1) / SPARSE_BLOCK - a.first2 / SPARSE_BLOCK);
     if (!a.compressed)
         k_sparse<FORCE, MODE, false, AA_OFF><<<grid, block, 0, st>>>(a);
     else if (a.aa == AA_ODD)
@@ -555,7 +563,7 @@ static void launch_sparse_t(const StepArgs &a, int block, cudaStream_t st) {
 static cudaError_t launch_any(bool sparse, int mode, const StepArgs &a, int block, cudaStream_t st) {
     if (block <= 0 || block > 256 || block % 32) block = 256;
     if (sparse) {
-        if (a.count == 0) return cudaSuccess;
+        if (a.count == 0 && (a.nb1 == 0xFFFFFFFFu || a.count2 == 0)) return cudaSuccess;
         DISPATCH(launch_sparse_t)
     } else {
         if (a.row_count == 0) return cudaSuccess;

@@ -47,6 +47,10 @@ struct StepArgs {
     // in a population plane is row*prow + k.  SoA layout: prow = nz, planes `stride` apart;
     // row-blocked layout [row][19][nzp]: prow = 19*nzp, planes nzp apart.
     uint32_t row_first, row_count, prow;
+    // one launch over TWO disjoint ranges (the two boundary planes of an x-slab): dense, launch row
+    // r >= row_split maps to row_first + r + row_skip; sparse, blocks >= nb1 walk [first2, first2+count2)
+    uint32_t row_split, row_skip;
+    uint32_t nb1, first2, count2;
     int spec;                       // 1: speculative pull (few solid nodes)
     int nx, ny, nz;                 // extents of this context's lattice (incl. ghost planes)
     int halo_x;                     // 1: planes 0 and nx-1 are ghost planes, x never wraps

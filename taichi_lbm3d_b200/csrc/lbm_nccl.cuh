@@ -1,13 +1,13 @@
-// NCCL, bound at run time from the library torch has already loaded (shared by the single-phase
-// and two-phase C-ABI layers; each translation unit gets its own copy of the binding).
+// NCCL, bound at run time from the library torch has already loaded.  One binding and ONE
+// communicator per process, shared by the single-phase and two-phase C-ABI layers and by every
+// context (C++17 inline variables): ncclCommInitRank costs seconds at 8 ranks, and several
+// communicators with kernels in flight on different streams can dead-lock each other.
 #pragma once
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
 #include <cstdlib>
 #include <string>
-
-namespace {
 
 // (prototypes from nccl.h 2.28: ncclUniqueId is 128 bytes, ncclFloat = 7, ncclSuccess = 0)
 struct NcclId { char internal[128]; };
@@ -23,9 +23,18 @@ struct NcclApi {
     const char *(*GetErrorString)(int) = nullptr;
     bool ok = false;
 };
-NcclApi g_nccl;
+inline NcclApi g_nccl;
 
-bool load_nccl(std::string &err) {
+// the process-wide communicator: created by the first lbm_comm_init / lbm2p_comm_init of a
+// (world, rank, device) and reused by every later context with the same triple; never destroyed
+// before process exit (contexts do not own it)
+struct NcclShared {
+    void *comm = nullptr;
+    int world = 0, rank = -1, device = -1;
+};
+inline NcclShared g_nccl_shared;
+
+inline bool load_nccl(std::string &err) {
     if (g_nccl.ok) return true;
     const char *names[] = {getenv("LBM3D_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
     for (const char *n : names) {
@@ -50,4 +59,23 @@ bool load_nccl(std::string &err) {
     return true;
 }
 
-}  // namespace
+// returns 0 and the shared communicator (creating it from `id` when there is none for this triple)
+inline int shared_comm(int world, int rank, const NcclId &id, void **comm) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    NcclShared &s = g_nccl_shared;
+    if (s.comm && s.world == world && s.rank == rank && s.device == dev) { *comm = s.comm; return 0; }
+    if (s.comm) { g_nccl.CommDestroy(s.comm); s.comm = nullptr; }
+    void *c = nullptr;
+    const int r = g_nccl.CommInitRank(&c, world, id, rank);
+    if (r != 0) return r;
+    s.comm = c; s.world = world; s.rank = rank; s.device = dev;
+    *comm = c;
+    return 0;
+}
+inline bool have_shared_comm(int world, int rank) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const NcclShared &s = g_nccl_shared;
+    return s.comm && s.world == world && s.rank == rank && s.device == dev;
+}

@@ -35,8 +35,12 @@ def _fast_loadtxt(filename):
     with open(filename, "rb") as fh:
         raw = fh.read()
     toks = np.frombuffer(raw, dtype=np.uint8)
-    if toks.size and np.all((toks == 48) | (toks == 49) | (toks == 10) | (toks == 13) | (toks == 32)):
-        return (toks[(toks == 48) | (toks == 49)] - 48).astype(np.float64)
+    digit = (toks == 48) | (toks == 49)
+    if toks.size and np.all(digit | (toks == 10) | (toks == 13) | (toks == 32)):
+        # fast only when every token is ONE character ("10" or "01" is one number for np.loadtxt):
+        # no two digits may be adjacent
+        if not np.any(digit[1:] & digit[:-1]):
+            return (toks[digit] - 48).astype(np.float64)
     return np.loadtxt(filename).reshape(-1)        # general numbers: the reference's own call
 
 

@@ -212,7 +212,12 @@ class LB3D_Solver_Two_Phase:
 
     def _set(self, name, arr):
         if self._ctx is not None:
-            raise _lib.LbmError("after init_simulation() use set_state() to replace fields")
+            if name not in ("solid", "psi"):
+                raise _lib.LbmError("after init_simulation() use set_state() to replace fields")
+            # new geometry / initial phase field (the script's init_geo): the running context is
+            # stale, the next init_simulation() rebuilds it
+            self._lib.lbm2p_destroy(self._ctx)
+            self._ctx = None
         a = np.asarray(arr)
         if a.shape != (self.nx, self.ny, self.nz):
             raise ValueError("%s must have shape %s" % (name, (self.nx, self.ny, self.nz)))
