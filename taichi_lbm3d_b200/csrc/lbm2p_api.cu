@@ -41,16 +41,17 @@ struct lbm2p_ctx {
     uint32_t nzp = 0, prow = 0;
     size_t fsize = 0, pad = 0, npad = 0;
     int spec = 1;
+    int gather = 0;               // dense colour pass gathers per node (few BULK nodes)
     // device
     int8_t *d_solid = nullptr;
     float *d_psi0 = nullptr;          // input phase field (kept for the solid nodes of get_psi)
     uint32_t *d_flags = nullptr;
     uint8_t *d_cls = nullptr;
     float *d_fbase[2] = {nullptr, nullptr}, *d_f[2] = {nullptr, nullptr};
-    float4 *d_recA = nullptr, *d_recC = nullptr;
-    float2 *d_recB = nullptr;
+    float4 *d_uq = nullptr, *d_recC = nullptr;     // colour record: (v, +-q) and, at the interface, (C, 1/|C|)
+    float2 *d_rrb[2] = {nullptr, nullptr};         // (rho_r, rho_b): colour pass reads [rcur], writes [rcur ^ 1]
+    int rcur = 0;
     float *d_psibase = nullptr, *d_psi = nullptr;
-    float *d_rho_r = nullptr, *d_rho_b = nullptr;
     float *d_rho = nullptr, *d_v = nullptr, *d_F = nullptr;
     float *d_vbc = nullptr;
     uint32_t vbc_off[6]{};
@@ -103,20 +104,18 @@ namespace {
 
 // init :173-186 on the node-linear arrays; the working psi array holds psi_solid at solid nodes
 __global__ void k2p_init_state(const int8_t *__restrict__ solid, const float *__restrict__ psi0, size_t n,
-                               float psi_solid, float *psi, float *rho_r, float *rho_b, float *rho, float *v) {
+                               float psi_solid, float *psi, float2 *rrb, float *rho, float *v) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (solid[i] == 0) {
         const float p = psi0[i];
         psi[i] = p;
         const float rr = (p + 1.0f) / 2.0f;
-        rho_r[i] = rr;
-        rho_b[i] = 1.0f - rr;
+        rrb[i] = make_float2(rr, 1.0f - rr);
         rho[i] = 1.0f;
     } else {
         psi[i] = psi_solid;
-        rho_r[i] = 0.f;
-        rho_b[i] = 0.f;
+        rrb[i] = make_float2(0.f, 0.f);
         rho[i] = 0.f;
     }
     v[3 * i] = 0.f; v[3 * i + 1] = 0.f; v[3 * i + 2] = 0.f;
@@ -140,14 +139,25 @@ __global__ void k2p_bake_psi(const int8_t *__restrict__ solid, float *psi, float
 
 // sparse storage: init :173-186 on the compact arrays; psi0 is the dense input phase field
 __global__ void k2p_init_compact(const uint32_t *__restrict__ lin, const float *__restrict__ psi0, size_t nf,
-                                 float *psi, float *rho_r, float *rho_b) {
+                                 float *psi, float2 *rrb) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nf) return;
     const float p = psi0[lin[i]];
     psi[i] = p;
     const float rr = (p + 1.0f) / 2.0f;
-    rho_r[i] = rr;
-    rho_b[i] = 1.0f - rr;
+    rrb[i] = make_float2(rr, 1.0f - rr);
+}
+// one colour of the interleaved (rho_r, rho_b) array as its own array (getters), and back (set_state)
+__global__ void k2p_split(const float2 *__restrict__ rrb, int which, size_t n, float *out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = which ? rrb[i].y : rrb[i].x;
+}
+__global__ void k2p_join(const float *__restrict__ rr, const float *__restrict__ rb, const uint32_t *__restrict__ lin,
+                         size_t n, float2 *rrb) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t j = lin ? lin[i] : i;
+    rrb[i] = make_float2(rr[j], rb[j]);
 }
 __global__ void k2p_init_macro(const int8_t *__restrict__ solid, size_t n, float *rho, float *v) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -169,10 +179,10 @@ __global__ void k2p_gather(const uint32_t *__restrict__ lin, const float *__rest
 void free2(lbm2p_ctx *c) {
     free_sparse_tables(c->sp);
     cudaFree(c->d_flags); cudaFree(c->d_cls); cudaFree(c->d_fbase[0]); cudaFree(c->d_fbase[1]);
-    cudaFree(c->d_recA); cudaFree(c->d_recB); cudaFree(c->d_recC); cudaFree(c->d_psibase); cudaFree(c->d_rho_r); cudaFree(c->d_rho_b);
+    cudaFree(c->d_uq); cudaFree(c->d_recC); cudaFree(c->d_psibase); cudaFree(c->d_rrb[0]); cudaFree(c->d_rrb[1]);
     cudaFree(c->d_rho); cudaFree(c->d_v); cudaFree(c->d_F); cudaFree(c->d_vbc); cudaFree(c->d_scalar);
     c->d_flags = nullptr; c->d_cls = nullptr; c->d_fbase[0] = c->d_fbase[1] = nullptr;
-    c->d_recA = c->d_recC = nullptr; c->d_recB = nullptr; c->d_psibase = nullptr; c->d_rho_r = c->d_rho_b = nullptr;
+    c->d_uq = c->d_recC = nullptr; c->d_psibase = nullptr; c->d_rrb[0] = c->d_rrb[1] = nullptr;
     c->d_rho = c->d_v = c->d_F = nullptr; c->d_vbc = nullptr; c->d_scalar = nullptr;
 }
 
@@ -191,6 +201,7 @@ void fill2(const lbm2p_ctx *c, Step2Args &A, const float *fin, float *fout) {
     }
     a.stride = 0;
     A.sparse = c->sparse ? 1 : 0;
+    A.gather = c->gather;
     if (c->sparse) {
         a.stride = c->sp.stride;
         a.first = c->sp.own_first;
@@ -224,8 +235,13 @@ void fill2(const lbm2p_ctx *c, Step2Args &A, const float *fin, float *fout) {
         A.bc_psi_type[i] = c->bc_psi_type[i];
         A.bc_psi_val[i] = c->bc_psi_val[i];
     }
-    A.recA = c->d_recA; A.recB = c->d_recB; A.recC = c->d_recC;
-    A.rho_r = c->d_rho_r; A.rho_b = c->d_rho_b; A.psi = c->d_psi;
+    A.uq = c->d_uq; A.recC = c->d_recC;
+    A.rrb = c->d_rrb[c->rcur]; A.rrb_out = c->d_rrb[c->rcur ^ 1];
+    A.psi = c->d_psi;
+    if (!c->sparse) {
+        const long long py = c->cfg.nz, px = (long long)c->cfg.ny * py;
+        for (int s = 0; s < 19; ++s) A.psi_nb[s] = c->d_psi + (e[s][0] * px + e[s][1] * py + e[s][2]);
+    }
     A.psi_solid = (float)c->psi_solid;
     A.CapA = (float)c->CapA;
     // :100-108, Python float arithmetic, one rounding to f32 where the kernel captures them
@@ -264,6 +280,13 @@ int launch_colour2(lbm2p_ctx *c, const Step2Args &A, cudaStream_t st) {
     return 0;
 }
 
+// the colour pass of a step is complete (it may take several launches over plane ranges): what it
+// wrote is the current (rho_r, rho_b) from here on
+void colour_done(lbm2p_ctx *c) {
+    c->rcur ^= 1;
+    c->colour_valid = true;
+}
+
 int ensure_F2(lbm2p_ctx *c) {
     if (c->d_F != nullptr) return 0;
     CU2(c, cudaMalloc(&c->d_F, c->N * 19 * sizeof(float)));
@@ -289,7 +312,8 @@ int sync2(lbm2p_ctx *c, bool need_macro, bool need_F) {
     if (!c->colour_valid) {
         int r = launch_colour2(c, A, c->stream);
         if (r) return r;
-        c->colour_valid = true;
+        colour_done(c);
+        fill2(c, A, c->d_f[c->cur], nullptr);
     }
     if ((need_macro && !c->macro_valid) || (need_F && !c->F_valid)) {
         A.a.F = need_F ? c->d_F : nullptr;
@@ -485,21 +509,19 @@ int lbm2p_init(lbm2p_ctx *c) {
             CU2(c, cudaMemset(c->d_fbase[b], 0, c->fsize * sizeof(float)));
             c->d_f[b] = c->d_fbase[b];
         }
-        CU2(c, cudaMalloc(&c->d_recA, st * sizeof(float4)));
-        CU2(c, cudaMalloc(&c->d_recB, st * sizeof(float2)));
+        CU2(c, cudaMalloc(&c->d_uq, st * sizeof(float4)));
         CU2(c, cudaMalloc(&c->d_recC, st * sizeof(float4)));
-        CU2(c, cudaMemset(c->d_recA, 0, st * sizeof(float4)));
-        CU2(c, cudaMemset(c->d_recB, 0, st * sizeof(float2)));
+        CU2(c, cudaMemset(c->d_uq, 0, st * sizeof(float4)));
         CU2(c, cudaMemset(c->d_recC, 0, st * sizeof(float4)));
         CU2(c, cudaMalloc(&c->d_psibase, st * sizeof(float)));
         CU2(c, cudaMemset(c->d_psibase, 0, st * sizeof(float)));
         c->d_psi = c->d_psibase;
-        CU2(c, cudaMalloc(&c->d_rho_r, st * sizeof(float)));
-        CU2(c, cudaMalloc(&c->d_rho_b, st * sizeof(float)));
-        CU2(c, cudaMemset(c->d_rho_r, 0, st * sizeof(float)));
-        CU2(c, cudaMemset(c->d_rho_b, 0, st * sizeof(float)));
+        for (int b = 0; b < 2; ++b) {
+            CU2(c, cudaMalloc(&c->d_rrb[b], st * sizeof(float2)));
+            CU2(c, cudaMemset(c->d_rrb[b], 0, st * sizeof(float2)));
+        }
         if (c->nf) {
-            k2p_init_compact<<<nblocks(c->nf, 256), 256>>>(c->sp.d_lin, c->d_psi0, c->nf, c->d_psi, c->d_rho_r, c->d_rho_b);
+            k2p_init_compact<<<nblocks(c->nf, 256), 256>>>(c->sp.d_lin, c->d_psi0, c->nf, c->d_psi, c->d_rrb[0]);
             CU2(c, cudaGetLastError());
         }
         k2p_init_macro<<<nblocks(N, 256), 256>>>(c->d_solid, N, c->d_rho, c->d_v);
@@ -527,6 +549,20 @@ int lbm2p_init(lbm2p_ctx *c) {
         c->nf = h;
         c->spec = (double)h >= 0.75 * (double)N ? 1 : 0;
         if (const char *sp = getenv("LBM3D_SPEC")) c->spec = atoi(sp) ? 1 : 0;
+        // the colour pass hands terms between lanes when most fluid nodes are BULK (no solid link,
+        // no face); in a porous medium nearly every node gathers for itself anyway
+        auto itb = thrust::make_transform_iterator((const uint8_t *)c->d_cls, IsBulk());
+        CU2(c, cudaMalloc(&d_out, sizeof(uint32_t)));
+        tmp = nullptr; tmp_bytes = 0;
+        cub::DeviceReduce::Sum(nullptr, tmp_bytes, itb, d_out, N);
+        CU2(c, cudaMalloc(&tmp, tmp_bytes));
+        e = cub::DeviceReduce::Sum(tmp, tmp_bytes, itb, d_out, N);
+        uint32_t hb = 0;
+        e2 = cudaMemcpy(&hb, d_out, sizeof hb, cudaMemcpyDeviceToHost);
+        cudaFree(tmp); cudaFree(d_out);
+        CU2(c, e); CU2(c, e2);
+        c->gather = (double)hb < 0.5 * (double)h ? 1 : 0;
+        if (const char *g = getenv("LBM3D_COLOUR_GATHER")) c->gather = atoi(g) ? 1 : 0;
     }
     c->nzp = (uint32_t)((nz + 31) / 32 * 32);
     c->prow = 19 * c->nzp;
@@ -541,19 +577,19 @@ int lbm2p_init(lbm2p_ctx *c) {
     // node-linear arrays with a guard band of a plane + a row
     c->npad = (plane + nz + 2 + 31) / 32 * 32;
     const size_t nlin = N + 2 * c->npad;
-    CU2(c, cudaMalloc(&c->d_recA, N * sizeof(float4)));
-    CU2(c, cudaMalloc(&c->d_recB, N * sizeof(float2)));
+    CU2(c, cudaMalloc(&c->d_uq, N * sizeof(float4)));
     CU2(c, cudaMalloc(&c->d_recC, N * sizeof(float4)));
-    CU2(c, cudaMemset(c->d_recA, 0, N * sizeof(float4)));
-    CU2(c, cudaMemset(c->d_recB, 0, N * sizeof(float2)));
+    CU2(c, cudaMemset(c->d_uq, 0, N * sizeof(float4)));
     CU2(c, cudaMemset(c->d_recC, 0, N * sizeof(float4)));
     CU2(c, cudaMalloc(&c->d_psibase, nlin * sizeof(float)));
     CU2(c, cudaMemset(c->d_psibase, 0, nlin * sizeof(float)));
     c->d_psi = c->d_psibase + c->npad;
-    CU2(c, cudaMalloc(&c->d_rho_r, N * sizeof(float)));
-    CU2(c, cudaMalloc(&c->d_rho_b, N * sizeof(float)));
-    k2p_init_state<<<nblocks(N, 256), 256>>>(c->d_solid, c->d_psi0, N, (float)c->psi_solid, c->d_psi, c->d_rho_r,
-                                              c->d_rho_b, c->d_rho, c->d_v);
+    for (int b = 0; b < 2; ++b) {
+        CU2(c, cudaMalloc(&c->d_rrb[b], N * sizeof(float2)));
+        CU2(c, cudaMemset(c->d_rrb[b], 0, N * sizeof(float2)));
+    }
+    k2p_init_state<<<nblocks(N, 256), 256>>>(c->d_solid, c->d_psi0, N, (float)c->psi_solid, c->d_psi, c->d_rrb[0],
+                                              c->d_rho, c->d_v);
     CU2(c, cudaGetLastError());
     c->launches++;
     }
@@ -565,6 +601,7 @@ int lbm2p_init(lbm2p_ctx *c) {
     if (c->cfg.strict) CU2(c, lbm2p_strict::set_inverse_matrix(c->invM));
     CU2(c, cudaDeviceSynchronize());
     c->cur = 0;
+    c->rcur = 0;
     c->pipe_valid = false;
     c->colour_valid = true;
     c->macro_valid = true;
@@ -598,6 +635,8 @@ int lbm2p_step(lbm2p_ctx *c, int nsteps, void *cuda_stream) {
         if (!c->colour_valid) {
             int r = launch_colour2(c, A, st);       // rho_r, rho_b, psi of the step just collided
             if (r) return r;
+            colour_done(c);
+            fill2(c, A, c->d_f[c->cur], c->d_f[c->cur ^ 1]);
         }
         int r = launch_main2(c, MODE_STEP, A, st);  // its stream/BC/macro + the next collision
         if (r) return r;
@@ -618,15 +657,16 @@ namespace {
 
 size_t halo_floats(const lbm2p_ctx *c, int stage) {
     const size_t P = (size_t)c->cfg.ny * c->cfg.nz;
-    return stage == 0 ? 15 * P : P;
+    return stage == 0 ? 13 * P : 3 * P;      // f* (5) + uq (4) + recC (4)  |  psi (1) + rho_r, rho_b (2)
 }
 
 int pack2(lbm2p_ctx *c, int stage, int side, float *dst, cudaStream_t st) {
     const size_t P = (size_t)c->cfg.ny * c->cfg.nz;
     const int x = side == 0 ? 1 : c->cfg.nx - 2;               // boundary plane that is sent
     const size_t off = (size_t)x * P;
-    if (stage == 1) {
+    if (stage == 1) {       // what the colour pass just wrote: psi and the current (rho_r, rho_b)
         CU2(c, cudaMemcpyAsync(dst, c->d_psi + off, P * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        CU2(c, cudaMemcpyAsync(dst + P, c->d_rrb[c->rcur] + off, P * sizeof(float2), cudaMemcpyDeviceToDevice, st));
         return 0;
     }
     static const HaloDirs kR = {{1, 7, 9, 11, 13}}, kL = {{2, 8, 10, 12, 14}};
@@ -635,9 +675,8 @@ int pack2(lbm2p_ctx *c, int stage, int side, float *dst, cudaStream_t st) {
     k_halo_pack<<<nblocks(P, 256), 256, 0, st>>>(A.a, (uint32_t)(x * c->cfg.ny), 0u, (uint32_t)P, side == 0 ? kL : kR, dst);
     CU2(c, cudaGetLastError());
     c->launches++;
-    CU2(c, cudaMemcpyAsync(dst + 5 * P, c->d_recA + off, P * sizeof(float4), cudaMemcpyDeviceToDevice, st));
-    CU2(c, cudaMemcpyAsync(dst + 9 * P, c->d_recB + off, P * sizeof(float2), cudaMemcpyDeviceToDevice, st));
-    CU2(c, cudaMemcpyAsync(dst + 11 * P, c->d_recC + off, P * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+    CU2(c, cudaMemcpyAsync(dst + 5 * P, c->d_uq + off, P * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+    CU2(c, cudaMemcpyAsync(dst + 9 * P, c->d_recC + off, P * sizeof(float4), cudaMemcpyDeviceToDevice, st));
     return 0;
 }
 
@@ -647,6 +686,7 @@ int unpack2(lbm2p_ctx *c, int stage, int side, const float *src, cudaStream_t st
     const size_t off = (size_t)x * P;
     if (stage == 1) {
         CU2(c, cudaMemcpyAsync(c->d_psi + off, src, P * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        CU2(c, cudaMemcpyAsync(c->d_rrb[c->rcur] + off, src + P, P * sizeof(float2), cudaMemcpyDeviceToDevice, st));
         return 0;
     }
     static const HaloDirs kR = {{1, 7, 9, 11, 13}}, kL = {{2, 8, 10, 12, 14}};
@@ -656,9 +696,8 @@ int unpack2(lbm2p_ctx *c, int stage, int side, const float *src, cudaStream_t st
     k_halo_unpack<<<nblocks(P, 256), 256, 0, st>>>(A.a, (uint32_t)(x * c->cfg.ny), 0u, (uint32_t)P, side == 0 ? kR : kL, src);
     CU2(c, cudaGetLastError());
     c->launches++;
-    CU2(c, cudaMemcpyAsync(c->d_recA + off, src + 5 * P, P * sizeof(float4), cudaMemcpyDeviceToDevice, st));
-    CU2(c, cudaMemcpyAsync(c->d_recB + off, src + 9 * P, P * sizeof(float2), cudaMemcpyDeviceToDevice, st));
-    CU2(c, cudaMemcpyAsync(c->d_recC + off, src + 11 * P, P * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+    CU2(c, cudaMemcpyAsync(c->d_uq + off, src + 5 * P, P * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+    CU2(c, cudaMemcpyAsync(c->d_recC + off, src + 9 * P, P * sizeof(float4), cudaMemcpyDeviceToDevice, st));
     return 0;
 }
 
@@ -710,7 +749,7 @@ int stage2(lbm2p_ctx *c, int stage, cudaStream_t st) {
         fill2(c, A, c->d_f[c->cur], nullptr);
         int r = launch_colour2(c, A, st);
         if (r) return r;
-        c->colour_valid = true;
+        colour_done(c);
     } else {
         if (!c->pipe_valid || !c->colour_valid) FAIL2(c, -4, "the colour pass of this step has not run");
         fill2(c, A, c->d_f[c->cur], c->d_f[c->cur ^ 1]);
@@ -863,7 +902,7 @@ int lbm2p_run_slab(lbm2p_ctx *c, int nsteps, void *cuda_stream) {
             if (r) return r;
             r = launch_planes2(c, 0, nx - 2, nx - 1, st);
             if (r) return r;
-            c->colour_valid = true;
+            colour_done(c);
         } else if (xa_pending) {
             CU2(c, cudaStreamWaitEvent(st, c->ev_xa, 0));
             xa_pending = false;
@@ -945,16 +984,33 @@ static int get_colour_field(lbm2p_ctx *c, float *dst, const float *field, const 
     return 0;
 }
 
+// rho_r (which = 0) or rho_b (1): one component of the interleaved array, as its own field
+static int get_colour_component(lbm2p_ctx *c, float *dst, int which) {
+    int r = sync2(c, false, false);
+    if (r) return r;
+    const size_t n = c->sparse ? c->sp.stride : c->N;
+    float *tmp = nullptr;
+    CU2(c, cudaMalloc(&tmp, (n ? n : 1) * sizeof(float)));
+    k2p_split<<<nblocks(n ? n : 1, 256), 256, 0, c->stream>>>(c->d_rrb[c->rcur], which, n, tmp);
+    cudaError_t e = cudaGetLastError();
+    c->launches++;
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) { cudaFree(tmp); CU2(c, e); }
+    r = get_colour_field(c, dst, tmp, nullptr);
+    cudaFree(tmp);
+    return r;
+}
+
 int lbm2p_get_rho_r(lbm2p_ctx *c, float *dst) {
     CTX2(c);
     if (!dst) FAIL2(c, -1, "null destination");
-    return get_colour_field(c, dst, c->d_rho_r, nullptr);
+    return get_colour_component(c, dst, 0);
 }
 
 int lbm2p_get_rho_b(lbm2p_ctx *c, float *dst) {
     CTX2(c);
     if (!dst) FAIL2(c, -1, "null destination");
-    return get_colour_field(c, dst, c->d_rho_b, nullptr);
+    return get_colour_component(c, dst, 1);
 }
 
 int lbm2p_get_psi(lbm2p_ctx *c, float *dst) {
@@ -988,23 +1044,41 @@ int lbm2p_set_state(lbm2p_ctx *c, const float *F, const float *rho, const float 
     if (c->sparse) {
         float *tmp = nullptr;
         CU2(c, cudaMalloc(&tmp, c->N * sizeof(float)));
-        const float *src[3] = {psi, rho_r, rho_b};
-        float *dstc[3] = {c->d_psi, c->d_rho_r, c->d_rho_b};
-        cudaError_t e = cudaSuccess;
-        for (int k = 0; k < 3 && e == cudaSuccess; ++k) {
-            e = cudaMemcpy(tmp, src[k], c->N * sizeof(float), cudaMemcpyDefault);
-            if (e == cudaSuccess && c->nf) {
-                k2p_gather<<<nblocks(c->nf, 256), 256>>>(c->sp.d_lin, tmp, c->nf, dstc[k]);
-                e = cudaGetLastError();
-            }
-            if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        float *tmp2 = nullptr;
+        cudaError_t e = cudaMalloc(&tmp2, c->N * sizeof(float));
+        if (e == cudaSuccess) e = cudaMemcpy(tmp, psi, c->N * sizeof(float), cudaMemcpyDefault);
+        if (e == cudaSuccess && c->nf) {
+            k2p_gather<<<nblocks(c->nf, 256), 256>>>(c->sp.d_lin, tmp, c->nf, c->d_psi);
+            e = cudaGetLastError();
         }
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        if (e == cudaSuccess) e = cudaMemcpy(tmp, rho_r, c->N * sizeof(float), cudaMemcpyDefault);
+        if (e == cudaSuccess) e = cudaMemcpy(tmp2, rho_b, c->N * sizeof(float), cudaMemcpyDefault);
+        if (e == cudaSuccess && c->nf) {
+            k2p_join<<<nblocks(c->nf, 256), 256>>>(tmp, tmp2, c->sp.d_lin, c->nf, c->d_rrb[c->rcur]);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
         cudaFree(tmp);
+        cudaFree(tmp2);
         CU2(c, e);
     } else {
     CU2(c, cudaMemcpy(c->d_psi, psi, c->N * sizeof(float), cudaMemcpyDefault));
-    CU2(c, cudaMemcpy(c->d_rho_r, rho_r, c->N * sizeof(float), cudaMemcpyDefault));
-    CU2(c, cudaMemcpy(c->d_rho_b, rho_b, c->N * sizeof(float), cudaMemcpyDefault));
+    {
+        float *t0 = nullptr, *t1 = nullptr;
+        cudaError_t e = cudaMalloc(&t0, c->N * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&t1, c->N * sizeof(float));
+        if (e == cudaSuccess) e = cudaMemcpy(t0, rho_r, c->N * sizeof(float), cudaMemcpyDefault);
+        if (e == cudaSuccess) e = cudaMemcpy(t1, rho_b, c->N * sizeof(float), cudaMemcpyDefault);
+        if (e == cudaSuccess) {
+            k2p_join<<<nblocks(c->N, 256), 256>>>(t0, t1, nullptr, c->N, c->d_rrb[c->rcur]);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        cudaFree(t0);
+        cudaFree(t1);
+        CU2(c, e);
+    }
     k2p_bake_psi<<<nblocks(c->N, 256), 256>>>(c->d_solid, c->d_psi, (float)c->psi_solid, c->N);
     }
     CU2(c, cudaGetLastError());

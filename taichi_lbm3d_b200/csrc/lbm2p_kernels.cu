@@ -7,9 +7,13 @@
 //
 //   k2p_colour   rho_r, rho_b of step n from the colour records of the 18 pull sources
 //                (the recoloured g_r, g_b of :345-363 are RE-EVALUATED from the source node's
-//                record (rho_r, rho_b, v, C) instead of being stored: 8 words per node instead
+//                record (rho_r, rho_b, v, C) instead of being stored: 6 words per node instead
 //                of 38, and a deterministic ascending-s sum instead of the reference's
 //                unordered float atomics :365-372); then psi (:605) and the psi BC (:445-486).
+//                A thread fetches the records of its 9 neighbour z-rows at its OWN z only; the
+//                contributions that travel along z come from the adjacent lanes (warp shuffles,
+//                shared memory across warps): 9 aligned record loads per node instead of 19
+//                misaligned gathers.
 //   k2p_main     pull-stream f* + flow BCs + macro of step n, then the collision of step n+1:
 //                C = grad(psi) over 18 neighbours (:259-275), surface-tension perturbation of
 //                meq (:316-321), psi-dependent relaxation (:278-299), Guo force (:241-247,
@@ -17,7 +21,7 @@
 //
 // The pull needs psi of step n at all neighbours before C can be formed, hence two kernels.
 // Algorithmic bytes per node-step: 152 (populations) + 16 (rho_r, rho_b r/w) +
-// 8 (psi r/w) = 176; this implementation moves 176 + 64 (record write + read) = 240.
+// 8 (psi r/w) = 176; this implementation moves 176 + 32 (record write + read) = 208.
 #include <cstdlib>
 
 #include "lbm2p_kernels.cuh"
@@ -43,11 +47,24 @@ __device__ __forceinline__ uint32_t vbc_slot2(const StepArgs &a, int face, uint3
 
 // Compute_S_local :278-299
 __device__ __forceinline__ void s_local(const Step2Args &A, float psi, float &sv, float &so) {
+#ifdef LBM_STRICT
     if (psi > 0.f)
         sv = psi > 0.1f ? A.wl : A.lg0 + A.l1 * psi + A.l2 * psi * psi;
     else
         sv = psi < -0.1f ? A.wg : A.lg0 + A.g1 * psi + A.g2 * psi * psi;
     so = 8.0f * (2.0f - sv) / (8.0f - sv);
+#else
+    // the same piecewise rate without branches; the quotient through the reciprocal unit
+    const bool pos = psi > 0.f;
+    const float c1 = pos ? A.l1 : A.g1, c2 = pos ? A.l2 : A.g2;
+    const float quad = A.lg0 + (c1 + c2 * psi) * psi;
+    sv = fabsf(psi) > 0.1f ? (pos ? A.wl : A.wg) : quad;
+#ifdef LBM2P_EXACT_DIV
+    so = 8.0f * (2.0f - sv) / (8.0f - sv);
+#else
+    so = __fdividef(8.0f * (2.0f - sv), 8.0f - sv);
+#endif
+#endif
 }
 
 #ifdef LBM_STRICT
@@ -58,8 +75,9 @@ __device__ __forceinline__ void macro2(const float (&f)[19], const LbmParams &P,
 }
 
 __device__ __forceinline__ void collide2(float (&f)[19], const Step2Args &A, bool force, float rho, float ux,
-                                         float uy, float uz, float psi, float Cx, float Cy, float Cz) {
+                                         float uy, float uz, float psi, float Cx, float Cy, float Cz, float &inv) {
     const LbmParams &P = A.a.P;
+    inv = 0.f;
     constexpr int M[19][19] = {
         {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1},
         {-1, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1},
@@ -147,14 +165,19 @@ __device__ __forceinline__ void macro2(const float (&f)[19], const LbmParams &P,
 }
 
 __device__ __forceinline__ void collide2(float (&f)[19], const Step2Args &A, bool force, float rho, float ux,
-                                         float uy, float uz, float psi, float Cx, float Cy, float Cz) {
+                                         float uy, float uz, float psi, float Cx, float Cy, float Cz, float &inv) {
     const LbmParams &P = A.a.P;
     float m[19];
     forward(f, m);
     const float c2 = Cx * Cx + Cy * Cy + Cz * Cz;
-    const float cc = sqrtf(c2);
+#ifdef LBM2P_EXACT_DIV
+    inv = c2 > 0.f ? 1.0f / sqrtf(c2) : 0.f;
+#else
+    inv = c2 > 0.f ? rsqrtf(c2) : 0.f;       // 1/|C|, shared with the colour record (unit normal)
+#endif
+    const float cc = c2 * inv;
     // 0.5 CapA cc (n_a n_b) = 0.5 CapA C_a C_b / cc
-    const float k = cc > 0.f ? 0.5f * A.CapA / cc : 0.f;
+    const float k = 0.5f * A.CapA * inv;
     float sv, so;
     s_local(A, psi, sv, so);
     const float uxx = ux * ux, uyy = uy * uy, uzz = uz * uz;
@@ -196,40 +219,64 @@ __device__ __forceinline__ void collide2(float (&f)[19], const Step2Args &A, boo
 }
 #endif
 
+// colour record of a collision (lbm2p_kernels.cuh): velocity, q = 1 - 1.5 v.v with the interface
+// flag in its sign, and for flagged nodes the interface vector the colour pass needs
+__device__ __forceinline__ void write_record(const Step2Args &A, uint32_t node, float ux, float uy, float uz,
+                                             float Cx, float Cy, float Cz, float inv) {
+    const float q = 1.0f - 1.5f * (ux * ux + uy * uy + uz * uz);
+#ifdef LBM_STRICT
+    (void)inv;
+    const float ccn = sqrtf(Cx * Cx + Cy * Cy + Cz * Cz);
+    A.uq[node] = make_float4(ux, uy, uz, ccn > 0.f ? -q : q);
+    if (ccn > 0.f) A.recC[node] = make_float4(Cx, Cy, Cz, 1.0f / ccn);
+#else
+    A.uq[node] = make_float4(ux, uy, uz, q);
+    A.recC[node] = make_float4(Cx * inv, Cy * inv, Cz * inv, 0.f);       // inv = 0 where C = 0
+#endif
+}
+
 // Accumulators of the colour pass: one running sum per colour, every term weighted before it
 // is added, directions ascending (the oracle's order; the reference's float atomics have none).
 // (Summing unweighted per weight class and weighting once at the end saves 4 of 12 flops per
-// direction but no time -- the pass is bound by its 38 gathers per node -- and its different
-// rounding flips the |rho_r - rho_b| > 0.9 wetting switch (:271) at a few nodes of config 4.)
+// direction but its different rounding flips the |rho_r - rho_b| > 0.9 wetting switch (:271) at a
+// few nodes of config 4.)
 struct ColourSum {
     float r = 0.f, b = 0.f;                  // accumulators start at 0 (:596)
-    __device__ __forceinline__ float red() const { return r; }
-    __device__ __forceinline__ float blue() const { return b; }
 };
 
 // Contribution of one pull source to rho_r, rho_b: the recoloured g_r[s], g_b[s] (:345-363) of
-// the source node, re-evaluated from its colour record, for the direction sg*e_S (sg = -1:
-// the opposite direction LR[S], evaluated on the node's OWN record when the source is solid
-// and its push came back, :370-372).  Negation commutes with rounding, min(a,b,c,d) is
-// symmetric and cs*(-x) = -(cs*x), so both members of a pair (kk, kk+1) reduce to
+// the source node, re-evaluated from its colour record (ab = rho_r, rho_b; uq = v, +-q; *pc = C),
+// for the direction sg*e_S (sg = -1: the opposite direction LR[S], evaluated on the node's OWN
+// record when the source is solid and its push came back, :370-372).  Negation commutes with
+// rounding, min(a,b,c,d) is symmetric and cs*(-x) = -(cs*x), so both members of a pair (kk, kk+1)
+// reduce to
 //     g_r += cs (e.C)/|C| ,  g_b -= cs (e.C)/|C|     with e the direction being evaluated,
-// bit-identically to the reference's pairwise update.
+// bit-identically to the reference's pairwise update.  Production arithmetic returns the terms
+// un-weighted (colour_acc weights them) and spells every rounding out with intrinsics: the term is
+// evaluated on the CONSUMER's lane for nodes next to solids / faces and on the SOURCE's lane
+// otherwise, and which of the two a node takes depends on the decomposition into slabs.
+// `rc` is the interface part of the record.  Verification arithmetic: (C, 1/|C|) as the collision
+// used them, present (and loaded by the caller) only for flagged records, uq.w < 0.  Production
+// arithmetic: the unit normal C/|C| of EVERY record, zero where C = 0 -- a few steps into a run
+// psi is nowhere exactly uniform any more, so the recolouring is evaluated everywhere, without
+// flags or branches: with t = q + eu (3 + 4.5 eu) the opposite direction has to = t - 6 eu, and the
+// four-way min of :351-356 is min(rho_r x, rho_b y) with x, y the smaller of (t, to) for a
+// non-negative density and the larger for a negative one (rounding is monotonic, so this is the
+// min of the four rounded products, bit for bit, while t, to > 0).
 template <int S, int EX, int EY, int EZ>
-__device__ __forceinline__ void colour_add(float sg, const float4 ra, const float2 rq, const float4 *__restrict__ pc,
-                                           ColourSum &acc) {
-    const float eu = sg * edotu<EX, EY, EZ>(ra.z, ra.w, rq.x);
+__device__ __forceinline__ void colour_term(float sg, const float2 ab, const float4 uq, const float4 rc,
+                                            float &gr, float &gb) {
+    const float eu = sg * edotu<EX, EY, EZ>(uq.x, uq.y, uq.z);
 #ifdef LBM_STRICT
-    float gr, gb;
-    const float uv = ra.z * ra.z + ra.w * ra.w + rq.x * rq.x;
+    const float uv = uq.x * uq.x + uq.y * uq.y + uq.z * uq.z;
     const float T1 = 1.0f + 3.0f * eu + 4.5f * eu * eu - 1.5f * uv;        // feq :161-170
-    gr = weight(S) * ra.x * T1;
-    gb = weight(S) * ra.y * T1;
-    if (S > 0 && rq.y < 0.f) {                   // flagged: |C| > 0
-        const float4 rc = __ldg(pc);
+    gr = weight(S) * ab.x * T1;
+    gb = weight(S) * ab.y * T1;
+    if (S > 0 && uq.w < 0.f) {                   // flagged: |C| > 0
         const float cc = sqrtf(rc.x * rc.x + rc.y * rc.y + rc.z * rc.z);
         const float em = -eu;
         const float T2 = 1.0f + 3.0f * em + 4.5f * em * em - 1.5f * uv;
-        const float gro = weight(S) * ra.x * T2, gbo = weight(S) * ra.y * T2;
+        const float gro = weight(S) * ab.x * T2, gbo = weight(S) * ab.y * T2;
         float cs = gr < gro ? gr : gro;
         cs = cs < gb ? cs : gb;
         cs = cs < gbo ? cs : gbo;
@@ -237,22 +284,38 @@ __device__ __forceinline__ void colour_add(float sg, const float4 ra, const floa
         gr = gr + cs;
         gb = gb - cs;
     }
+#else
+    const float t = __fmaf_rn(eu, __fmaf_rn(4.5f, eu, 3.0f), uq.w);
+    if (S > 0) {
+        const float to = __fmaf_rn(-6.0f, eu, t);
+        const float lo = fminf(t, to), hi = fmaxf(t, to);
+        const float pa = __fmul_rn(ab.x, ab.x >= 0.f ? lo : hi), pb = __fmul_rn(ab.y, ab.y >= 0.f ? lo : hi);
+        const float cs = __fmul_rn(fminf(pa, pb), sg * edotu<EX, EY, EZ>(rc.x, rc.y, rc.z));
+        gr = __fmaf_rn(ab.x, t, cs);
+        gb = __fmaf_rn(ab.y, t, -cs);
+    } else {
+        gr = __fmul_rn(ab.x, t);
+        gb = __fmul_rn(ab.y, t);
+    }
+#endif
+}
+// interface part of a record (see colour_term)
+__device__ __forceinline__ float4 load_interface(const float4 *__restrict__ pc, float qflag) {
+#ifdef LBM_STRICT
+    return qflag < 0.f ? __ldg(pc) : make_float4(0.f, 0.f, 0.f, 0.f);
+#else
+    (void)qflag;
+    return __ldg(pc);
+#endif
+}
+template <int S>
+__device__ __forceinline__ void colour_acc(ColourSum &acc, float gr, float gb) {
+#ifdef LBM_STRICT
     acc.r = acc.r + gr;
     acc.b = acc.b + gb;
 #else
-    // feq(s) = w rho t with t = q + eu (3 + 4.5 eu); the opposite direction has t - 6 eu
-    const float t = fabsf(rq.y) + eu * (3.0f + 4.5f * eu);
-    float gr = ra.x * t, gb = ra.y * t;
-    if (S > 0 && rq.y < 0.f) {                   // interface node; most nodes skip this
-        const float4 rc = __ldg(pc);
-        const float to = t - 6.0f * eu;
-        const float cs = fminf(fminf(gr, ra.x * to), fminf(gb, ra.y * to)) *
-                         (sg * edotu<EX, EY, EZ>(rc.x, rc.y, rc.z) * rc.w);
-        gr = gr + cs;
-        gb = gb - cs;
-    }
-    acc.r = acc.r + gr * weight(S);
-    acc.b = acc.b + gb * weight(S);
+    acc.r = __fmaf_rn(gr, weight(S), acc.r);
+    acc.b = __fmaf_rn(gb, weight(S), acc.b);
 #endif
 }
 
@@ -262,60 +325,14 @@ __device__ __forceinline__ void colour_add(float sg, const float4 ra, const floa
 #ifndef LBM2P_COLOUR_MINB
 #define LBM2P_COLOUR_MINB 8
 #endif
+#ifndef LBM2P_COLOUR_MINB_ROWS
+#define LBM2P_COLOUR_MINB_ROWS 4
+#endif
 #ifndef LBM2P_MAIN_MINB
 #define LBM2P_MAIN_MINB 5
 #endif
-__global__ void __launch_bounds__(256, LBM2P_COLOUR_MINB) k2p_colour(const Step2Args A) {
-    const StepArgs &a = A.a;
-    // blockIdx.x walks the z-chunks of a row (fastest), (blockIdx.z, blockIdx.y) the row groups:
-    // blocks that run together then cover whole z-rows, i.e. contiguous 19*nzp*4-byte chunks
-    const uint32_t z = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t r = (blockIdx.z * gridDim.y + blockIdx.y) * blockDim.y + threadIdx.y;
-    if (z >= (uint32_t)a.nz || r >= a.row_count) return;
-    const uint32_t row = a.row_first + r;
-    const uint32_t idx = row * (uint32_t)a.nz + z;
-    const uint8_t cls = a.cls[idx];
-    if (cls == NODE_SOLID || cls == NODE_SOLID_WRITE) return;
-    const int sx = a.ny * a.nz, sy = a.nz;
-    const float4 *__restrict__ pA = A.recA + idx;
-    const float2 *__restrict__ pB = A.recB + idx;
-    const float4 *__restrict__ pC = A.recC + idx;
-    ColourSum acc;
-    uint32_t fl = 0;
-    if (cls == NODE_BULK) {
-        // no solid link, no wrap: sources at uniform offsets
-#define X(s, ex, ey, ez, o)                                                                    \
-    {                                                                                          \
-        const int off = -((ex) * sx + (ey) * sy + (ez));                                       \
-        colour_add<s, ex, ey, ez>(1.0f, __ldg(pA + off), __ldg(pB + off), pC + off, acc);   \
-    }
-        D3Q19_DIRS(X)
-#undef X
-    } else {
-        fl = a.flags[idx];
-        // with ghost planes (x-slab) the x neighbours are always at -+sx: no periodic wrap
-        const uint32_t flw = a.halo_x ? fl & ~(FL_AT_X0 | FL_AT_X1) : fl;
-        // node-linear offsets to x-1 / x+1 ... with the periodic wrap of periodic_index :377-387
-        const int oxm = (flw & FL_AT_X0) ? (a.nx - 1) * sx : -sx;
-        const int oxp = (flw & FL_AT_X1) ? -(a.nx - 1) * sx : sx;
-        const int oym = (fl & FL_AT_Y0) ? (a.ny - 1) * sy : -sy;
-        const int oyp = (fl & FL_AT_Y1) ? -(a.ny - 1) * sy : sy;
-        const int ozm = (fl & FL_AT_Z0) ? (a.nz - 1) : -1;
-        const int ozp = (fl & FL_AT_Z1) ? -(a.nz - 1) : 1;
-#define OFF(ex, ey, ez)                                                                        \
-    ((ex > 0 ? oxm : (ex < 0 ? oxp : 0)) + (ey > 0 ? oym : (ey < 0 ? oyp : 0)) +               \
-     (ez > 0 ? ozm : (ez < 0 ? ozp : 0)))
-#define X(s, ex, ey, ez, o)                                                                    \
-    {                                                                                          \
-        const bool bounce = (fl >> s) & 1u;                                                    \
-        const int off = (s == 0 || bounce) ? 0 : OFF(ex, ey, ez);                              \
-        colour_add<s, ex, ey, ez>(bounce ? -1.0f : 1.0f, __ldg(pA + off), __ldg(pB + off), pC + off, acc); \
-    }
-        D3Q19_DIRS(X)
-#undef X
-#undef OFF
-    }
-    float rr = acc.red(), rb = acc.blue();
+// psi (:605) and Boundary_condition_psi (:445-486) from the colour sums; stores the node's state
+__device__ __forceinline__ void colour_finish(const Step2Args &A, uint32_t node, uint32_t fl, float rr, float rb) {
     float psi = rr - rb / (rr + rb);         // :605, precedence as written
     // Boundary_condition_psi :445-486, faces in order, the last matching face wins
     int win = -1;
@@ -332,9 +349,137 @@ __global__ void __launch_bounds__(256, LBM2P_COLOUR_MINB) k2p_colour(const Step2
         rr = (psi + 1.0f) / 2.0f;
         rb = 1.0f - rr;
     }
-    A.rho_r[idx] = rr;
-    A.rho_b[idx] = rb;
-    A.psi[idx] = psi;
+    A.rrb_out[node] = make_float2(rr, rb);
+    A.psi[node] = psi;
+}
+
+// GATHER = false (lattices that are mostly bulk fluid): a WARP owns 30 consecutive nodes of a z-row
+// and sits on 32 -- one more on either side, wrapped periodically like periodic_index (:377-387).
+// Every lane loads the records of its 9 neighbour z-rows at its own z, evaluates on them the
+// terms that go to z (own), z+1 (up) and z-1 (dn), and hands the up / dn terms to the adjacent
+// lanes with shuffles; the two outer lanes only give.  A node without solid links is complete with
+// that.  9 aligned-row record loads per node instead of 19 gathers, and the 8 warps of a block
+// (8 consecutive y-rows) find most of their rows in L1.  Every other fluid node (solid link) -- and
+// every fluid node when GATHER = true (porous media, where almost every node has a solid link) --
+// evaluates its 19 terms itself from gathered records.
+#define COLOUR_TILE 30
+template <bool GATHER>
+__global__ void __launch_bounds__(256, GATHER ? LBM2P_COLOUR_MINB : LBM2P_COLOUR_MINB_ROWS) k2p_colour(const Step2Args A) {
+    const StepArgs &a = A.a;
+    // blockIdx.x walks the z-chunks of a row (fastest), (blockIdx.z, blockIdx.y) the row groups
+    const uint32_t r = (blockIdx.z * gridDim.y + blockIdx.y) * blockDim.y + threadIdx.y;
+    const uint32_t nz = (uint32_t)a.nz;
+    uint32_t z;
+    bool inside;
+    if (GATHER) {
+        z = blockIdx.x * blockDim.x + threadIdx.x;
+        inside = z < nz && r < a.row_count;
+        if (!inside) return;
+    } else {
+        // blockDim.x = 32: lane l of tile t sits on z = 30 t - 1 + l (mod nz) and owns it for l = 1..30
+        const int zu = (int)(blockIdx.x * COLOUR_TILE + threadIdx.x) - 1;
+        inside = threadIdx.x >= 1u && threadIdx.x <= COLOUR_TILE && zu < (int)nz && r < a.row_count;
+        const int zw = zu % (int)nz;
+        z = (uint32_t)(zw < 0 ? zw + (int)nz : zw);
+    }
+    // rows outside the launch stay (the hand-over is warp-wide) on a clamped address
+    const uint32_t rc = r < a.row_count ? r : a.row_count - 1u;
+    const uint32_t row = a.row_first + rc + (rc >= a.row_split ? a.row_skip : 0u);
+    const uint32_t idx = row * nz + z;
+    const uint8_t cls = a.cls[idx];
+    const bool fluid = inside && (cls == NODE_BULK || cls == NODE_SPECIAL);
+    if (GATHER && !fluid) return;
+    const uint32_t fl = (fluid && cls == NODE_SPECIAL) ? a.flags[idx] : 0u;
+    ColourSum acc;
+    bool done = false;
+    if (!GATHER) {
+        const uint32_t ny = (uint32_t)a.ny, nx = (uint32_t)a.nx;
+        const uint32_t x = row / ny, y = row - x * ny;
+        // neighbour rows with the periodic wrap (in an x-slab the ghost planes make x +- 1 exist)
+        const uint32_t xm = x > 0 ? x - 1 : nx - 1, xp = x + 1 < nx ? x + 1 : 0;
+        const uint32_t ym = y > 0 ? y - 1 : ny - 1, yp = y + 1 < ny ? y + 1 : 0;
+        float up[5][2], dn[5][2];
+        // axis rows: own term (e_z = 0), up term (e_z = +1, for the node above), dn term (e_z = -1)
+#define AXIS_ROW(k, X_, Y_, SO, SU, SD, ex, ey)                                                \
+    {                                                                                          \
+        const uint32_t nb = ((X_) * ny + (Y_)) * nz + z;                                       \
+        const float4 q4 = __ldg(A.uq + nb);                                                    \
+        const float2 ab = __ldg(A.rrb + nb);                                                   \
+        const float4 n4 = load_interface(A.recC + nb, q4.w);                                   \
+        float gr, gb, ur, ub, dr, db;                                                          \
+        colour_term<SO, ex, ey, 0>(1.0f, ab, q4, n4, gr, gb);                                  \
+        colour_term<SU, ex, ey, 1>(1.0f, ab, q4, n4, ur, ub);                                  \
+        colour_term<SD, ex, ey, -1>(1.0f, ab, q4, n4, dr, db);                                 \
+        colour_acc<SO>(acc, gr, gb);                                                           \
+        up[k][0] = __shfl_up_sync(0xffffffffu, ur, 1);                                         \
+        up[k][1] = __shfl_up_sync(0xffffffffu, ub, 1);                                         \
+        dn[k][0] = __shfl_down_sync(0xffffffffu, dr, 1);                                       \
+        dn[k][1] = __shfl_down_sync(0xffffffffu, db, 1);                                       \
+    }
+        AXIS_ROW(0, x, y, 0, 5, 6, 0, 0)           // s = 0 ; 5 = (0,0,1) ; 6 = (0,0,-1)
+        AXIS_ROW(1, xm, y, 1, 11, 13, 1, 0)        // s = 1 = (1,0,0) ; 11 = (1,0,1) ; 13 = (1,0,-1)
+        AXIS_ROW(2, xp, y, 2, 14, 12, -1, 0)       // s = 2 ; 14 = (-1,0,1) ; 12 = (-1,0,-1)
+        AXIS_ROW(3, x, ym, 3, 15, 17, 0, 1)        // s = 3 ; 15 = (0,1,1) ; 17 = (0,1,-1)
+        AXIS_ROW(4, x, yp, 4, 18, 16, 0, -1)       // s = 4 ; 18 = (0,-1,1) ; 16 = (0,-1,-1)
+#undef AXIS_ROW
+        colour_acc<5>(acc, up[0][0], up[0][1]);
+        colour_acc<6>(acc, dn[0][0], dn[0][1]);
+#define DIAG_ROW(S, X_, Y_, ex, ey)                                                            \
+    {                                                                                          \
+        const uint32_t nb = ((X_) * ny + (Y_)) * nz + z;                                       \
+        const float4 q4 = __ldg(A.uq + nb);                                                    \
+        float gr, gb;                                                                          \
+        colour_term<S, ex, ey, 0>(1.0f, __ldg(A.rrb + nb), q4, load_interface(A.recC + nb, q4.w), gr, gb); \
+        colour_acc<S>(acc, gr, gb);                                                            \
+    }
+        DIAG_ROW(7, xm, ym, 1, 1)
+        DIAG_ROW(8, xp, yp, -1, -1)
+        DIAG_ROW(9, xm, yp, 1, -1)
+        DIAG_ROW(10, xp, ym, -1, 1)
+#undef DIAG_ROW
+        colour_acc<11>(acc, up[1][0], up[1][1]);
+        colour_acc<12>(acc, dn[2][0], dn[2][1]);
+        colour_acc<13>(acc, dn[1][0], dn[1][1]);
+        colour_acc<14>(acc, up[2][0], up[2][1]);
+        colour_acc<15>(acc, up[3][0], up[3][1]);
+        colour_acc<16>(acc, dn[4][0], dn[4][1]);
+        colour_acc<17>(acc, dn[3][0], dn[3][1]);
+        colour_acc<18>(acc, up[4][0], up[4][1]);
+        if (!fluid) return;
+        done = (fl & FL_LINK_MASK) == 0u;          // no solid link: nothing bounced back
+    }
+    if (!done) {
+        acc = ColourSum();
+        const int sx = a.ny * a.nz, sy = a.nz;
+        // with ghost planes (x-slab) the x neighbours are always at -+sx: no periodic wrap
+        const uint32_t flw = a.halo_x ? fl & ~(FL_AT_X0 | FL_AT_X1) : fl;
+        // node-linear offsets to x-1 / x+1 ... with the periodic wrap of periodic_index :377-387
+        const int oxm = (flw & FL_AT_X0) ? (a.nx - 1) * sx : -sx;
+        const int oxp = (flw & FL_AT_X1) ? -(a.nx - 1) * sx : sx;
+        const int oym = (fl & FL_AT_Y0) ? (a.ny - 1) * sy : -sy;
+        const int oyp = (fl & FL_AT_Y1) ? -(a.ny - 1) * sy : sy;
+        const int ozm = (fl & FL_AT_Z0) ? (a.nz - 1) : -1;
+        const int ozp = (fl & FL_AT_Z1) ? -(a.nz - 1) : 1;
+        const float4 *__restrict__ pU = A.uq + idx;
+        const float2 *__restrict__ pR = A.rrb + idx;
+        const float4 *__restrict__ pC = A.recC + idx;
+#define OFF(ex, ey, ez)                                                                        \
+    ((ex > 0 ? oxm : (ex < 0 ? oxp : 0)) + (ey > 0 ? oym : (ey < 0 ? oyp : 0)) +               \
+     (ez > 0 ? ozm : (ez < 0 ? ozp : 0)))
+#define X(s, ex, ey, ez, o)                                                                    \
+    {                                                                                          \
+        const bool bounce = (fl >> s) & 1u;                                                    \
+        const int off = (s == 0 || bounce) ? 0 : OFF(ex, ey, ez);                              \
+        float gr, gb;                                                                          \
+        const float4 q4 = __ldg(pU + off);                                                     \
+        colour_term<s, ex, ey, ez>(bounce ? -1.0f : 1.0f, __ldg(pR + off), q4, load_interface(pC + off, q4.w), gr, gb); \
+        colour_acc<s>(acc, gr, gb);                                                            \
+    }
+        D3Q19_DIRS(X)
+#undef X
+#undef OFF
+    }
+    colour_finish(A, idx, fl, acc.r, acc.b);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -473,39 +618,50 @@ __global__ void __launch_bounds__(256, LBM2P_MAIN_MINB) k2p_main(const Step2Args
     if (compute) {
         // Compute_C :259-275: C = sum_s 3 w_s e_s psi(i + e_s); solid nodes of the psi array hold
         // psi_solid; constant-psi faces clamp the stencil (:390-428)
-        const int sx = a.ny * a.nz, sy = a.nz;
-        int oxm = -sx, oxp = sx, oym = -sy, oyp = sy, ozm = -1, ozp = 1;
-        if (fl & (FL_AT_X0 | FL_AT_X1 | FL_AT_Y0 | FL_AT_Y1 | FL_AT_Z0 | FL_AT_Z1)) {
+        float Cx = 0.f, Cy = 0.f, Cz = 0.f;
+        const float *__restrict__ ps = A.psi + idx;
+#define GRAD(val, s, ex, ey, ez)                                                               \
+        if (ex != 0) Cx = Cx + (3.0f * weight(s) * (float)(ex)) * val;                           \
+        if (ey != 0) Cy = Cy + (3.0f * weight(s) * (float)(ey)) * val;                           \
+        if (ez != 0) Cz = Cz + (3.0f * weight(s) * (float)(ez)) * val;
+        if (!(fl & (FL_AT_X0 | FL_AT_X1 | FL_AT_Y0 | FL_AT_Y1 | FL_AT_Z0 | FL_AT_Z1))) {
+            // away from the lattice faces the stencil sits at fixed offsets
+#define X(s, ex, ey, ez, o)                                                                    \
+    if (s > 0) {                                                                               \
+        const float val = __ldg(A.psi_nb[s] + idx);                                            \
+        GRAD(val, s, ex, ey, ez)                                                               \
+    }
+            D3Q19_DIRS(X)
+#undef X
+        } else {
+            const int sx = a.ny * a.nz, sy = a.nz;
+            int oxm = -sx, oxp = sx, oym = -sy, oyp = sy, ozm = -1, ozp = 1;
             if (fl & FL_AT_X0) oxm = A.bc_psi_type[0] == 0 ? (a.halo_x ? -sx : (a.nx - 1) * sx) : 0;
             if (fl & FL_AT_X1) oxp = A.bc_psi_type[1] == 0 ? (a.halo_x ? sx : -(a.nx - 1) * sx) : 0;
             if (fl & FL_AT_Y0) oym = A.bc_psi_type[2] == 0 ? (a.ny - 1) * sy : 0;
             if (fl & FL_AT_Y1) oyp = A.bc_psi_type[3] == 0 ? -(a.ny - 1) * sy : 0;
             if (fl & FL_AT_Z0) ozm = A.bc_psi_type[4] == 0 ? (a.nz - 1) : 0;
             if (fl & FL_AT_Z1) ozp = A.bc_psi_type[5] == 0 ? -(a.nz - 1) : 0;
-        }
-        const float *__restrict__ ps = A.psi + idx;
-        float Cx = 0.f, Cy = 0.f, Cz = 0.f;
 #define X(s, ex, ey, ez, o)                                                                    \
     if (s > 0) {                                                                               \
         const float val = __ldg(ps + ((ex > 0 ? oxp : (ex < 0 ? oxm : 0)) + (ey > 0 ? oyp : (ey < 0 ? oym : 0)) + \
                                       (ez > 0 ? ozp : (ez < 0 ? ozm : 0))));                   \
-        if (ex != 0) Cx = Cx + (3.0f * weight(s) * (float)(ex)) * val;                           \
-        if (ey != 0) Cy = Cy + (3.0f * weight(s) * (float)(ey)) * val;                           \
-        if (ez != 0) Cz = Cz + (3.0f * weight(s) * (float)(ez)) * val;                           \
+        GRAD(val, s, ex, ey, ez)                                                               \
     }
-        D3Q19_DIRS(X)
+            D3Q19_DIRS(X)
 #undef X
-        const float rr = A.rho_r[idx], rb = A.rho_b[idx];
-        if ((fl & FL_NEAR_SOLID) && fabsf(rr - rb) > 0.9f) { Cx = 0.f; Cy = 0.f; Cz = 0.f; }   // :271-273
+        }
+#undef GRAD
+        if (fl & FL_NEAR_SOLID) {                                   // :271-273 (wetting switch)
+            const float2 ab = A.rrb[idx];
+            if (fabsf(ab.x - ab.y) > 0.9f) { Cx = 0.f; Cy = 0.f; Cz = 0.f; }
+        }
         const float psi = ps[0];
-        collide2(f, A, FORCE, rho, ux, uy, uz, psi, Cx, Cy, Cz);
-        // colour record of this collision (see lbm2p_kernels.cuh)
-        const float c2 = Cx * Cx + Cy * Cy + Cz * Cz;
-        const float ccn = sqrtf(c2);
-        const float q = 1.0f - 1.5f * (ux * ux + uy * uy + uz * uz);
-        A.recA[idx] = make_float4(rr, rb, ux, uy);
-        A.recB[idx] = make_float2(uz, ccn > 0.f ? -q : q);
-        if (ccn > 0.f) A.recC[idx] = make_float4(Cx, Cy, Cz, 1.0f / ccn);
+        float inv;
+        collide2(f, A, FORCE, rho, ux, uy, uz, psi, Cx, Cy, Cz, inv);
+        // colour record of this collision (lbm2p_kernels.cuh); rho_r, rho_b stay where the colour
+        // pass left them
+        write_record(A, idx, ux, uy, uz, Cx, Cy, Cz, inv);
     }
 #pragma unroll
     for (int s = 0; s < 19; ++s) a.pout[s][pidx] = f[s];
@@ -585,30 +741,14 @@ __global__ void __launch_bounds__(SPARSE_BLOCK, LBM2P_COLOUR_MINB) k2p_colour_sp
         const bool bounce = s > 0 && ((fl >> s) & 1u);                                         \
         uint32_t j = i;                                                                        \
         if (s > 0 && !bounce) j = exc ? (uint32_t)__ldg(a.exc[s > 0 ? s - 1 : 0] + slot) : (uint32_t)comp_source<ex, ey, ez>(i, fl, rb); \
-        colour_add<s, ex, ey, ez>(bounce ? -1.0f : 1.0f, __ldg(A.recA + j), __ldg(A.recB + j), A.recC + j, acc); \
+        float gr, gb;                                                                          \
+        const float4 q4 = __ldg(A.uq + j);                                                     \
+        colour_term<s, ex, ey, ez>(bounce ? -1.0f : 1.0f, __ldg(A.rrb + j), q4, load_interface(A.recC + j, q4.w), gr, gb); \
+        colour_acc<s>(acc, gr, gb);                                                            \
     }
     D3Q19_DIRS(X)
 #undef X
-    float rr = acc.red(), rbl = acc.blue();
-    float psi = rr - rbl / (rr + rbl);       // :605, precedence as written
-    // Boundary_condition_psi :445-486, faces in order, the last matching face wins
-    int win = -1;
-    if (fl & (FL_AT_X0 | FL_AT_X1 | FL_AT_Y0 | FL_AT_Y1 | FL_AT_Z0 | FL_AT_Z1)) {
-        if ((fl & FL_AT_X0) && A.bc_psi_type[0] == 1) win = 0;
-        if ((fl & FL_AT_X1) && A.bc_psi_type[1] == 1) win = 1;
-        if ((fl & FL_AT_Y0) && A.bc_psi_type[2] == 1) win = 2;
-        if ((fl & FL_AT_Y1) && A.bc_psi_type[3] == 1) win = 3;
-        if ((fl & FL_AT_Z0) && A.bc_psi_type[4] == 1) win = 4;
-        if ((fl & FL_AT_Z1) && A.bc_psi_type[5] == 1) win = 5;
-    }
-    if (win >= 0) {
-        psi = A.bc_psi_val[win];
-        rr = (psi + 1.0f) / 2.0f;
-        rbl = 1.0f - rr;
-    }
-    A.rho_r[i] = rr;
-    A.rho_b[i] = rbl;
-    A.psi[i] = psi;
+    colour_finish(A, i, fl, acc.r, acc.b);
 }
 
 template <bool FORCE, int MODE>
@@ -736,15 +876,14 @@ __global__ void __launch_bounds__(SPARSE_BLOCK, LBM2P_MAIN_MINB) k2p_main_sparse
         D3Q19_DIRS(X)
 #undef X
     }
-    const float rr = A.rho_r[i], rbl = A.rho_b[i];
-    if ((fl & FL_NEAR_SOLID) && fabsf(rr - rbl) > 0.9f) { Cx = 0.f; Cy = 0.f; Cz = 0.f; }   // :271-273
+    if (fl & FL_NEAR_SOLID) {                                       // :271-273 (wetting switch)
+        const float2 ab = A.rrb[i];
+        if (fabsf(ab.x - ab.y) > 0.9f) { Cx = 0.f; Cy = 0.f; Cz = 0.f; }
+    }
     const float psi = A.psi[i];
-    collide2(f, A, FORCE, rho, ux, uy, uz, psi, Cx, Cy, Cz);
-    const float ccn = sqrtf(Cx * Cx + Cy * Cy + Cz * Cz);
-    const float q = 1.0f - 1.5f * (ux * ux + uy * uy + uz * uz);
-    A.recA[i] = make_float4(rr, rbl, ux, uy);
-    A.recB[i] = make_float2(uz, ccn > 0.f ? -q : q);
-    if (ccn > 0.f) A.recC[i] = make_float4(Cx, Cy, Cz, 1.0f / ccn);
+    float inv;
+    collide2(f, A, FORCE, rho, ux, uy, uz, psi, Cx, Cy, Cz, inv);
+    write_record(A, i, ux, uy, uz, Cx, Cy, Cz, inv);
 #pragma unroll
     for (int s = 0; s < 19; ++s) a.pout[s][i] = f[s];
 }
@@ -823,8 +962,18 @@ cudaError_t launch_colour(const Step2Args &A, int block, cudaStream_t st) {
         zmax = e ? atoi(e) : 32;
         if (zmax < 32 || zmax > 256 || zmax % 32) zmax = 32;
     }
-    geometry(A.a, block, grid, blk, zmax);
-    k2p_colour<<<grid, blk, 0, st>>>(A);
+    if (!A.gather) {
+        // mostly bulk fluid: a warp per 30 nodes of a z-row (+ one either side), 8 y-rows per block
+        const unsigned by = 8, rg = (A.a.row_count + by - 1) / by, gy = rg < 32768u ? rg : 32768u;
+        blk = dim3(32, by, 1);
+        grid = dim3((A.a.nz + COLOUR_TILE - 1) / COLOUR_TILE, gy, (rg + gy - 1) / gy);
+        k2p_colour<false><<<grid, blk, 0, st>>>(A);
+    } else {
+        // porous medium: almost every node gathers; a block of a few y-rows x 32 z shares most of
+        // the records through L1 (half the L2->L1 traffic of a one-row block)
+        geometry(A.a, block, grid, blk, zmax);
+        k2p_colour<true><<<grid, blk, 0, st>>>(A);
+    }
     return cudaGetLastError();
 }
 

@@ -153,6 +153,10 @@ struct IsFluid {
     __host__ __device__ uint32_t operator()(const int8_t &s) const { return s == 0 ? 1u : 0u; }
 };
 
+struct IsBulk {
+    __host__ __device__ uint32_t operator()(const uint8_t &c) const { return c == NODE_BULK ? 1u : 0u; }
+};
+
 __global__ void k_fill(float *p, size_t n, float v) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
