@@ -454,8 +454,9 @@ def main():
     part = SlabPartition(gnx, world, rank)
     planes = range(gnx) if world == 1 else part.local_planes()
     pinned = torch.from_numpy(cavity_planes(gnx, ny, nz, planes)).pin_memory()
-    rho_pin = torch.empty((part.own, ny, nz), dtype=torch.float32, pin_memory=True)
-    v_pin = torch.empty((part.own, ny, nz, 3), dtype=torch.float32, pin_memory=True)
+    ghosts = 0 if world == 1 else 2            # a slab is read back with its two ghost planes
+    rho_pin = torch.empty((part.own + ghosts, ny, nz), dtype=torch.float32, pin_memory=True)
+    v_pin = torch.empty((part.own + ghosts, ny, nz, 3), dtype=torch.float32, pin_memory=True)
     env.barrier()
     t0 = time.perf_counter()
     lb2 = make_cavity_solver(env, gnx, ny, nz, pinned=pinned.numpy())     # H2D + flag build
@@ -468,9 +469,8 @@ def main():
         rho_h = lb2.rho.to_numpy(out=rho_pin.numpy())                     # D2H into pinned host buffers
         v_h = lb2.v.to_numpy(out=v_pin.numpy())
     else:
-        rho_pin.numpy()[...] = lb2.local_field("rho")
-        v_pin.numpy()[...] = lb2.local_field("v")
-        rho_h, v_h = rho_pin.numpy(), v_pin.numpy()
+        rho_h = lb2.local_field("rho", out=rho_pin.numpy())            # views of the owned planes
+        v_h = lb2.local_field("v", out=v_pin.numpy())
     mv = lb2.get_max_v()
     env.barrier()
     dt = env.max_over_ranks(time.perf_counter() - t0)

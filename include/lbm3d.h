@@ -86,6 +86,10 @@ const char *lbm_last_error(const lbm_ctx *ctx);   /* ctx may be NULL: last creat
 int lbm_set_geometry(lbm_ctx *ctx, const int8_t *solid_host_or_dev);
 /* set_bc_vel_* / set_bc_rho_* (:405-451): type 2 uses vel (rho ignored), type 1 uses rho */
 int lbm_set_bc(lbm_ctx *ctx, int face, int type, float rho, const float vel[3]);
+/* form of the fixed-velocity faces: 0 = the class (:283-288), F = feq(1, u) on all 19 populations;
+ * 1 = the script copies of the solver (Single_phase/lbm_solver_3d.py:253,268), in place for
+ * s = 0..18:  F[s] = feq(LR[s], 1, u) - F[LR[s]] + feq(s, 1, u).  Before lbm_init. */
+int lbm_set_vel_bc_form(lbm_ctx *ctx, int script_form);
 /* set_force (:457); force_flag as :137-140 */
 int lbm_set_force(lbm_ctx *ctx, const float force[3]);
 /* form of the Guo force term in the collision: 0 = the class (:236, parts divided by 3 and 9:
@@ -133,6 +137,11 @@ int lbm_set_v(lbm_ctx *ctx, const float *src_host_or_dev);
 int lbm_set_F(lbm_ctx *ctx, const float *src_host_or_dev);
 /* get_max_v + cal_max_v (:394-402) */
 int lbm_get_max_v(lbm_ctx *ctx, float *out);
+/* probe: the fields at n selected nodes (linear index i*ny*nz + j*nz + k), what F[i,j,k], rho[i,j,k],
+ * v[i,j,k] read in the reference -- without copying whole lattices to the host (F of a 512^3 lattice
+ * is 10 GB).  Any of the three outputs may be NULL; F_out is [n][19], v_out [n][3]. */
+int lbm_get_nodes(lbm_ctx *ctx, int64_t n, const int64_t *index_host_or_dev, float *F_out_host_or_dev,
+                  float *rho_out_host_or_dev, float *v_out_host_or_dev);
 
 /* ---- sparse storage tables (bit-exact compaction tests; north_star item 1) ------------ */
 int lbm_get_num_fluid(lbm_ctx *ctx, int64_t *n_fluid);

@@ -13,14 +13,14 @@ import numpy as np
 from . import ref_single_phase as _np_ref
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_BUILD = os.path.join(_HERE, "_build")
+_BUILD = os.environ.get("LBM3D_ORACLE_BUILD") or os.path.join(_HERE, "_build")      # override: a scratch build
 
 
 def build(force=False):
     """Compile the C oracle (gcc, OpenMP) into oracle/_build/."""
     targets = [os.path.join(_BUILD, n) for n in ("libref_strict.so", "libref_fast.so")]
     if force or not all(os.path.exists(t) for t in targets):
-        subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), check=True,
+        subprocess.run(["make", "-C", _HERE, "OUT=" + _BUILD] + (["-B"] if force else []), check=True,
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     return targets
 
@@ -43,7 +43,8 @@ def _params_struct(ctype):
                     ("force_flag", ctypes.c_int), ("bc_type", ctypes.c_int * 6),
                     ("S", ctype * 19), ("invM", ctype * 361), ("w", ctype * 19),
                     ("force", ctype * 3), ("bc_rho", ctype * 6), ("bc_vel", (ctype * 3) * 6),
-                    ("force_field", ctypes.c_void_p), ("guo_unscaled", ctypes.c_int)]
+                    ("force_field", ctypes.c_void_p), ("guo_unscaled", ctypes.c_int),
+                    ("vel_bc_script", ctypes.c_int)]
     return P
 
 
@@ -54,8 +55,9 @@ _P64 = _params_struct(ctypes.c_double)
 class RefSinglePhaseC(_np_ref.RefSinglePhase):
     """Same state and setters as the NumPy oracle; the four passes run in C."""
 
-    def __init__(self, nx, ny, nz, dtype=np.float32, tau_mode="class", kind="strict", guo_mode="class"):
-        super().__init__(nx, ny, nz, dtype=dtype, tau_mode=tau_mode, guo_mode=guo_mode)
+    def __init__(self, nx, ny, nz, dtype=np.float32, tau_mode="class", kind="strict", guo_mode="class",
+                 vel_bc_mode="class"):
+        super().__init__(nx, ny, nz, dtype=dtype, tau_mode=tau_mode, guo_mode=guo_mode, vel_bc_mode=vel_bc_mode)
         self._lib = load(kind)
         self._suf = "f32" if self.dtype == np.float32 else "f64"
         self._ct = ctypes.c_float if self.dtype == np.float32 else ctypes.c_double
@@ -95,6 +97,7 @@ class RefSinglePhaseC(_np_ref.RefSinglePhase):
         ff = getattr(self, "force_field", None)
         p.force_field = None if ff is None else ff.ctypes.data
         p.guo_unscaled = 1 if self.guo_mode == "unscaled" else 0
+        p.vel_bc_script = 1 if self.vel_bc_mode == "script" else 0
         self._p = p
 
     def set_force_field(self, force):

@@ -71,6 +71,7 @@ typedef struct {
     REAL bc_vel[6][3];
     const REAL *force_field; /* [n][3] per-node force = cal_local_force(i,j,k) :217-220, or NULL */
     int guo_unscaled;        /* 1: Phase_change/LBM_3D_SinglePhase_Solver.py:235 (no /3, /9) */
+    int vel_bc_script;       /* 1: Single_phase/lbm_solver_3d.py:253 (in-place velocity form) */
 } FN(ref_params);
 typedef FN(ref_params) params_t;
 
@@ -180,6 +181,11 @@ void FN(ref_sp_boundary_condition)(const params_t *p, const int8_t *solid, const
                     size_t cin = nidx(p, ijk_in[0], ijk_in[1], ijk_in[2]);
                     const REAL *u = solid[cin] > 0 ? v + cin * 3 : v + c * 3;
                     for (int s = 0; s < 19; ++s) F[c * 19 + s] = feq(p, s, p->bc_rho[face], u);
+                } else if (p->vel_bc_script) {
+                    /* Single_phase/lbm_solver_3d.py:253, in place for s = 0..18 */
+                    for (int s = 0; s < 19; ++s)
+                        F[c * 19 + s] = feq(p, LRi[s], R(1.0), p->bc_vel[face]) - F[c * 19 + LRi[s]] +
+                                        feq(p, s, R(1.0), p->bc_vel[face]);
                 } else {
                     for (int s = 0; s < 19; ++s) F[c * 19 + s] = feq(p, s, R(1.0), p->bc_vel[face]);
                 }

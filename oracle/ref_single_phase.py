@@ -96,11 +96,12 @@ class RefSinglePhase:
     nodes keep f = F = w, rho = 1, v = 0.
     """
 
-    def __init__(self, nx, ny, nz, dtype=np.float32, tau_mode="class", guo_mode="class"):
+    def __init__(self, nx, ny, nz, dtype=np.float32, tau_mode="class", guo_mode="class", vel_bc_mode="class"):
         self.nx, self.ny, self.nz = nx, ny, nz
         self.dtype = np.dtype(dtype)
         self.tau_mode = tau_mode
         self.guo_mode = guo_mode            # "unscaled": Phase_change/LBM_3D_SinglePhase_Solver.py:235
+        self.vel_bc_mode = vel_bc_mode      # "script": Single_phase/lbm_solver_3d.py:253,268
         # :17-18
         self.fx, self.fy, self.fz = 0.0e-6, 0.0, 0.0
         self.force_field = None             # array form of an overridden cal_local_force
@@ -272,6 +273,15 @@ class RefSinglePhase:
                 for s in range(19):
                     val = self._feq(s, dt(self.bc_rho[face]), u)
                     Fs = self.F[idx + (s,)]
+                    Fs[fl] = val[fl]
+            elif self.vel_bc_mode == "script":
+                # Single_phase/lbm_solver_3d.py:253: F[s] = feq(LR[s],1,u) - F[LR[s]] + feq(s,1,u), in
+                # place for s = 0..18 -- for LR[s] < s the F[LR[s]] read is the value just written
+                u = np.array(self.bc_vel[face]).astype(self.dtype)
+                for s in range(19):
+                    Fs = self.F[idx + (s,)]
+                    Fo = self.F[idx + (int(LR[s]),)]
+                    val = self._feq(int(LR[s]), dt(1.0), u) - Fo + self._feq(s, dt(1.0), u)
                     Fs[fl] = val[fl]
             else:                                             # :283-288 etc.
                 u = np.array(self.bc_vel[face]).astype(self.dtype)

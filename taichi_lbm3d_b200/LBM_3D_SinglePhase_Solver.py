@@ -67,7 +67,7 @@ class _Field:
 
 class LB3D_Solver_Single_Phase:
     def __init__(self, nx, ny, nz, sparse_storage=False, strict=False, tau_mode="class", device=None,
-                 in_place=None, guo_mode="class"):
+                 in_place=None, guo_mode="class", vel_bc_mode="class"):
         # reference :13-28
         self.enable_projection = True
         self.sparse_storage = sparse_storage
@@ -90,6 +90,12 @@ class LB3D_Solver_Single_Phase:
         if guo_mode not in ("class", "unscaled"):
             raise ValueError("guo_mode must be 'class' or 'unscaled'")
         self.guo_mode = guo_mode
+        # "class": a fixed-velocity face overwrites its nodes with feq(1, u) (:283-288); "script": the
+        # form of the solver's script copies (Single_phase/lbm_solver_3d.py:253), in place for s = 0..18:
+        # F[s] = feq(LR[s], 1, u) - F[LR[s]] + feq(s, 1, u)
+        if vel_bc_mode not in ("class", "script"):
+            raise ValueError("vel_bc_mode must be 'class' or 'script'")
+        self.vel_bc_mode = vel_bc_mode
         self.device = device
         self._solid_host = np.zeros((nx, ny, nz), np.int8)
         self._force_field = None
@@ -231,6 +237,7 @@ class LB3D_Solver_Single_Phase:
         fc = (ctypes.c_float * 3)(float(np.float32(self.fx)), float(np.float32(self.fy)), float(np.float32(self.fz)))
         self._ck(lib.lbm_set_force(ctx, fc), "lbm_set_force")
         self._ck(lib.lbm_set_guo_form(ctx, 1 if self.guo_mode == "unscaled" else 0), "lbm_set_guo_form")
+        self._ck(lib.lbm_set_vel_bc_form(ctx, 1 if self.vel_bc_mode == "script" else 0), "lbm_set_vel_bc_form")
         self._ck(lib.lbm_set_relaxation(ctx, S.ctypes.data_as(_lib._FP)), "lbm_set_relaxation")
         if self.strict:
             from .constants import M_np
@@ -264,6 +271,18 @@ class LB3D_Solver_Single_Phase:
     def launch_count(self):
         return int(self._lib.lbm_launch_count(self._require_ctx()))
 
+    def sample(self, index, fields=("F", "rho", "v")):
+        """F, rho, v at the nodes with linear index ``i*ny*nz + j*nz + k`` (addition: a probe that
+        does not copy whole lattices to the host); returns a dict of arrays [n,19], [n], [n,3]"""
+        idx = np.ascontiguousarray(np.asarray(index, dtype=np.int64).reshape(-1))
+        out = {"F": np.empty((idx.size, 19), np.float32) if "F" in fields else None,
+               "rho": np.empty(idx.size, np.float32) if "rho" in fields else None,
+               "v": np.empty((idx.size, 3), np.float32) if "v" in fields else None}
+        ptr = lambda a: ctypes.c_void_p(None) if a is None else a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+        self._ck(self._lib.lbm_get_nodes(self._require_ctx(), idx.size, idx.ctypes.data_as(ctypes.c_void_p),
+                                         ptr(out["F"]), ptr(out["rho"]), ptr(out["v"])), "lbm_get_nodes")
+        return {k: v for k, v in out.items() if v is not None}
+
     # ---- output, reference :462-475 ----------------------------------------------------------
     def export_VTK(self, n):
         v = self.v.to_numpy()
@@ -287,7 +306,7 @@ class LB3D_Solver_Single_Phase:
             t, rho, vel = self._bc_tuple(face)
             bcs.append([float(t), float(rho)] + [float(c) for c in vel])
         return {"niu": float(self.niu), "force": [float(self.fx), float(self.fy), float(self.fz)],
-                "tau_mode": self.tau_mode, "guo_mode": self.guo_mode, "bc": bcs}
+                "tau_mode": self.tau_mode, "guo_mode": self.guo_mode, "vel_bc_mode": self.vel_bc_mode, "bc": bcs}
 
     def save_checkpoint(self, path):
         """state of the run (F, rho, v), geometry, per-node force and the case settings (viscosity,

@@ -47,6 +47,7 @@ SIGNATURES = {
     "lbm_set_force": (_I, [_VP, _FP]),
     "lbm_set_force_field": (_I, [_VP, _VP]),
     "lbm_set_guo_form": (_I, [_VP, _I]),
+    "lbm_set_vel_bc_form": (_I, [_VP, _I]),
     "lbm_set_viscosity": (_I, [_VP, _c.c_double, _I]),
     "lbm_set_relaxation": (_I, [_VP, _FP]),
     "lbm_set_inverse_matrix": (_I, [_VP, _FP]),
@@ -62,6 +63,7 @@ SIGNATURES = {
     "lbm_set_v": (_I, [_VP, _VP]),
     "lbm_set_F": (_I, [_VP, _VP]),
     "lbm_get_max_v": (_I, [_VP, _FP]),
+    "lbm_get_nodes": (_I, [_VP, _I64, _VP, _VP, _VP, _VP]),
     "lbm_get_num_fluid": (_I, [_VP, _c.POINTER(_I64)]),
     "lbm_get_fluid_index": (_I, [_VP, _VP]),
     "lbm_get_neighbor_table": (_I, [_VP, _VP]),

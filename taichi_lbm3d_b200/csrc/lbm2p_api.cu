@@ -208,7 +208,7 @@ void fill2(const lbm2p_ctx *c, Step2Args &A, const float *fin, float *fout) {
         a.count = c->sp.own_count;
         a.lin = c->sp.d_lin;
         a.compressed = 1;
-        for (int k = 0; k < 8; ++k) a.rb16[k] = c->sp.d_rb16 + (size_t)k * c->sp.stride;
+        for (int k = 0; k < 8; ++k) a.rb8[k] = c->sp.d_rb8 + (size_t)k * c->sp.stride;
         a.blk = c->sp.d_blk;
         for (int k = 0; k < 18; ++k) a.exc[k] = c->sp.d_exc + (size_t)k * c->sp.exc_stride;
     }
@@ -489,6 +489,7 @@ int lbm2p_init(lbm2p_ctx *c) {
     g.xface0 = c->xface0; g.xface1 = c->xface1;
     for (int i = 0; i < 6; ++i) { g.bc_type[i] = c->face[i].type; g.bc_psi_type[i] = c->bc_psi_type[i]; }
     g.two_phase = 1;
+    g.vel_in_place = 0;
     CU2(c, cudaMalloc(&c->d_scalar, 16));
     CU2(c, cudaMalloc(&c->d_rho, N * sizeof(float)));
     CU2(c, cudaMalloc(&c->d_v, N * 3 * sizeof(float)));
@@ -847,16 +848,16 @@ static int launch_planes2(lbm2p_ctx *c, int kind, int x0, int x1, cudaStream_t s
 }
 
 // nsteps iterations of the main loop :626-632 on one x-slab, halo exchanges inside.
-// Default: colour ; exchange(psi) ; main ; exchange(f*, records) on one stream.
-// LBM3D_2P_OVERLAP=1 (EXPERIMENTAL, off by default): boundary planes first, their exchange on a
-// highest-priority side stream while the interior planes are updated.  Bit-identical in the ring
-// of one and over NCCL on 2 B200, +13 % at 2 x 128 x 256^2 as the first solver of a process, but it
-// hangs at that size when other slab solvers / communicators were used earlier in the same
-// process (scripts/multi_gpu_check_2p.py), so it is not enabled:
+// Default: boundary planes first, their exchange on a highest-priority side stream while the interior
+// planes are updated (bit-identical to the plain schedule; 2 B200, 2 x 128 x 256^2: 0.590 ms per step
+// against 0.704):
 //   main stream  colour(interior) . wait XA' . colour(boundary) . main(interior) . wait XB . main(boundary) ...
-//   side stream                                  XB = exchange(psi)                XA = exchange(f*, records)
+//   side stream                                  XB = exchange(psi, rho_r, rho_b)   XA = exchange(f*, records)
 // (XA' = the exchange of the previous step; the colour pass of interior planes only reads records
-// of owned planes, so it runs beside it).
+// of owned planes, so it runs beside it).  LBM3D_2P_OVERLAP=0 selects the plain schedule: colour ;
+// exchange ; main ; exchange on one stream.  (With one NCCL communicator per CONTEXT, as in round 1,
+// this schedule hung once earlier solvers of the same process had used theirs; the process-wide
+// communicator of lbm_nccl.cuh removed that.)
 int lbm2p_run_slab(lbm2p_ctx *c, int nsteps, void *cuda_stream) {
     CTX2(c);
     if (!c->inited || !c->halo) FAIL2(c, -4, "needs an initialised x-slab context");
@@ -873,7 +874,7 @@ int lbm2p_run_slab(lbm2p_ctx *c, int nsteps, void *cuda_stream) {
         nsteps -= 1;
     }
     const int nx = c->cfg.nx, own = nx - 2;
-    static const bool want_overlap = getenv("LBM3D_2P_OVERLAP") ? atoi(getenv("LBM3D_2P_OVERLAP")) != 0 : false;
+    static const bool want_overlap = getenv("LBM3D_2P_OVERLAP") ? atoi(getenv("LBM3D_2P_OVERLAP")) != 0 : true;
     if (!want_overlap || own < 3) {
         for (int it = 0; it < nsteps; ++it) {
             int r = stage2(c, 1, st);                  // rho_r, rho_b, psi of the step just collided

@@ -727,14 +727,13 @@ __global__ void __launch_bounds__(SPARSE_BLOCK, LBM2P_COLOUR_MINB) k2p_colour_sp
     __syncthreads();
     if (threadIdx.x == 0) table_fetch(a, blk, s_tab, &s_bar);
     const uint32_t i = blk * SPARSE_BLOCK + threadIdx.x;
-    mbar_wait(&s_bar, 0);
+    table_wait(a, blk, s_tab, &s_bar);
     if (i < a.first || i >= a.first + a.count) return;
     const uint32_t fl = s_tab.fl[threadIdx.x];
     const bool exc = fl & FL_EXCEPTION;
     int32_t rb[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) rb[k] = s_tab.blk[k] + (int32_t)s_tab.rb[k][threadIdx.x];
-    const uint32_t slot = (uint32_t)s_tab.blk[8] + s_tab.rb[0][threadIdx.x];
+    table_ranks(s_tab, i, rb);
+    const uint32_t slot = table_exc_slot(s_tab);
     ColourSum acc;
 #define X(s, ex, ey, ez, o)                                                                    \
     {                                                                                          \
@@ -761,14 +760,13 @@ __global__ void __launch_bounds__(SPARSE_BLOCK, LBM2P_MAIN_MINB) k2p_main_sparse
     __syncthreads();
     if (threadIdx.x == 0) table_fetch(a, blk, s_tab, &s_bar);
     const uint32_t i = blk * SPARSE_BLOCK + threadIdx.x;
-    mbar_wait(&s_bar, 0);
+    table_wait(a, blk, s_tab, &s_bar);
     if (i < a.first || i >= a.first + a.count) return;
     const uint32_t fl = s_tab.fl[threadIdx.x];
     const bool exc = fl & FL_EXCEPTION;
     int32_t rb[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) rb[k] = s_tab.blk[k] + (int32_t)s_tab.rb[k][threadIdx.x];
-    const uint32_t slot = (uint32_t)s_tab.blk[8] + s_tab.rb[0][threadIdx.x];
+    table_ranks(s_tab, i, rb);
+    const uint32_t slot = table_exc_slot(s_tab);
     const bool need_lin = MODE != MODE_STEP || a.has_bc;
     const uint32_t lin = need_lin ? a.lin[i] : 0u;
     float f[19];

@@ -28,7 +28,7 @@ struct Step2Args {
     int bc_psi_type[6];       // :34-39
     float bc_psi_val[6];
     // sparse storage (lbm_solver_3d_2phase_sparse.py): compact fluid list + the single-phase pull
-    // table (a.flags, a.rb16, a.blk, a.exc, a.lin, a.first, a.count); records, rho_r, rho_b, psi
+    // table (a.flags, a.rb8, a.blk, a.exc, a.lin, a.first, a.count); records, rho_r, rho_b, psi
     // are then indexed by stored node and a solid neighbour of the psi stencil reads psi_solid
     int sparse;
     // dense colour pass: 1 = every node gathers its 19 records (lattices where few nodes are BULK),

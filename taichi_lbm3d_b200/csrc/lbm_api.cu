@@ -40,6 +40,7 @@ struct lbm_ctx {
     float S[19]{};
     float force[3] = {0.f, 0.f, 0.f};
     int guo_unscaled = 0;
+    int vel_bc_script = 0;
     Face face[6];
     float invM[361]{};
     bool have_geometry = false;
@@ -61,7 +62,8 @@ struct lbm_ctx {
     int8_t *d_solid = nullptr;
     uint32_t *d_flags = nullptr;   // dense: [N] link words; sparse: [nf] BC words
     int32_t *d_nbr = nullptr;      // sparse, full table: [18][stride]
-    uint16_t *d_rb16 = nullptr;    // sparse, compressed table: [8][stride] neighbour-row ranks - block base
+    uint8_t *d_rb8 = nullptr;      // sparse, compressed table: [8][stride] 8-bit offsets of rank - index; exception slots
+    size_t n_wide = 0;             // table blocks turned into exceptions
     int32_t *d_blk = nullptr;      // sparse, compressed table: [stride/256][16] rank bases + exception-slot base
     int32_t *d_exc = nullptr;      // sparse, compressed table: [18][exc_stride] explicit sources
     size_t n_exc = 0, exc_stride = 0;
@@ -134,8 +136,8 @@ __global__ void k_decode_table(StepArgs a, uint32_t nf, int32_t *__restrict__ ou
     const uint32_t fl = a.flags[i];
     const int32_t *blk = a.blk + (size_t)(i / 256u) * 16;
     int32_t rb[8];
-    for (int k = 0; k < 8; ++k) rb[k] = blk[k] + (int32_t)a.rb16[k][i];
-    const uint32_t slot = (uint32_t)blk[8] + a.rb16[0][i];
+    for (int k = 0; k < 8; ++k) rb[k] = blk[k] + (int32_t)i + (int32_t)a.rb8[k][i];
+    const uint32_t slot = (uint32_t)blk[8] + a.rb8[0][i];
 #define X(s, ex, ey, ez, o)                                                                    \
     if (s > 0) {                                                                               \
         int32_t j = -1;                                                                        \
@@ -145,6 +147,15 @@ __global__ void k_decode_table(StepArgs a, uint32_t nf, int32_t *__restrict__ ou
     }
     D3Q19_DIRS(X)
 #undef X
+}
+
+// lbm_get_nodes: rows of a [N][width] array at selected nodes
+__global__ void k_take_rows(const float *__restrict__ src, const int64_t *__restrict__ index, int64_t n, int width,
+                            float *__restrict__ dst) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * width) return;
+    const int64_t i = t / width;
+    dst[t] = src[index[i] * width + (t - i * width)];
 }
 
 // user force array [N][3] (reference layout) -> three planes in stored order
@@ -169,8 +180,8 @@ void default_relaxation(double niu, int textbook, float S[19]) {
 void free_device(lbm_ctx *c) {
     cudaFree(c->d_solid); cudaFree(c->d_flags); cudaFree(c->d_nbr); cudaFree(c->d_lin);
     cudaFree(c->d_rank); cudaFree(c->d_fbase[0]); cudaFree(c->d_fbase[1]); cudaFree(c->d_rho);
-    cudaFree(c->d_rb16); cudaFree(c->d_blk); cudaFree(c->d_exc);
-    c->d_rb16 = nullptr; c->d_blk = nullptr; c->d_exc = nullptr;
+    cudaFree(c->d_rb8); cudaFree(c->d_blk); cudaFree(c->d_exc);
+    c->d_rb8 = nullptr; c->d_blk = nullptr; c->d_exc = nullptr;
     cudaFree(c->d_cls); c->d_cls = nullptr; c->d_fbase[0] = c->d_fbase[1] = nullptr;
     cudaFree(c->d_v); cudaFree(c->d_F); cudaFree(c->d_vbc); cudaFree(c->d_scalar);
     cudaFree(c->d_ff); c->d_ff = nullptr;
@@ -199,7 +210,7 @@ void fill_args(const lbm_ctx *c, StepArgs &a) {
         a.nbr[s] = c->d_nbr ? c->d_nbr + (size_t)s * c->stride : nullptr;
         a.exc[s] = c->d_exc ? c->d_exc + (size_t)s * c->exc_stride : nullptr;
     }
-    for (int k = 0; k < 8; ++k) a.rb16[k] = c->d_rb16 ? c->d_rb16 + (size_t)k * c->stride : nullptr;
+    for (int k = 0; k < 8; ++k) a.rb8[k] = c->d_rb8 ? c->d_rb8 + (size_t)k * c->stride : nullptr;
     a.blk = c->d_blk;
     a.compressed = c->cfg.sparse ? c->compressed : 0;
     a.prefetch_dist = c->prefetch_dist;
@@ -231,6 +242,7 @@ void fill_args(const lbm_ctx *c, StepArgs &a) {
         a.P.gc[3] = (float)(2.0 * gb / 9.0);
         a.P.gc[4] = (float)(gb / 9.0);
     }
+    a.P.vel_bc_script = c->vel_bc_script;
     for (int i = 0; i < 6; ++i) {
         a.P.bc_type[i] = c->face[i].type;
         a.P.bc_rho[i] = c->face[i].rho;
@@ -560,6 +572,13 @@ int lbm_set_guo_form(lbm_ctx *ctx, int unscaled) {
     return LBM_OK;
 }
 
+int lbm_set_vel_bc_form(lbm_ctx *ctx, int script_form) {
+    CTX_CHECK(ctx);
+    if (ctx->inited) FAIL(ctx, LBM_ERR_STATE, "the form of the velocity faces is fixed at lbm_init");
+    ctx->vel_bc_script = script_form ? 1 : 0;
+    return LBM_OK;
+}
+
 int lbm_set_force_field(lbm_ctx *c, const float *force3) {
     CTX_CHECK(c);
     if (!c->inited) FAIL(c, LBM_ERR_STATE, "the force array is set after lbm_init (it is stored in node order)");
@@ -665,6 +684,7 @@ int lbm_init(lbm_ctx *c) {
     g.xface0 = c->xface0; g.xface1 = c->xface1;
     for (int i = 0; i < 6; ++i) g.bc_type[i] = c->face[i].type;
     g.two_phase = 0;
+    g.vel_in_place = c->vel_bc_script;
     for (int i = 0; i < 6; ++i) g.bc_psi_type[i] = 0;
 
     CU(c, cudaMalloc(&c->d_scalar, 16));
@@ -740,7 +760,11 @@ int lbm_init(lbm_ctx *c) {
         // the context owns the tables from here on
         c->nf = t.nf; c->stride = t.stride; c->n_exc = t.n_exc; c->exc_stride = t.exc_stride;
         c->d_rank = t.d_rank; c->d_lin = t.d_lin; c->d_flags = t.d_flags; c->d_nbr = t.d_nbr;
-        c->d_rb16 = t.d_rb16; c->d_blk = t.d_blk; c->d_exc = t.d_exc;
+        c->d_rb8 = t.d_rb8; c->d_blk = t.d_blk; c->d_exc = t.d_exc;
+        c->n_wide = t.n_wide;
+        if (getenv("LBM3D_DEBUG"))
+            fprintf(stderr, "[lbm3d] sparse table: %zu nodes, %zu blocks, %zu of them all-exception, %zu exception nodes\n",
+                    t.nf, t.stride / 256, t.n_wide, t.n_exc);
         c->plane_rank = t.plane_rank;
         c->own_first = t.own_first; c->own_count = t.own_count;
         for (int i = 0; i < 4; ++i) { c->plane_first[i] = t.plane_first[i]; c->plane_count[i] = t.plane_count[i]; }
@@ -900,6 +924,38 @@ int lbm_get_max_v(lbm_ctx *c, float *out) {
     if (r) return r;
     CU(c, max_v_reduce(c->d_v, c->N, c->d_scalar, c->stream, out));
     c->launches++;
+    return LBM_OK;
+}
+
+int lbm_get_nodes(lbm_ctx *c, int64_t n, const int64_t *index, float *F_out, float *rho_out, float *v_out) {
+    CTX_CHECK(c);
+    if (n < 0 || (n > 0 && !index)) FAIL(c, LBM_ERR_INVALID, "bad node list");
+    int r = sync_fields(c, F_out != nullptr);
+    if (r) return r;
+    if (n == 0) return LBM_OK;
+    CU(c, cudaStreamSynchronize(c->stream));
+    std::vector<int64_t> host(n);
+    CU(c, cudaMemcpy(host.data(), index, n * sizeof(int64_t), cudaMemcpyDefault));
+    for (int64_t i = 0; i < n; ++i)
+        if (host[i] < 0 || (size_t)host[i] >= c->N) FAIL(c, LBM_ERR_INVALID, "node index %lld outside the lattice", (long long)host[i]);
+    int64_t *d_index = nullptr;
+    float *d_tmp = nullptr;
+    CU(c, cudaMalloc(&d_index, n * sizeof(int64_t)));
+    cudaError_t e = cudaMemcpy(d_index, host.data(), n * sizeof(int64_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&d_tmp, (size_t)n * 19 * sizeof(float));
+    const float *src[3] = {c->d_F, c->d_rho, c->d_v};
+    float *dst[3] = {F_out, rho_out, v_out};
+    const int width[3] = {19, 1, 3};
+    for (int k = 0; k < 3 && e == cudaSuccess; ++k) {
+        if (!dst[k]) continue;
+        k_take_rows<<<nblocks((size_t)n * width[k], 256), 256>>>(src[k], d_index, n, width[k], d_tmp);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpy(dst[k], d_tmp, (size_t)n * width[k] * sizeof(float), cudaMemcpyDefault);
+        c->launches++;
+    }
+    cudaFree(d_index);
+    cudaFree(d_tmp);
+    CU(c, e);
     return LBM_OK;
 }
 

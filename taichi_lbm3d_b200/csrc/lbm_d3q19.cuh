@@ -47,6 +47,10 @@ struct LbmParams {
     // production arithmetic: moment 0, 1, (3,5,7), (9,11), (13,14,15).
     int guo_unscaled;
     float gc[5];
+    // form of a fixed-velocity face: 0 = the class, F = feq(1, u) for all 19 populations (:288);
+    // 1 = the script copies (Single_phase/lbm_solver_3d.py:253), in place for s = 0..18:
+    //     F[s] = feq(LR[s], 1, u) - F[LR[s]] + feq(s, 1, u)
+    int vel_bc_script;
     int bc_type[6];       // x0,x1,y0,y1,z0,z1
     float bc_rho[6];
     float bc_vel[6][3];

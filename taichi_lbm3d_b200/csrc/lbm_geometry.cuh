@@ -18,6 +18,8 @@ struct GeoParams {
     int xface0, xface1;
     int bc_type[6];
     int two_phase;          // also flag nodes whose phase-field stencil touches a solid
+    int vel_in_place;       // velocity faces use the scripts' in-place form (not an overwrite): the BC
+                            // word records the last PRESSURE face, velocity faces go by the at-face bits
     int bc_psi_type[6];     // two-phase: 0 periodic / 1 constant psi per face (clamped stencil)
 };
 
@@ -50,7 +52,7 @@ __device__ __forceinline__ uint32_t bc_word(const GeoParams &g, const int8_t *so
     // the current F, so the word records the last PRESSURE face and the kernel then applies
     // the later velocity faces in order from the at-face bits.
     int win = -1;
-    const bool only_p = g.two_phase != 0;
+    const bool only_p = g.two_phase != 0 || g.vel_in_place != 0;
 #define BC_MATCH(f) (g.bc_type[f] && (!only_p || g.bc_type[f] == 1))
     if (BC_MATCH(0) && x == g.xface0) win = 0;
     if (BC_MATCH(1) && x == g.xface1) win = 1;
@@ -86,7 +88,7 @@ __device__ __forceinline__ uint32_t at_face_bits(const GeoParams &g, int x, int 
     if (!g.halo_x) {
         if (x == 0) fl |= FL_AT_X0;
         if (x == g.nx - 1) fl |= FL_AT_X1;
-    } else if (g.two_phase) {
+    } else if (g.two_phase || g.vel_in_place) {
         if (x == g.xface0) fl |= FL_AT_X0;
         if (x == g.xface1) fl |= FL_AT_X1;
     }

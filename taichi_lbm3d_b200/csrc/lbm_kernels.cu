@@ -51,32 +51,56 @@ __device__ __forceinline__ void macro_force(const StepArgs &a, uint32_t node, fl
     for (int k = 0; k < 3; ++k) frc[k] = FORCE == 3 ? __ldg(a.ffm[k] + node) : (FORCE == 2 ? __ldg(a.ff[k] + node) : a.P.force[k]);
 }
 
+// Boundary_condition :272-370 on the streamed populations of a node that sits on a face with a BC.
+// The link word names the face that decides (the last one in the order x0,x1,y0,y1,z0,z1: both forms
+// of the class overwrite all 19 populations).  With the script copies' velocity form, which reads
+// the current F and so is no overwrite, the word names the last PRESSURE face and every velocity
+// face after it is applied in order, found through the at-face bits.  Returns true for a pressure
+// node: its velocity of this step goes to vbc[slot] for the next one (:279-281).
+__device__ __forceinline__ bool face_bcs(float (&f)[19], const StepArgs &a, uint32_t fl, uint32_t lin, uint32_t &slot) {
+    bool pressure = false;
+    const uint32_t bc = (fl >> FL_BC_SHIFT) & FL_BC_MASK;
+    int after = 0;
+    if (bc) {
+        const int face = (int)bc - 1;
+        const int type = a.P.bc_type[face];
+        if (type == 1) {                      // :274-281  F = feq(rho_bc, v_prev)
+            float u0 = 0.f, u1 = 0.f, u2 = 0.f;
+            slot = vbc_slot(a, face, lin);
+            if (!(fl & FL_PIN_SOLID)) {
+                u0 = a.vbc[3 * (size_t)slot + 0];
+                u1 = a.vbc[3 * (size_t)slot + 1];
+                u2 = a.vbc[3 * (size_t)slot + 2];
+            }
+            feq_all(f, a.P.bc_rho[face], u0, u1, u2);
+            pressure = true;
+        } else if (type == 2) {               // :283-288  F = feq(1, bc_vel)
+            feq_all(f, 1.0f, a.P.bc_vel[face][0], a.P.bc_vel[face][1], a.P.bc_vel[face][2]);
+        }
+        after = face + 1;
+    }
+    if (a.P.vel_bc_script) {
+        for (int face = after; face < 6; ++face) {
+            if (a.P.bc_type[face] != 2 || !(fl & (FL_AT_X0 << face))) continue;
+            // Single_phase/lbm_solver_3d.py:253  F[s] = feq(LR[s],1,u) - F[LR[s]] + feq(s,1,u), IN PLACE
+            // for s = 0..18 (a later s reads the F[LR[s]] an earlier one has already replaced)
+            const float u0 = a.P.bc_vel[face][0], u1 = a.P.bc_vel[face][1], u2 = a.P.bc_vel[face][2];
+#define X(s, ex, ey, ez, o)                                                                    \
+    f[s] = feq<o, -(ex), -(ey), -(ez)>(1.0f, u0, u1, u2) - f[o] + feq<s, ex, ey, ez>(1.0f, u0, u1, u2);
+            D3Q19_DIRS(X)
+#undef X
+        }
+    }
+    return pressure;
+}
+
 template <int FORCE, int MODE>
 __device__ __forceinline__ void node_update(float (&f)[19], const StepArgs &a, uint32_t fl,
                                             uint32_t lin, uint32_t node, float &rho, float &ux, float &uy,
                                             float &uz) {
     uint32_t slot = 0;
     bool pressure = false;
-    if (a.has_bc) {
-        const uint32_t bc = (fl >> FL_BC_SHIFT) & FL_BC_MASK;
-        if (bc) {
-            const int face = (int)bc - 1;
-            const int type = a.P.bc_type[face];
-            if (type == 1) {                      // :274-281  F = feq(rho_bc, v_prev)
-                float u0 = 0.f, u1 = 0.f, u2 = 0.f;
-                slot = vbc_slot(a, face, lin);
-                if (!(fl & FL_PIN_SOLID)) {
-                    u0 = a.vbc[3 * (size_t)slot + 0];
-                    u1 = a.vbc[3 * (size_t)slot + 1];
-                    u2 = a.vbc[3 * (size_t)slot + 2];
-                }
-                feq_all(f, a.P.bc_rho[face], u0, u1, u2);
-                pressure = true;
-            } else if (type == 2) {               // :283-288  F = feq(1, bc_vel)
-                feq_all(f, 1.0f, a.P.bc_vel[face][0], a.P.bc_vel[face][1], a.P.bc_vel[face][2]);
-            }
-        }
-    }
+    if (a.has_bc) pressure = face_bcs(f, a, fl, lin, slot);
     float frc[3];
     macro_force<FORCE>(a, node, frc);
     macro(f, frc, FORCE != 0, rho, ux, uy, uz);
@@ -179,10 +203,12 @@ __global__ void __launch_bounds__(256) k_dense(const StepArgs a) {
         uint32_t slot = 0;
         if (cls == NODE_SPECIAL) {
             const uint32_t fl = a.flags[idx];
+            // with ghost planes (x-slab) x never wraps; the x bits then mark the GLOBAL faces (BCs)
+            const uint32_t flw = a.halo_x ? fl & ~(FL_AT_X0 | FL_AT_X1) : fl;
             const int sx = a.ny * (int)a.prow, sy = (int)a.prow;
             // offsets to the x-1 / x+1 ... neighbours with the periodic wrap of :247-257
-            const int oxm = (fl & FL_AT_X0) ? (a.nx - 1) * sx : -sx;
-            const int oxp = (fl & FL_AT_X1) ? -(a.nx - 1) * sx : sx;
+            const int oxm = (flw & FL_AT_X0) ? (a.nx - 1) * sx : -sx;
+            const int oxp = (flw & FL_AT_X1) ? -(a.nx - 1) * sx : sx;
             const int oym = (fl & FL_AT_Y0) ? (a.ny - 1) * sy : -sy;
             const int oyp = (fl & FL_AT_Y1) ? -(a.ny - 1) * sy : sy;
             const int ozm = (fl & FL_AT_Z0) ? (a.nz - 1) : -1;
@@ -194,7 +220,7 @@ __global__ void __launch_bounds__(256) k_dense(const StepArgs a) {
     ((ex > 0 ? oxm : (ex < 0 ? oxp : 0)) + (ey > 0 ? oym : (ey < 0 ? oyp : 0)) +               \
      (ez > 0 ? ozm : (ez < 0 ? ozp : 0)))
 #define WRAPS(ex, ey, ez)                                                                      \
-    (fl & ((ex > 0 ? FL_AT_X0 : (ex < 0 ? FL_AT_X1 : 0u)) | (ey > 0 ? FL_AT_Y0 : (ey < 0 ? FL_AT_Y1 : 0u)) | \
+    (flw & ((ex > 0 ? FL_AT_X0 : (ex < 0 ? FL_AT_X1 : 0u)) | (ey > 0 ? FL_AT_Y0 : (ey < 0 ? FL_AT_Y1 : 0u)) | \
            (ez > 0 ? FL_AT_Z0 : (ez < 0 ? FL_AT_Z1 : 0u))))
 #define X(s, ex, ey, ez, o)                                                                    \
     if (s > 0) {                                                                               \
@@ -205,26 +231,7 @@ __global__ void __launch_bounds__(256) k_dense(const StepArgs a) {
 #undef X
 #undef WRAPS
 #undef OFF
-            if (a.has_bc) {
-                const uint32_t bc = (fl >> FL_BC_SHIFT) & FL_BC_MASK;
-                if (bc) {
-                    const int face = (int)bc - 1;
-                    const int type = a.P.bc_type[face];
-                    if (type == 1) {                  // :274-281  F = feq(rho_bc, v_prev)
-                        float u0 = 0.f, u1 = 0.f, u2 = 0.f;
-                        slot = vbc_slot(a, face, idx);
-                        if (!(fl & FL_PIN_SOLID)) {
-                            u0 = a.vbc[3 * (size_t)slot + 0];
-                            u1 = a.vbc[3 * (size_t)slot + 1];
-                            u2 = a.vbc[3 * (size_t)slot + 2];
-                        }
-                        feq_all(f, a.P.bc_rho[face], u0, u1, u2);
-                        pressure = true;
-                    } else if (type == 2) {           // :283-288  F = feq(1, bc_vel)
-                        feq_all(f, 1.0f, a.P.bc_vel[face][0], a.P.bc_vel[face][1], a.P.bc_vel[face][2]);
-                    }
-                }
-            }
+            if (a.has_bc) pressure = face_bcs(f, a, fl, idx, slot);
         }
         // one copy of the arithmetic for every fluid lane of the warp
         if (compute) {
@@ -305,26 +312,7 @@ __global__ void __launch_bounds__(256) k_dense_aa(const StepArgs a) {
             D3Q19_DIRS(X)
 #undef X
         }
-        if (a.has_bc) {
-            const uint32_t bc = (fl >> FL_BC_SHIFT) & FL_BC_MASK;
-            if (bc) {
-                const int face = (int)bc - 1;
-                const int type = a.P.bc_type[face];
-                if (type == 1) {                  // :274-281  F = feq(rho_bc, v_prev)
-                    float u0 = 0.f, u1 = 0.f, u2 = 0.f;
-                    slot = vbc_slot(a, face, idx);
-                    if (!(fl & FL_PIN_SOLID)) {
-                        u0 = a.vbc[3 * (size_t)slot + 0];
-                        u1 = a.vbc[3 * (size_t)slot + 1];
-                        u2 = a.vbc[3 * (size_t)slot + 2];
-                    }
-                    feq_all(f, a.P.bc_rho[face], u0, u1, u2);
-                    pressure = true;
-                } else if (type == 2) {           // :283-288  F = feq(1, bc_vel)
-                    feq_all(f, 1.0f, a.P.bc_vel[face][0], a.P.bc_vel[face][1], a.P.bc_vel[face][2]);
-                }
-            }
-        }
+        if (a.has_bc) pressure = face_bcs(f, a, fl, idx, slot);
     }
     float rho, ux, uy, uz;
     float frc[3];
@@ -378,8 +366,8 @@ __global__ void __launch_bounds__(256) k_dense_aa(const StepArgs a) {
 // one stored node: pull (through the table slice in shared memory once `bar` flips to
 // `parity`), BC, macro, collide, store
 template <int FORCE, int MODE, bool COMP, int AA>
-__device__ __forceinline__ void sparse_node(const StepArgs &a, const SparseTable &s_tab, uint64_t *s_bar,
-                                            uint32_t parity, uint32_t i, uint32_t first, uint32_t count) {
+__device__ __forceinline__ void sparse_node(const StepArgs &a, SparseTable &s_tab, uint64_t *s_bar,
+                                            uint32_t blk, uint32_t i, uint32_t first, uint32_t count) {
     const bool active = i >= first && i < first + count;
     float f[19];
     uint32_t fl = 0;
@@ -400,19 +388,18 @@ __device__ __forceinline__ void sparse_node(const StepArgs &a, const SparseTable
             D3Q19_DIRS(X)
 #undef X
         } else if (COMP) {
-            mbar_wait(s_bar, parity);
+            table_wait(a, blk, s_tab, s_bar);
             if (!active) return;
             fl = s_tab.fl[threadIdx.x];
             if (!(fl & FL_EXCEPTION)) {
                 int32_t rb[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) rb[k] = s_tab.blk[k] + (int32_t)s_tab.rb[k][threadIdx.x];
+                table_ranks(s_tab, i, rb);
 #define X(s, ex, ey, ez, o)                                                                    \
     if (s > 0) f[s] = ldg_gather(a.pown[s] + (((fl >> s) & 1u) ? ((o) > (s) ? ip : im) : comp_source<ex, ey, ez>(i, fl, rb)));
                 D3Q19_DIRS(X)
 #undef X
             } else {
-                const uint32_t slot = (uint32_t)s_tab.blk[8] + s_tab.rb[0][threadIdx.x];
+                const uint32_t slot = table_exc_slot(s_tab);
 #define X(s, ex, ey, ez, o)                                                                    \
     if (s > 0) f[s] = __ldg(a.pown[s] + (((fl >> s) & 1u) ? ((o) > (s) ? ip : im) : __ldg(a.exc[s > 0 ? s - 1 : 0] + slot)));
                 D3Q19_DIRS(X)
@@ -447,14 +434,13 @@ __device__ __forceinline__ void sparse_node(const StepArgs &a, const SparseTable
         a.pout[0][i] = f[0];
         if (!(fl & FL_EXCEPTION)) {
             int32_t rb[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) rb[k] = s_tab.blk[k] + (int32_t)s_tab.rb[k][threadIdx.x];
+            table_ranks(s_tab, i, rb);
 #define X(s, ex, ey, ez, o)                                                                    \
     if (s > 0) a.pout[s][((fl >> s) & 1u) ? ((o) > (s) ? ip : im) : comp_source<ex, ey, ez>(i, fl, rb)] = f[o];
             D3Q19_DIRS(X)
 #undef X
         } else {
-            const uint32_t slot = (uint32_t)s_tab.blk[8] + s_tab.rb[0][threadIdx.x];
+            const uint32_t slot = table_exc_slot(s_tab);
 #define X(s, ex, ey, ez, o)                                                                    \
     if (s > 0) a.pout[s][((fl >> s) & 1u) ? ((o) > (s) ? ip : im) : __ldg(a.exc[s > 0 ? s - 1 : 0] + slot)] = f[o];
             D3Q19_DIRS(X)
@@ -492,13 +478,13 @@ k_sparse(const StepArgs a) {
                 if (pb + SPARSE_BLOCK <= first + count) {
 #pragma unroll
                     for (int k = 0; k < 8; ++k)
-                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.rb16[k] + pb), "r"(SPARSE_BLOCK * 2u) : "memory");
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.rb8[k] + pb), "r"(SPARSE_BLOCK * 1u) : "memory");
                     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.flags + pb), "r"(SPARSE_BLOCK * 4u) : "memory");
                 }
             }
         }
     }
-    sparse_node<FORCE, MODE, COMP, AA>(a, s_tab, &s_bar, 0u, blk * SPARSE_BLOCK + threadIdx.x, first, count);
+    sparse_node<FORCE, MODE, COMP, AA>(a, s_tab, &s_bar, blk, blk * SPARSE_BLOCK + threadIdx.x, first, count);
 }
 
 template <int FORCE, int MODE>

@@ -65,14 +65,17 @@ struct StepArgs {
     // 20..23 BC, 31 exception) + rb[k][i] = fluid rank of the position (x-ex, y-ey, z) in the
     // k-th neighbour z-row, k over (ex,ey) = (1,0),(-1,0),(0,1),(0,-1),(1,1),(-1,-1),(1,-1),(-1,1).
     // The list is sorted with z fastest, so the three sources (z-1, z, z+1) of a neighbour row
-    // are rb-1, rb, rb+fluid(center).  The ranks are stored as 16-bit offsets from a per-block
-    // base: rb[k][i] = blk[B][k] + rb16[k][i], B = i / 256 (the ranks of 256 consecutive nodes
-    // span little more than 256): 8 x 2 B + 4 B = 20 B per node instead of 18 x 4 = 72 B.
-    // Nodes for which the rank rule fails (periodic z wrap), and all nodes of a block whose
-    // ranks span more than 16 bits (periodic x / y wrap inside the block), carry FL_EXCEPTION and
-    // keep their 18 sources in exc[s-1][slot], slot = blk[B][8] + rb16[0][i].
-    const uint16_t *rb16[8];
-    const int32_t *blk;             // [n_blocks][16]: 8 rank bases, exception-slot base, padding
+    // are rb-1, rb, rb+fluid(center).  What is stored is how far that rank runs ahead of the node's
+    // own index, rb[k][i] - i, as an 8-bit offset from its minimum over the 256-node block:
+    //     rb[k][i] = blk[B][k] + i + rb8[k][i],  B = i / 256
+    // (neighbouring z-rows fill at nearly the same rate, so over a block the lead changes by a few
+    // tens): 8 x 1 B + 4 B = 12 B per node instead of 18 x 4 = 72 B.
+    // Nodes for which the rank rule fails (periodic z wrap), and all nodes of a block in which a
+    // lead varies by more than 255 (a periodic x / y wrap inside the block; < 1 % of the blocks of
+    // a 512^3 sphere pack), carry FL_EXCEPTION and keep their 18 sources in exc[s-1][slot],
+    // slot = blk[B][8] + rb8[0][i].
+    const uint8_t *rb8[8];
+    const int32_t *blk;             // [n_blocks][16]: 8 lead bases, exception-slot base, padding
     const int32_t *exc[18];
     int compressed;
     uint32_t prefetch_dist;         // nodes ahead whose table lines are pulled into L2 (0 = off)

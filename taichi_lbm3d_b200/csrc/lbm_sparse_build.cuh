@@ -1,6 +1,6 @@
 // Host-side construction of the sparse storage: compacted fluid-node list (ascending linear
 // index, z fastest) and its compressed 18-neighbour pull table (lbm_kernels.cuh: 8 neighbour-row
-// ranks as 16-bit offsets from per-block bases + link word, exception table).  Shared by the
+// ranks as 8-bit offsets of rank - index from per-block bases + link word, exception table).  Shared by the
 // single-phase and two-phase C-ABI layers; everything is in an anonymous namespace.
 // Reference: Single_phase/LBM_3D_SinglePhase_Solver.py:36-44 (the pointer SNode tree this
 // replaces), :247-257 (periodic_index), :259-268 (the push whose pull form the table encodes).
@@ -9,6 +9,8 @@
 #include <thrust/iterator/transform_iterator.h>
 
 #include <climits>
+#include <cstdlib>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -48,6 +50,7 @@ __global__ void k_build_sparse(const GeoParams g, const int8_t *__restrict__ sol
     // two-phase: face bits (psi / velocity BCs, clamped psi stencil) and the wetting flag; the
     // single-phase word leaves bits 24..30 clear (wraps live in the table)
     if (g.two_phase) fl |= at_face_bits(g, x, y, z) | near_solid_bit(g, solid, x, y, z);
+    else if (g.vel_in_place) fl |= at_face_bits(g, x, y, z);
     if (nbr != nullptr)
         for (int s = 1; s < 19; ++s) nbr[(size_t)(s - 1) * stride + r] = j[s - 1];
     if (rb != nullptr) {
@@ -69,40 +72,42 @@ __global__ void k_build_sparse(const GeoParams g, const int8_t *__restrict__ sol
     flags[r] = fl;
 }
 
-// Pass 2, one thread block per 256-node table block: 16-bit rank offsets from the block's
-// minimum.  A block whose ranks span more than 16 bits (a periodic x / y wrap falls inside
-// it) turns all its nodes into exceptions.  Exception nodes get consecutive slots from
+// Pass 2, one thread block per 256-node table block: 8-bit offsets of rank - index from the block's
+// minimum.  A block in which one of them varies by more than 255 (a periodic x / y wrap falls inside
+// it, or the neighbouring rows fill very unevenly) turns all its nodes into exceptions.  Exception nodes get consecutive slots from
 // blk[B][8]; their index inside the block goes to rb16[0].  Nodes outside [own_first, own_end)
 // (ghost planes of a slab) are never updated and do not take part.
 __global__ void __launch_bounds__(256) k_pack_table(uint32_t own_first, uint32_t own_end, size_t stride,
                                                     const int32_t *__restrict__ rb32, uint32_t *__restrict__ flags,
-                                                    uint16_t *__restrict__ rb16, int32_t *__restrict__ blk,
-                                                    uint32_t *__restrict__ exc_count) {
-    __shared__ int s_min[8], s_max[8];
+                                                    uint8_t *__restrict__ rb8, int32_t *__restrict__ blk,
+                                                    uint32_t *__restrict__ exc_count, uint32_t *__restrict__ wide_count) {
+    __shared__ int s_dmin[8], s_dmax[8];
     __shared__ uint32_t s_warp[8], s_base;
     __shared__ int s_wide;
     const uint32_t B = blockIdx.x, t = threadIdx.x, i = B * 256u + t;
     const bool valid = i >= own_first && i < own_end;
     uint32_t fl = valid ? flags[i] : 0u;
-    if (t < 8) { s_min[t] = INT32_MAX; s_max[t] = INT32_MIN; }
+    if (t < 8) { s_dmin[t] = INT32_MAX; s_dmax[t] = INT32_MIN; }
     __syncthreads();
     int32_t v[8];
     for (int k = 0; k < 8; ++k) {
         v[k] = valid ? rb32[(size_t)k * stride + i] : 0;
-        int lo = (valid && !(fl & FL_EXCEPTION)) ? v[k] : INT32_MAX;
-        int hi = (valid && !(fl & FL_EXCEPTION)) ? v[k] : INT32_MIN;
+        const bool use = valid && !(fl & FL_EXCEPTION);
+        // rb - i: how far the neighbour row's rank runs ahead of the node's own index
+        int dlo = use ? v[k] - (int32_t)i : INT32_MAX, dhi = use ? v[k] - (int32_t)i : INT32_MIN;
         for (int o = 16; o > 0; o >>= 1) {
-            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+            dlo = min(dlo, __shfl_xor_sync(0xffffffffu, dlo, o));
+            dhi = max(dhi, __shfl_xor_sync(0xffffffffu, dhi, o));
         }
-        if ((t & 31) == 0) { atomicMin(&s_min[k], lo); atomicMax(&s_max[k], hi); }
+        if ((t & 31) == 0) { atomicMin(&s_dmin[k], dlo); atomicMax(&s_dmax[k], dhi); }
     }
     __syncthreads();
     if (t == 0) {
         int wide = 0;
         for (int k = 0; k < 8; ++k)
-            if (s_max[k] >= s_min[k] && (int64_t)s_max[k] - (int64_t)s_min[k] > 65535) wide = 1;
+            if (s_dmax[k] >= s_dmin[k] && (int64_t)s_dmax[k] - (int64_t)s_dmin[k] > 255) wide = 1;
         s_wide = wide;
+        if (wide) atomicAdd(wide_count, 1u);
     }
     __syncthreads();
     if (s_wide && valid) fl |= FL_EXCEPTION;
@@ -118,13 +123,19 @@ __global__ void __launch_bounds__(256) k_pack_table(uint32_t own_first, uint32_t
     }
     if (t == 0) s_base = total ? atomicAdd(exc_count, total) : 0u;
     __syncthreads();
-    if (t < 16) blk[(size_t)B * 16 + t] = t < 8 ? (s_max[t] >= s_min[t] && !s_wide ? s_min[t] : 0) : (t == 8 ? (int32_t)s_base : 0);
+    if (t < 16) {
+        int32_t b = 0;
+        if (t < 8) {
+            if (s_dmax[t] >= s_dmin[t] && !s_wide) b = s_dmin[t];
+        } else if (t == 8) b = (int32_t)s_base;
+        blk[(size_t)B * 16 + t] = b;
+    }
     if (i < stride) {
         for (int k = 0; k < 8; ++k) {
-            uint16_t w = 0;
-            if (exc) w = k == 0 ? (uint16_t)before : (uint16_t)0;
-            else if (valid) w = (uint16_t)(v[k] - s_min[k]);
-            rb16[(size_t)k * stride + i] = w;
+            uint8_t w8 = 0;
+            if (exc) { if (k == 0) w8 = (uint8_t)before; }           // slot inside the block, < 256
+            else if (valid) w8 = (uint8_t)(v[k] - (int32_t)i - s_dmin[k]);
+            rb8[(size_t)k * stride + i] = w8;
         }
         if (valid) flags[i] = fl;
     }
@@ -134,7 +145,7 @@ __global__ void __launch_bounds__(256) k_pack_table(uint32_t own_first, uint32_t
 __global__ void k_fill_exceptions(const GeoParams g, const int8_t *__restrict__ solid,
                                   const uint32_t *__restrict__ rank, uint32_t nf, size_t stride,
                                   const uint32_t *__restrict__ lin, const uint32_t *__restrict__ flags,
-                                  const uint16_t *__restrict__ rb16, const int32_t *__restrict__ blk,
+                                  const uint8_t *__restrict__ rb8, const int32_t *__restrict__ blk,
                                   int32_t *__restrict__ exc, size_t exc_stride) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nf || !(flags[r] & FL_EXCEPTION)) return;
@@ -144,7 +155,7 @@ __global__ void k_fill_exceptions(const GeoParams g, const int8_t *__restrict__ 
     const int y = (int)(t % g.ny), x = (int)(t / g.ny);
     int32_t j[18];
     true_sources(g, solid, rank, x, y, z, j);
-    const uint32_t slot = (uint32_t)blk[(size_t)(r / 256u) * 16 + 8] + rb16[r];
+    const uint32_t slot = (uint32_t)blk[(size_t)(r / 256u) * 16 + 8] + rb8[r];
     for (int s = 0; s < 18; ++s) exc[(size_t)s * exc_stride + slot] = j[s];
 }
 
@@ -156,7 +167,8 @@ struct SparseTables {
     uint32_t *d_lin = nullptr;     // [stride] linear index of each stored node
     uint32_t *d_flags = nullptr;   // [stride] link word
     int32_t *d_nbr = nullptr;      // full table [18][stride] (only when !compressed)
-    uint16_t *d_rb16 = nullptr;    // [8][stride]
+    uint8_t *d_rb8 = nullptr;      // [8][stride]  8-bit offsets of rank - index; exception slots in row 0
+    size_t n_wide = 0;             // table blocks turned into exceptions (a lead varies by more than 255)
     int32_t *d_blk = nullptr;      // [stride/256][16]
     int32_t *d_exc = nullptr;      // [18][exc_stride]
     std::vector<uint32_t> plane_rank;   // rank at the start of every x plane, [nx+1] (host)
@@ -165,7 +177,7 @@ struct SparseTables {
 
 inline void free_sparse_tables(SparseTables &t) {
     cudaFree(t.d_rank); cudaFree(t.d_lin); cudaFree(t.d_flags); cudaFree(t.d_nbr);
-    cudaFree(t.d_rb16); cudaFree(t.d_blk); cudaFree(t.d_exc);
+    cudaFree(t.d_rb8); cudaFree(t.d_blk); cudaFree(t.d_exc);
     t = SparseTables();
 }
 
@@ -247,17 +259,23 @@ inline cudaError_t build_sparse_tables(const GeoParams &g, const int8_t *d_solid
     }
     if (e == cudaSuccess && compressed) {
         const unsigned nblk = (unsigned)(t.stride / 256);
-        e = cudaMalloc(&t.d_rb16, t.stride * 8 * sizeof(uint16_t));
+        e = cudaMalloc(&t.d_rb8, t.stride * 8);
         if (e == cudaSuccess) e = cudaMalloc(&t.d_blk, (size_t)nblk * 16 * sizeof(int32_t));
+        uint32_t *d_narrow = nullptr;
+        if (e == cudaSuccess) e = cudaMalloc(&d_narrow, sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMemset(d_narrow, 0, sizeof(uint32_t));
         if (e == cudaSuccess) {
             k_pack_table<<<nblk, 256>>>(t.own_first, t.own_first + t.own_count, t.stride, d_rb32, t.d_flags,
-                                        t.d_rb16, t.d_blk, d_cnt);
+                                        t.d_rb8, t.d_blk, d_cnt, d_narrow);
             e = cudaGetLastError();
             t.launches++;
         }
         if (e == cudaSuccess) e = cudaDeviceSynchronize();
-        uint32_t ne = 0;
+        uint32_t ne = 0, nn = 0;
         if (e == cudaSuccess) e = cudaMemcpy(&ne, d_cnt, sizeof ne, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(&nn, d_narrow, sizeof nn, cudaMemcpyDeviceToHost);
+        cudaFree(d_narrow);
+        t.n_wide = nn;
         if (e == cudaSuccess) {
             t.n_exc = ne;
             t.exc_stride = (ne + 31) / 32 * 32 + 32;
@@ -266,7 +284,7 @@ inline cudaError_t build_sparse_tables(const GeoParams &g, const int8_t *d_solid
         if (e == cudaSuccess) e = cudaMemset(t.d_exc, 0xff, t.exc_stride * 18 * sizeof(int32_t));
         if (e == cudaSuccess && ne) {
             k_fill_exceptions<<<nblocks(t.nf, 256), 256>>>(g, d_solid, t.d_rank, nf32, t.stride, t.d_lin, t.d_flags,
-                                                           t.d_rb16, t.d_blk, t.d_exc, t.exc_stride);
+                                                           t.d_rb8, t.d_blk, t.d_exc, t.exc_stride);
             e = cudaGetLastError();
             t.launches++;
         }

@@ -56,7 +56,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 // aligned); threads outside [first, first+count) idle.
 //
 // Phase 1 (COMP): one elected thread pulls the block's slice of the pull table (8 arrays of
-// 16-bit row-rank offsets, the link words, the block's rank bases: 5.2 KB) into shared memory
+// 8-bit row-rank offsets, the link words, the block's rank bases: 3.1 KB) into shared memory
 // with TMA bulk copies on one mbarrier.  Doing this through registers instead lets ptxas sink
 // each index load to its first use and chains up to 9 DRAM round trips; through shared memory
 // it is exactly one, costs no registers, and 10 instructions per block.
@@ -65,19 +65,33 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 // (half-way bounce-back); the node INDEX is selected, so either way it is one load (and, in
 // place, one store) per direction and warp.
 struct SparseTable {
-    alignas(128) uint16_t rb[8][SPARSE_BLOCK];
+    alignas(128) uint8_t rb8[8][SPARSE_BLOCK];     // 8-bit offsets of rb - i from the block's base; exception slots in row 0
     alignas(16) uint32_t fl[SPARSE_BLOCK];
     alignas(16) int32_t blk[16];
 };
-constexpr uint32_t kTableBytes = 8u * SPARSE_BLOCK * 2u + SPARSE_BLOCK * 4u + 64u;
+constexpr uint32_t kTableBytes = 8u * SPARSE_BLOCK + SPARSE_BLOCK * 4u + 64u;
 
 // issue the bulk copies of table block `blk` into `tab`, completing on `bar`
 __device__ __forceinline__ void table_fetch(const StepArgs &a, uint32_t blk, SparseTable &tab, uint64_t *bar) {
     const uint32_t base = blk * SPARSE_BLOCK;
     mbar_expect_tx(bar, kTableBytes);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) bulk_g2s(&tab.rb[k][0], a.rb16[k] + base, SPARSE_BLOCK * 2u, bar);
+    for (int k = 0; k < 8; ++k) bulk_g2s(&tab.rb8[k][0], a.rb8[k] + base, SPARSE_BLOCK, bar);
     bulk_g2s(&tab.fl[0], a.flags + base, SPARSE_BLOCK * 4u, bar);
     bulk_g2s(&tab.blk[0], a.blk + (size_t)blk * 16, 64u, bar);
 }
 
+// every thread of the block: wait for the slice
+__device__ __forceinline__ void table_wait(const StepArgs &a, uint32_t blk, SparseTable &tab, uint64_t *bar) {
+    (void)a; (void)blk; (void)tab;
+    mbar_wait(bar, 0u);
+}
+
+// neighbour-row ranks of stored node i (thread threadIdx.x of the block that fetched `tab`)
+__device__ __forceinline__ void table_ranks(const SparseTable &tab, uint32_t i, int32_t (&rb)[8]) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) rb[k] = tab.blk[k] + (int32_t)i + (int32_t)tab.rb8[k][threadIdx.x];
+}
+__device__ __forceinline__ uint32_t table_exc_slot(const SparseTable &tab) {
+    return (uint32_t)tab.blk[8] + tab.rb8[0][threadIdx.x];
+}

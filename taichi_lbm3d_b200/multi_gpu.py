@@ -154,7 +154,7 @@ class SlabSolver:
     is initialised, otherwise runs as a single slab whose ring closes on itself."""
 
     def __init__(self, nx, ny, nz, sparse_storage=False, strict=False, tau_mode="class", overlap=True,
-                 transport="native"):
+                 transport="native", guo_mode="class", vel_bc_mode="class"):
         """transport="native": the step loop and the ncclSend/ncclRecv halo exchange run inside
         the C library (lbm_run_slab), a handful of launches per step and no Python in between;
         transport="torch": the same schedule driven from Python over torch.distributed P2P ops
@@ -171,7 +171,7 @@ class SlabSolver:
         self.nx, self.ny, self.nz = nx, ny, nz
         self.part = SlabPartition(nx, world, rank)
         self.local = _LocalSlab(self.part, ny, nz, sparse_storage=sparse_storage, strict=strict,
-                                tau_mode=tau_mode)
+                                tau_mode=tau_mode, guo_mode=guo_mode, vel_bc_mode=vel_bc_mode)
         self.overlap = bool(overlap) and self.part.own >= 3
         self._started = False
         self._comm_stream = None
@@ -189,6 +189,14 @@ class SlabSolver:
     def set_local_solid(self, local_solid_with_ghosts):
         """for domains too large to hold on every host: planes [x0-1 .. x1] of this rank"""
         self.local.solid.from_numpy(local_solid_with_ghosts)
+
+    def set_force_field(self, global_force):
+        """per-node force (nx, ny, nz, 3) of the whole domain, or None: every rank keeps its planes"""
+        if global_force is None:
+            self.local.set_force_field(None)
+            return
+        g = np.asarray(global_force, np.float32)
+        self.local.set_force_field(np.ascontiguousarray(np.take(g, self.part.local_planes(), axis=0)))
 
     def init_simulation(self):
         self.local.init_simulation()
@@ -286,20 +294,36 @@ class SlabSolver:
             m = float(t.item())
         return m
 
-    def local_field(self, name):
-        """owned planes of rho / v / F / solid on this rank, shape (own, ny, nz[, C])"""
-        return self.part.owned(getattr(self.local, name).to_numpy())
+    def local_field(self, name, out=None):
+        """owned planes of rho / v / F / solid on this rank, shape (own, ny, nz[, C]).  `out`: a
+        C-contiguous float32 buffer for the WHOLE local slab, ghost planes included, shape
+        (own + 2, ny, nz[, C]) -- e.g. pinned host memory -- whose owned part is returned as a view."""
+        return self.part.owned(getattr(self.local, name).to_numpy(out=out) if out is not None
+                               else getattr(self.local, name).to_numpy())
 
     def gather_field(self, name, dst=0):
         """the global field on rank `dst` (None elsewhere)"""
-        loc = self.local_field(name)
-        if not self.dist:
-            return loc
-        parts = [None] * self.part.world if self.part.rank == dst else None
-        self.dist.gather_object(loc, parts, dst=dst)
-        if self.part.rank != dst:
-            return None
-        return np.concatenate(parts, axis=0)
+        return _gather_planes(self, self.local_field(name), dst)
+
+
+def _gather_planes(solver, loc, dst):
+    """concatenate the owned planes of every rank on rank `dst`: one tensor gather over the process
+    group (slabs padded to the largest), no pickling of whole fields"""
+    dist, part = solver.dist, solver.part
+    if not dist:
+        return loc
+    torch = solver.torch
+    on_gpu = dist.get_backend() == "nccl"
+    most = max(part.sizes)
+    t = torch.zeros((most,) + loc.shape[1:], dtype=torch.from_numpy(loc[:0]).dtype)
+    t[:loc.shape[0]] = torch.from_numpy(np.ascontiguousarray(loc))
+    if on_gpu:
+        t = t.cuda()
+    parts = [torch.empty_like(t) for _ in range(part.world)] if part.rank == dst else None
+    dist.gather(t, parts, dst=dst)
+    if part.rank != dst:
+        return None
+    return np.concatenate([p.cpu().numpy()[:n] for p, n in zip(parts, part.sizes)], axis=0)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -480,11 +504,4 @@ class TwoPhaseSlabSolver:
         return self.part.owned(getattr(self.local, name).to_numpy())
 
     def gather_field(self, name, dst=0):
-        loc = self.local_field(name)
-        if not self.dist:
-            return loc
-        parts = [None] * self.part.world if self.part.rank == dst else None
-        self.dist.gather_object(loc, parts, dst=dst)
-        if self.part.rank != dst:
-            return None
-        return np.concatenate(parts, axis=0)
+        return _gather_planes(self, self.local_field(name), dst)

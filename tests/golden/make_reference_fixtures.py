@@ -36,6 +36,11 @@ CASES = {
     # one whole 3^3 block solid: never activated in the reference's sparse mode (reads give 0)
     "solid_block": ((6, 6, 6), 0.15, 13, [("set_bc_rho_x0", 1.0), ("set_bc_rho_x1", 0.995),
                                          ("set_force", [0.0, 1e-5, 0.0])], 2),
+    # example_porous_medium.py in small, at a horizon where round-off has had time to grow: 16^3
+    # porous block, pressure faces in x plus a transverse body force, 100 steps (20 minutes of
+    # interpreted loops for the dense and the sparse run; the fixture is committed)
+    "porous16": ((16, 16, 16), 0.2, 17, [("set_bc_rho_x0", 1.0), ("set_bc_rho_x1", 0.99),
+                                         ("set_force", [0.0, 1e-5, 0.0])], 100),
 }
 
 
@@ -149,6 +154,8 @@ CASES2P = {
         "bc_psi_y_right, psi_y_right": "1, 1.0"}, 3),
     "periodic_bubble": ((6, 6, 6), 0.0, 1, {"bc_psi_x_left, psi_x_left": "0, -1.0", "fx,fy,fz": "1e-5,0.0,0.0",
                                             "niu_l": "0.05", "niu_g": "0.2"}, 3),
+    # config 4 in small at a longer horizon: 10^3 porous block, psi = -1 slab entering from x0, 50 steps
+    "drainage10": ((10, 10, 10), 0.2, 4, {"niu_l": "0.05", "niu_g": "0.2", "fx,fy,fz": "5.0e-5,-2e-5,0.0"}, 50),
 }
 
 
@@ -208,10 +215,97 @@ def run_reference_two_phase(name, script=REF2P):
     return out
 
 
+# ---- single-phase script copy --------------------------------------------------------------------
+# Single_phase/lbm_solver_3d.py: the flat-script copy of the single-phase solver (x faces only).  It
+# differs from the class in three places: tau = 3 niu + 1/2 (:47), the Guo term without the /3, /9
+# (:175-180) and the fixed-velocity face, F[s] = feq(LR[s],1,u) - F[LR[s]] + feq(s,1,u) in place
+# (:253, :268).  Executed like the two-phase script: kernel part through the shim with only the
+# hand-edited parameter lines replaced, driver loop body (:304-308) called from here.
+REFSP_SCRIPT = "/root/reference/Single_phase/lbm_solver_3d.py"
+CASES_SCRIPT = {
+    # name -> (shape, solid fraction, seed, parameter-line overrides, steps)
+    "vel_x0_rho_x1": ((6, 5, 4), 0.2, 6, {
+        "fx,fy,fz": "1.0e-5,0.0,-2.0e-6", "niu": "0.1",
+        "bc_x_left, rho_bcxl, vx_bcxl, vy_bcxl, vz_bcxl": "2, 1.0, 0.02, 0.0, 0.005",
+        "bc_x_right, rho_bcxr, vx_bcxr, vy_bcxr, vz_bcxr": "1, 0.99, 0.0, 0.0, 0.0"}, 5),
+    "vel_both": ((5, 4, 5), 0.15, 12, {
+        "fx,fy,fz": "0.0e-6,0.0,0.0", "niu": "0.16",
+        "bc_x_left, rho_bcxl, vx_bcxl, vy_bcxl, vz_bcxl": "2, 1.0, 0.03, 0.0, 0.0",
+        "bc_x_right, rho_bcxr, vx_bcxr, vy_bcxr, vz_bcxr": "2, 1.0, 0.03, 0.01, 0.0"}, 4),
+}
+
+
+def case_script_solid(name):
+    shape, frac, seed, _, _ = CASES_SCRIPT[name]
+    return (np.random.default_rng(seed).random(shape) < frac).astype(np.int8)
+
+
+def run_reference_sp_script(name):
+    import re
+    shape, _, _, overrides, steps = CASES_SCRIPT[name]
+    src = open(REFSP_SCRIPT).read()
+    head = src[:src.index("time_init = time.time()")]
+    lines = dict(overrides)
+    lines["nx,ny,nz"] = "%d,%d,%d" % shape
+    for lhs, rhs in lines.items():
+        head, n = re.subn(r"^%s\s*=.*$" % re.escape(lhs), "%s = %s" % (lhs, rhs), head, count=1, flags=re.M)
+        assert n == 1, lhs
+    shim = os.path.join(ROOT, "tests", "taichi_shim")
+    sys.path.insert(0, shim)
+    try:
+        for m in ("taichi", "pyevtk", "pyevtk.hl"):
+            sys.modules.pop(m, None)
+        ns = {"__name__": "lbm_solver_3d"}
+        exec(compile(head, REFSP_SCRIPT, "exec"), ns)
+    finally:
+        sys.path.remove(shim)
+    for k, val in list(ns.items()):      # Python-scope floats read by kernels are embedded as f32
+        if isinstance(val, float):
+            ns[k] = np.float32(val)
+    solid = case_script_solid(name)
+    ns["solid"].from_numpy(solid.astype(np.int32))
+    ns["static_init"]()
+    ns["init"]()
+    for _ in range(steps):                  # the driver's loop body, :304-308
+        ns["colission"]()
+        ns["streaming1"]()
+        ns["Boundary_condition"]()
+        ns["streaming3"]()
+    out = {"solid": solid, "steps": steps}
+    for n in ("F", "rho", "v"):
+        out[n] = ns[n].to_numpy()
+    out["S"] = np.asarray(ns["S_dig"].to_numpy())
+    return out
+
+
+def write_script(name):
+    out = run_reference_sp_script(name)
+    np.savez_compressed(os.path.join(HERE, "ref_script_%s.npz" % name), **out)
+    print("single-phase script", name, "steps", out["steps"], "max |v|", float(np.abs(out["v"]).max()))
+
+
 def main():
+    only = [a for a in sys.argv[1:] if not a.startswith("--")]        # case names: just those
+    if only:
+        mod = load_reference()
+        for name in only:
+            if name in CASES:
+                write_single(mod, name)
+            elif name in CASES_SCRIPT:
+                write_script(name)
+            else:
+                write_two_phase(name)
+        return
     if "--two-phase-only" not in sys.argv:
         main_single()
     for name in CASES2P:
+        write_two_phase(name)
+    for name in CASES_SCRIPT:
+        write_script(name)
+
+
+def write_two_phase(name):
+    if True:
         out = run_reference_two_phase(name)
         sp = run_reference_two_phase(name, REF2P_SPARSE)
         for n in ("F", "rho", "v", "psi", "rho_r", "rho_b"):
@@ -232,6 +326,11 @@ def main_single():
         np.savez_compressed(os.path.join(HERE, "ref_sp_local_force_%s.npz" % name), **out)
         print("cal_local_force override", name, "max |v|", float(np.abs(out["v"]).max()))
     for name in CASES:
+        write_single(mod, name)
+
+
+def write_single(mod, name):
+    if True:
         out = run_reference(mod, name)
         # the same case with sparse_storage=True (pointer SNode tree of 3^3 blocks, :36-44)
         sp = run_reference(mod, name, sparse_storage=True)

@@ -169,6 +169,56 @@ def test_reference_other_copy_and_force_hook_fixtures(cuda, sparse):
             assert np.array_equal(getattr(lb, n).to_numpy()[fl], g[n][fl]), ("force hook", name, n)
 
 
+@pytest.mark.parametrize("sparse", [False, True, "aa", "daa"])
+def test_reference_script_copy_fixtures(cuda, sparse):
+    """tests/golden/ref_script_*.npz: what Single_phase/lbm_solver_3d.py -- the flat-script copy with
+    tau = 3 niu + 1/2, the un-scaled Guo term and the in-place fixed-velocity faces (:253,:268) --
+    computes through the shim; tau_mode="textbook", guo_mode="unscaled", vel_bc_mode="script"."""
+    from tests import refpin
+    for name in refpin.NAMES_SCRIPT:
+        g = refpin.fixture_script(name)
+        fl = g["solid"] == 0
+        lb = refpin.make_solver_script(name, sparse=sparse, strict=True)
+        lb.run(int(g["steps"]))
+        for n in ("F", "rho", "v"):
+            assert np.array_equal(getattr(lb, n).to_numpy()[fl], g[n][fl]), (name, n)
+        lbf = refpin.make_solver_script(name, sparse=sparse, strict=False)
+        lbf.run(int(g["steps"]))
+        assert rel_linf(lbf.F.to_numpy()[fl], g["F"][fl]) <= TOL and rel_linf(lbf.rho.to_numpy()[fl], g["rho"][fl]) <= TOL
+        assert np.abs(lbf.v.to_numpy()[fl] - g["v"][fl]).max() <= 3e-7
+
+
+@pytest.mark.parametrize("sparse", [False, True, "aa", "daa"])
+def test_script_velocity_faces_on_every_axis(cuda, sparse):
+    """the in-place velocity form next to pressure faces on all six faces (the script copy has x
+    faces only; the class API has six): a later pressure face overwrites, every velocity face after
+    the last pressure face is applied in order -- against the oracle, bit for bit, 30 steps"""
+    from oracle.cref import RefSinglePhaseC
+    solid = cases.random_porous((10, 9, 8), 0.2, 77)
+    bcs = [(0, "vel", [0.02, 0.0, 0.0]), (1, "rho", 0.98), (2, "vel", [0.0, 0.01, 0.0]), (3, "vel", [0.0, -0.01, 0.01]),
+           (4, "rho", 1.01), (5, "vel", [0.0, 0.0, 0.03])]
+    o = RefSinglePhaseC(*solid.shape, vel_bc_mode="script")
+    o.set_solid(solid)
+    from taichi_lbm3d_b200 import LB3D_Solver_Single_Phase
+    lb = LB3D_Solver_Single_Phase(*solid.shape, sparse_storage=sparse in (True, "aa"), in_place=sparse in ("aa", "daa"),
+                                  strict=True, vel_bc_mode="script")
+    lb.solid.from_numpy(solid)
+    for face, kind, val in bcs:
+        if kind == "rho":
+            o.set_bc_rho(face, val)
+            getattr(lb, cases.FACE_SETTERS_RHO[face])(val)
+        else:
+            o.set_bc_vel(face, val)
+            getattr(lb, cases.FACE_SETTERS_VEL[face])(val)
+    o.set_force([1e-5, 0.0, -1e-5])
+    lb.set_force([1e-5, 0.0, -1e-5])
+    o.init_simulation()
+    lb.init_simulation()
+    o.run(30)
+    lb.run(30)
+    _compare(lb, o, exact=True)
+
+
 def test_step_by_step_equals_run(cuda):
     """step() x n, with field reads in between, equals run(n) (state machine, :477-481)."""
     case = cases.case_mixed_bc()

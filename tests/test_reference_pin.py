@@ -79,6 +79,23 @@ def test_cal_local_force_override_is_the_force_array(name, cls):
         assert np.array_equal(getattr(o, n)[fl], g[n][fl]), n
 
 
+@pytest.mark.parametrize("name", refpin.NAMES_SCRIPT)
+@pytest.mark.parametrize("cls", [RefSinglePhase, RefSinglePhaseC])
+def test_script_copy_of_the_single_phase_solver(name, cls):
+    """Single_phase/lbm_solver_3d.py, the flat-script copy (tau = 3 niu + 1/2 :47, Guo term not
+    divided :175-180, fixed-velocity faces F[s] = feq(LR[s],1,u) - F[LR[s]] + feq(s,1,u) in place
+    :253,:268), its kernels run through the shim with only the parameter lines replaced: bit for bit
+    what tau_mode="textbook", guo_mode="unscaled", vel_bc_mode="script" compute"""
+    g = refpin.fixture_script(name)
+    o = refpin.make_oracle_script(cls, name)
+    assert np.array_equal(o.S, g["S"])
+    for _ in range(int(g["steps"])):
+        o.step()
+    fl = g["solid"] == 0
+    for n in ("F", "rho", "v"):
+        assert np.array_equal(getattr(o, n)[fl], g[n][fl]), n
+
+
 @pytest.mark.parametrize("name", refpin.NAMES)
 def test_reference_sparse_storage_semantics(name):
     """sparse_storage=True of the reference (pointer SNode tree of 3^3 blocks, :36-44, modelled by
