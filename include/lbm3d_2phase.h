@@ -30,13 +30,13 @@ typedef struct lbm2p_ctx lbm2p_ctx;
 #define LBM2P_HOLDS_X1 4   /* this slab's last owned plane is the global x1 face */
 #define LBM2P_SPARSE 8     /* compact fluid-node list + pull table instead of the full lattice: the
                               storage of 2phase/lbm_solver_3d_2phase_sparse.py (:54-75), as the
-                              single-phase sparse mode does it; not combined with LBM2P_HALO_X */
+                              single-phase sparse mode does it; combines with LBM2P_HALO_X */
 
 typedef struct {
     int32_t nx, ny, nz;   /* :17 */
     int32_t strict;       /* 1: oracle evaluation order, no FMA contraction (verification) */
     int32_t device;
-    int32_t reserved;     /* 0, LBM2P_SPARSE, or LBM2P_HALO_X | LBM2P_HOLDS_X0 | LBM2P_HOLDS_X1 */
+    int32_t reserved;     /* bit set of LBM2P_SPARSE, LBM2P_HALO_X, LBM2P_HOLDS_X0, LBM2P_HOLDS_X1 */
 } lbm2p_config;
 
 int lbm2p_create(const lbm2p_config *cfg, lbm2p_ctx **out);
@@ -80,16 +80,20 @@ int lbm2p_get_max_v(lbm2p_ctx *ctx, float *out);
 /* ---- multi-GPU x-slabs (contexts created with LBM2P_HALO_X) -------------------------------
  * The collision of a node needs psi of its 18 neighbours and the colour pass the records of its
  * 18 pull sources, so a step has TWO exchanges across every cut:
- *   stage 0 (after the main pass):   the 5 populations of f* that cross the cut + the colour
- *                                    records (rho_r, rho_b, v, q, C) of the boundary plane,
- *                                    15 floats per face node
- *   stage 1 (after the colour pass): psi of the boundary plane, 1 float per face node
+ *   stage 0 (after the main pass):   the 5 populations of f* that cross the cut + the part of
+ *                                    the colour record the collision writes (v, q and the
+ *                                    interface vector) of the boundary plane, 13 floats per node
+ *   stage 1 (after the colour pass): psi, rho_r, rho_b of the boundary plane, 3 floats per node
+ * A plane of a dense slab has ny*nz nodes, a plane of a sparse slab its fluid nodes, so the four
+ * halo planes (0 = left ghost, 1 = first owned, 2 = last owned, 3 = right ghost) differ in size:
+ * lbm2p_halo_count(plane) nodes; lbm2p_halo_floats(stage) is the largest message of that stage.
  * lbm2p_run_slab drives colour ; exchange(1) ; main ; exchange(0) with ncclSend/ncclRecv.  The
  * pack / unpack / stage entry points let another transport (torch.distributed, or several
  * emulated ranks in one process) run the same schedule:
  *   stage(0) ; exchange(0) ; repeat { stage(1) ; exchange(1) ; stage(2) ; exchange(0) }
  * side 0 = towards x-1 (packs local plane 1, fills ghost plane 0), side 1 = towards x+1. */
 int64_t lbm2p_halo_floats(lbm2p_ctx *ctx, int stage);
+int64_t lbm2p_halo_count(lbm2p_ctx *ctx, int plane);
 int lbm2p_halo_pack(lbm2p_ctx *ctx, int stage, int side, float *dst_dev, void *cuda_stream);
 int lbm2p_halo_unpack(lbm2p_ctx *ctx, int stage, int side, const float *src_dev, void *cuda_stream);
 /* stage 0: first collision of the user-visible state (returns 1 if already done), 1: colour

@@ -107,6 +107,7 @@ SIGNATURES_2P = {
     "lbm2p_set_state": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "lbm2p_get_max_v": (_I, [_VP, _FP]),
     "lbm2p_halo_floats": (_I64, [_VP, _I]),
+    "lbm2p_halo_count": (_I64, [_VP, _I]),
     "lbm2p_halo_pack": (_I, [_VP, _I, _I, _VP, _VP]),
     "lbm2p_halo_unpack": (_I, [_VP, _I, _I, _VP, _VP]),
     "lbm2p_slab_stage": (_I, [_VP, _I, _VP]),

@@ -364,7 +364,6 @@ int lbm2p_create(const lbm2p_config *cfg, lbm2p_ctx **out) {
     c->N = N;
     c->halo = (cfg->reserved & LBM2P_HALO_X) != 0;
     c->sparse = (cfg->reserved & LBM2P_SPARSE) != 0;
-    if (c->halo && c->sparse) { g2_create_error = "x-slabs of the two-phase solver use dense storage"; delete c; return -1; }
     if (c->halo && cfg->nx < 3) { g2_create_error = "an x-slab needs nx >= 3 (two ghost planes)"; delete c; return -1; }
     if (const char *b = getenv("LBM3D_BLOCK")) {
         int v = atoi(b);
@@ -656,15 +655,29 @@ int lbm2p_step(lbm2p_ctx *c, int nsteps, void *cuda_stream) {
 //   stage 1, after the colour pass: psi
 namespace {
 
+// nodes of halo plane 0 (left ghost), 1 (first owned), 2 (last owned), 3 (right ghost) and where
+// the plane starts in the node-indexed arrays (dense: node-linear; sparse: compact list)
+size_t plane_nodes(const lbm2p_ctx *c, int plane) {
+    return c->sparse ? (size_t)c->sp.plane_count[plane] : (size_t)c->cfg.ny * c->cfg.nz;
+}
+size_t plane_start(const lbm2p_ctx *c, int plane) {
+    if (c->sparse) return c->sp.plane_first[plane];
+    const int x = plane == 0 ? 0 : (plane == 1 ? 1 : (plane == 2 ? c->cfg.nx - 2 : c->cfg.nx - 1));
+    return (size_t)x * c->cfg.ny * c->cfg.nz;
+}
+size_t stage_floats(int stage, size_t nodes) {
+    return (stage == 0 ? 13 : 3) * nodes;      // f* (5) + uq (4) + recC (4)  |  psi (1) + rho_r, rho_b (2)
+}
 size_t halo_floats(const lbm2p_ctx *c, int stage) {
-    const size_t P = (size_t)c->cfg.ny * c->cfg.nz;
-    return stage == 0 ? 13 * P : 3 * P;      // f* (5) + uq (4) + recC (4)  |  psi (1) + rho_r, rho_b (2)
+    size_t most = 0;
+    for (int pl = 0; pl < 4; ++pl) most = plane_nodes(c, pl) > most ? plane_nodes(c, pl) : most;
+    return stage_floats(stage, most);
 }
 
 int pack2(lbm2p_ctx *c, int stage, int side, float *dst, cudaStream_t st) {
-    const size_t P = (size_t)c->cfg.ny * c->cfg.nz;
-    const int x = side == 0 ? 1 : c->cfg.nx - 2;               // boundary plane that is sent
-    const size_t off = (size_t)x * P;
+    const int plane = side == 0 ? 1 : 2;                       // boundary plane that is sent
+    const size_t P = plane_nodes(c, plane), off = plane_start(c, plane);
+    if (P == 0) return 0;
     if (stage == 1) {       // what the colour pass just wrote: psi and the current (rho_r, rho_b)
         CU2(c, cudaMemcpyAsync(dst, c->d_psi + off, P * sizeof(float), cudaMemcpyDeviceToDevice, st));
         CU2(c, cudaMemcpyAsync(dst + P, c->d_rrb[c->rcur] + off, P * sizeof(float2), cudaMemcpyDeviceToDevice, st));
@@ -673,7 +686,13 @@ int pack2(lbm2p_ctx *c, int stage, int side, float *dst, cudaStream_t st) {
     static const HaloDirs kR = {{1, 7, 9, 11, 13}}, kL = {{2, 8, 10, 12, 14}};
     Step2Args A;
     fill2(c, A, c->d_f[c->cur], nullptr);
-    k_halo_pack<<<nblocks(P, 256), 256, 0, st>>>(A.a, (uint32_t)(x * c->cfg.ny), 0u, (uint32_t)P, side == 0 ? kL : kR, dst);
+    if (c->sparse) {
+        A.a.nz = 0;
+        k_halo_pack<<<nblocks(P, 256), 256, 0, st>>>(A.a, 0u, (uint32_t)off, (uint32_t)P, side == 0 ? kL : kR, dst);
+    } else {
+        const int x = side == 0 ? 1 : c->cfg.nx - 2;
+        k_halo_pack<<<nblocks(P, 256), 256, 0, st>>>(A.a, (uint32_t)(x * c->cfg.ny), 0u, (uint32_t)P, side == 0 ? kL : kR, dst);
+    }
     CU2(c, cudaGetLastError());
     c->launches++;
     CU2(c, cudaMemcpyAsync(dst + 5 * P, c->d_uq + off, P * sizeof(float4), cudaMemcpyDeviceToDevice, st));
@@ -682,9 +701,9 @@ int pack2(lbm2p_ctx *c, int stage, int side, float *dst, cudaStream_t st) {
 }
 
 int unpack2(lbm2p_ctx *c, int stage, int side, const float *src, cudaStream_t st) {
-    const size_t P = (size_t)c->cfg.ny * c->cfg.nz;
-    const int x = side == 0 ? 0 : c->cfg.nx - 1;               // ghost plane that is filled
-    const size_t off = (size_t)x * P;
+    const int plane = side == 0 ? 0 : 3;                       // ghost plane that is filled
+    const size_t P = plane_nodes(c, plane), off = plane_start(c, plane);
+    if (P == 0) return 0;
     if (stage == 1) {
         CU2(c, cudaMemcpyAsync(c->d_psi + off, src, P * sizeof(float), cudaMemcpyDeviceToDevice, st));
         CU2(c, cudaMemcpyAsync(c->d_rrb[c->rcur] + off, src + P, P * sizeof(float2), cudaMemcpyDeviceToDevice, st));
@@ -694,7 +713,13 @@ int unpack2(lbm2p_ctx *c, int stage, int side, const float *src, cudaStream_t st
     Step2Args A;
     fill2(c, A, nullptr, c->d_f[c->cur]);
     // the left ghost receives what the left neighbour sent to its right (e_x = +1) and v.v.
-    k_halo_unpack<<<nblocks(P, 256), 256, 0, st>>>(A.a, (uint32_t)(x * c->cfg.ny), 0u, (uint32_t)P, side == 0 ? kR : kL, src);
+    if (c->sparse) {
+        A.a.nz = 0;
+        k_halo_unpack<<<nblocks(P, 256), 256, 0, st>>>(A.a, 0u, (uint32_t)off, (uint32_t)P, side == 0 ? kR : kL, src);
+    } else {
+        const int x = side == 0 ? 0 : c->cfg.nx - 1;
+        k_halo_unpack<<<nblocks(P, 256), 256, 0, st>>>(A.a, (uint32_t)(x * c->cfg.ny), 0u, (uint32_t)P, side == 0 ? kR : kL, src);
+    }
     CU2(c, cudaGetLastError());
     c->launches++;
     CU2(c, cudaMemcpyAsync(c->d_uq + off, src + 5 * P, P * sizeof(float4), cudaMemcpyDeviceToDevice, st));
@@ -717,13 +742,12 @@ int exchange2(lbm2p_ctx *c, int stage, cudaStream_t st) {
     if (c->comm_world > 1) {
         const int left = (c->comm_rank + c->comm_world - 1) % c->comm_world;
         const int right = (c->comm_rank + 1) % c->comm_world;
-        const size_t n = halo_floats(c, stage);
         NC2(c, g_nccl.GroupStart());
         // posting order matters when left == right (two ranks): pairs match in order
-        NC2(c, g_nccl.Send(c->d_send[1], n, 7, right, c->comm, st));
-        NC2(c, g_nccl.Send(c->d_send[0], n, 7, left, c->comm, st));
-        NC2(c, g_nccl.Recv(c->d_recv[0], n, 7, left, c->comm, st));
-        NC2(c, g_nccl.Recv(c->d_recv[1], n, 7, right, c->comm, st));
+        NC2(c, g_nccl.Send(c->d_send[1], stage_floats(stage, plane_nodes(c, 2)), 7, right, c->comm, st));
+        NC2(c, g_nccl.Send(c->d_send[0], stage_floats(stage, plane_nodes(c, 1)), 7, left, c->comm, st));
+        NC2(c, g_nccl.Recv(c->d_recv[0], stage_floats(stage, plane_nodes(c, 0)), 7, left, c->comm, st));
+        NC2(c, g_nccl.Recv(c->d_recv[1], stage_floats(stage, plane_nodes(c, 3)), 7, right, c->comm, st));
         NC2(c, g_nccl.GroupEnd());
         from_left = c->d_recv[0];
         from_right = c->d_recv[1];
@@ -771,6 +795,11 @@ int64_t lbm2p_halo_floats(lbm2p_ctx *c, int stage) {
     return (int64_t)halo_floats(c, stage);
 }
 
+int64_t lbm2p_halo_count(lbm2p_ctx *c, int plane) {
+    if (!c || !c->inited || !c->halo || plane < 0 || plane > 3) return -1;
+    return (int64_t)plane_nodes(c, plane);
+}
+
 int lbm2p_halo_pack(lbm2p_ctx *c, int stage, int side, float *dst, void *cuda_stream) {
     CTX2(c);
     if (!c->inited || !c->halo) FAIL2(c, -4, "needs an initialised x-slab context");
@@ -813,8 +842,8 @@ int lbm2p_comm_init(lbm2p_ctx *c, const void *id128, int world, int rank) {
     c->comm_world = world;
     c->comm_rank = rank;
     for (int i = 0; i < 2; ++i) {
-        if (!c->d_send[i]) CU2(c, cudaMalloc(&c->d_send[i], halo_floats(c, 0) * sizeof(float)));
-        if (!c->d_recv[i]) CU2(c, cudaMalloc(&c->d_recv[i], halo_floats(c, 0) * sizeof(float)));
+        if (!c->d_send[i]) CU2(c, cudaMalloc(&c->d_send[i], (halo_floats(c, 0) + 4) * sizeof(float)));
+        if (!c->d_recv[i]) CU2(c, cudaMalloc(&c->d_recv[i], (halo_floats(c, 0) + 4) * sizeof(float)));
     }
     if (!c->comm_stream) {
         int lo = 0, hi = 0;
@@ -842,8 +871,14 @@ static int launch_planes2(lbm2p_ctx *c, int kind, int x0, int x1, cudaStream_t s
     if (x1 <= x0) return 0;
     Step2Args A;
     fill2(c, A, c->d_f[c->cur], kind ? c->d_f[c->cur ^ 1] : nullptr);
-    A.a.row_first = (uint32_t)(x0 * c->cfg.ny);
-    A.a.row_count = (uint32_t)((x1 - x0) * c->cfg.ny);
+    if (c->sparse) {
+        A.a.first = c->sp.plane_rank[x0];
+        A.a.count = c->sp.plane_rank[x1] - A.a.first;
+        if (A.a.count == 0) return 0;
+    } else {
+        A.a.row_first = (uint32_t)(x0 * c->cfg.ny);
+        A.a.row_count = (uint32_t)((x1 - x0) * c->cfg.ny);
+    }
     return kind ? launch_main2(c, MODE_STEP, A, st) : launch_colour2(c, A, st);
 }
 

@@ -399,8 +399,41 @@ int exchange_impl(lbm_ctx *c, int which, cudaStream_t st) {
     return halo_unpack_impl(c, 1, which, from_right, st);
 }
 
+// LBM3D_TIMELINE=<file>: CUDA-event timestamps of the last steps of lbm_run_slab on both streams
+// (there is no nsys in this image): per step, when the interior kernel, the boundary kernel and the
+// pack / ncclSend+Recv / unpack of the exchange started and ended, in microseconds from the first
+// recorded event.  Timed events serialise nothing, but they are only created when asked for.
+struct Timeline {
+    struct Mark { const char *what; int step; cudaEvent_t ev; };
+    std::vector<Mark> marks;
+    bool on = false;
+    void mark(const char *what, int step, cudaStream_t st) {
+        if (!on) return;
+        cudaEvent_t ev;
+        if (cudaEventCreate(&ev) != cudaSuccess) return;
+        cudaEventRecord(ev, st);
+        marks.push_back({what, step, ev});
+    }
+    void write(const char *path, int rank) {
+        if (!on || marks.empty()) return;
+        cudaDeviceSynchronize();
+        std::string name = std::string(path) + (rank >= 0 ? ".rank" + std::to_string(rank) : "");
+        FILE *fh = fopen(name.c_str(), "w");
+        if (fh) fprintf(fh, "step,event,us_since_first\n");
+        for (auto &m : marks) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, marks[0].ev, m.ev);
+            if (fh) fprintf(fh, "%d,%s,%.1f\n", m.step, m.what, ms * 1e3f);
+        }
+        if (fh) fclose(fh);
+        for (auto &m : marks) cudaEventDestroy(m.ev);
+        marks.clear();
+    }
+};
+Timeline g_timeline;
+
 // the same exchange with one pack launch and one unpack launch for both sides (native slab loop)
-int exchange_merged(lbm_ctx *c, int which, cudaStream_t st) {
+int exchange_merged(lbm_ctx *c, int which, cudaStream_t st, int step = -1) {
     static const HaloDirs kR = {{1, 7, 9, 11, 13}}, kL = {{2, 8, 10, 12, 14}};
     float *buf = c->d_f[which ? c->cur ^ 1 : c->cur];
     StepArgs a;
@@ -415,6 +448,7 @@ int exchange_merged(lbm_ctx *c, int which, cudaStream_t st) {
         CU(c, cudaGetLastError());
         c->launches++;
     }
+    g_timeline.mark("pack_end", step, st);
     float *from_left = c->d_send[1], *from_right = c->d_send[0];   // ring of one slab
     if (c->comm_world > 1) {
         const int left = (c->comm_rank + c->comm_world - 1) % c->comm_world;
@@ -429,6 +463,7 @@ int exchange_merged(lbm_ctx *c, int which, cudaStream_t st) {
         from_left = c->d_recv[0];
         from_right = c->d_recv[1];
     }
+    g_timeline.mark("sendrecv_end", step, st);
     if (most_g) {
         set_buffers(c, a, nullptr, buf);
         // the left ghost receives what the left neighbour sent to its right (e_x = +1) and v.v.
@@ -437,6 +472,7 @@ int exchange_merged(lbm_ctx *c, int which, cudaStream_t st) {
         CU(c, cudaGetLastError());
         c->launches++;
     }
+    g_timeline.mark("unpack_end", step, st);
     return LBM_OK;
 }
 
@@ -1120,7 +1156,10 @@ int lbm_run_slab(lbm_ctx *c, int nsteps, int overlap, void *cuda_stream) {
         nsteps -= 1;
     }
     StepArgs a;
+    const char *tl_path = getenv("LBM3D_TIMELINE");
+    const int tl_first = nsteps > 4 ? nsteps - 4 : 0;          // the last four steps of this call
     for (int it = 0; it < nsteps; ++it) {
+        g_timeline.on = tl_path != nullptr && overlap && it >= tl_first;
         if (!overlap) {
             fill_args(c, a);
             set_buffers(c, a, c->d_f[c->cur], c->d_f[c->cur ^ 1]);
@@ -1145,14 +1184,18 @@ int lbm_run_slab(lbm_ctx *c, int nsteps, int overlap, void *cuda_stream) {
             CU(c, cudaEventRecord(c->ev_boundary, st));
         }
         CU(c, cudaStreamWaitEvent(st, c->ev_boundary, 0));       // boundary(n-1)
+        g_timeline.mark("interior_begin", it, st);
         int r = lbm_step_planes(c, 2, own, st);                  // interior(n)
         if (r) return r;
+        g_timeline.mark("interior_end", it, st);
         CU(c, cudaStreamWaitEvent(c->comm_stream, c->ev_interior, 0));   // interior(n-1)
         CU(c, cudaEventRecord(c->ev_interior, st));              // interior(n)
+        g_timeline.mark("boundary_begin", it, c->comm_stream);
         r = launch_boundary_planes(c, c->comm_stream);           // boundary(n)
         if (r) return r;
+        g_timeline.mark("boundary_end", it, c->comm_stream);
         CU(c, cudaEventRecord(c->ev_boundary, c->comm_stream));
-        r = exchange_merged(c, 1, c->comm_stream);               // ghost planes of buffer cur ^ 1
+        r = exchange_merged(c, 1, c->comm_stream, it);           // ghost planes of buffer cur ^ 1
         if (r) return r;
         c->cur ^= 1;
         c->ffm_pending = false;
@@ -1160,6 +1203,11 @@ int lbm_run_slab(lbm_ctx *c, int nsteps, int overlap, void *cuda_stream) {
     if (overlap) {                                               // st continues after both streams
         CU(c, cudaEventRecord(c->ev_comm, c->comm_stream));
         CU(c, cudaStreamWaitEvent(st, c->ev_comm, 0));
+    }
+    if (tl_path) {
+        g_timeline.on = true;
+        g_timeline.write(tl_path, c->comm_world > 1 ? c->comm_rank : -1);
+        g_timeline.on = false;
     }
     c->macro_valid = false;
     c->F_valid = false;

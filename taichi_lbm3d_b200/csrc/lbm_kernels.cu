@@ -51,6 +51,20 @@ __device__ __forceinline__ void macro_force(const StepArgs &a, uint32_t node, fl
     for (int k = 0; k < 3; ++k) frc[k] = FORCE == 3 ? __ldg(a.ffm[k] + node) : (FORCE == 2 ? __ldg(a.ff[k] + node) : a.P.force[k]);
 }
 
+// The script copies' fixed-velocity faces (Single_phase/lbm_solver_3d.py:253,268), every one after
+// face `after` in order:  F[s] = feq(LR[s],1,u) - F[LR[s]] + feq(s,1,u), IN PLACE for s = 0..18 (a
+// later s reads the F[LR[s]] an earlier one has already replaced).
+__device__ __forceinline__ void script_velocity_faces(float (&f)[19], const StepArgs &a, uint32_t fl, int after) {
+    for (int face = after; face < 6; ++face) {
+        if (a.P.bc_type[face] != 2 || !(fl & (FL_AT_X0 << face))) continue;
+        const float u0 = a.P.bc_vel[face][0], u1 = a.P.bc_vel[face][1], u2 = a.P.bc_vel[face][2];
+#define X(s, ex, ey, ez, o)                                                                    \
+    f[s] = feq<o, -(ex), -(ey), -(ez)>(1.0f, u0, u1, u2) - f[o] + feq<s, ex, ey, ez>(1.0f, u0, u1, u2);
+        D3Q19_DIRS(X)
+#undef X
+    }
+}
+
 // Boundary_condition :272-370 on the streamed populations of a node that sits on a face with a BC.
 // The link word names the face that decides (the last one in the order x0,x1,y0,y1,z0,z1: both forms
 // of the class overwrite all 19 populations).  With the script copies' velocity form, which reads
@@ -79,18 +93,7 @@ __device__ __forceinline__ bool face_bcs(float (&f)[19], const StepArgs &a, uint
         }
         after = face + 1;
     }
-    if (a.P.vel_bc_script) {
-        for (int face = after; face < 6; ++face) {
-            if (a.P.bc_type[face] != 2 || !(fl & (FL_AT_X0 << face))) continue;
-            // Single_phase/lbm_solver_3d.py:253  F[s] = feq(LR[s],1,u) - F[LR[s]] + feq(s,1,u), IN PLACE
-            // for s = 0..18 (a later s reads the F[LR[s]] an earlier one has already replaced)
-            const float u0 = a.P.bc_vel[face][0], u1 = a.P.bc_vel[face][1], u2 = a.P.bc_vel[face][2];
-#define X(s, ex, ey, ez, o)                                                                    \
-    f[s] = feq<o, -(ex), -(ey), -(ez)>(1.0f, u0, u1, u2) - f[o] + feq<s, ex, ey, ez>(1.0f, u0, u1, u2);
-            D3Q19_DIRS(X)
-#undef X
-        }
-    }
+    if (a.P.vel_bc_script) script_velocity_faces(f, a, fl, after);
     return pressure;
 }
 
@@ -264,8 +267,13 @@ __global__ void __launch_bounds__(256) k_dense(const StepArgs a) {
 // every location is read and written by exactly one thread.  EVEN: everything a node needs sits
 // in its own 19 slots (F_q = slot LR[q]); natural layout again afterwards.  Solid nodes never
 // store: a sector written here was read in the same launch, so a partial write merges in L2.
+// (The ten directions with e_z != 0 store one element off the 128-byte lines -- two transactions
+// per warp store, the odd step takes 1.31 x the even one.  Handing those values to the z neighbour
+// through shared memory so that every thread stores at its own z was measured on B200 and is slower,
+// 36.2 against 39.1 GLUPS at 256^3: ten STS/LDS pairs, a block barrier and no early exit for solid
+// lanes cost more than the split stores.)
 template <int FORCE, int MODE, int AA>
-__global__ void __launch_bounds__(256) k_dense_aa(const StepArgs a) {
+__global__ void __launch_bounds__(256, 5) k_dense_aa(const StepArgs a) {
     const uint32_t z = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t r = (blockIdx.z * gridDim.y + blockIdx.y) * blockDim.y + threadIdx.y;
     if (z >= (uint32_t)a.nz || r >= a.row_count) return;

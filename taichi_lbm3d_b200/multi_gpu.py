@@ -339,7 +339,8 @@ def _two_phase_slab_class():
 
         def _config_flags(self):
             m = self._part.x_face_mask
-            return 1 | (2 if m & 1 else 0) | (4 if m & 2 else 0)       # LBM2P_HALO_X | HOLDS_X0 | HOLDS_X1
+            return 1 | (2 if m & 1 else 0) | (4 if m & 2 else 0) | (8 if self.sparse_storage else 0)
+            # LBM2P_HALO_X | HOLDS_X0 | HOLDS_X1 | LBM2P_SPARSE
 
     return _Slab
 
@@ -385,8 +386,11 @@ class _Cuda2PBackend:
         lib, ctx = slab._lib, slab._ctx
         dev = torch.device("cuda", torch.cuda.current_device())
         self.count = [int(lib.lbm2p_halo_floats(ctx, 0)), int(lib.lbm2p_halo_floats(ctx, 1))]
-        self.send = [torch.empty(self.count[0], dtype=torch.float32, device=dev) for _ in range(2)]
-        self.recv = [torch.empty(self.count[0], dtype=torch.float32, device=dev) for _ in range(2)]
+        # nodes of the four halo planes (a sparse slab's planes hold their fluid nodes only)
+        self.nodes = [int(lib.lbm2p_halo_count(ctx, pl)) for pl in range(4)]
+        self.per_node = (13, 3)
+        self.send = [torch.empty(self.count[0] + 4, dtype=torch.float32, device=dev) for _ in range(2)]
+        self.recv = [torch.empty(self.count[0] + 4, dtype=torch.float32, device=dev) for _ in range(2)]
 
     def _stream(self):
         return ctypes.c_void_p(self.torch.cuda.current_stream().cuda_stream)
@@ -395,7 +399,7 @@ class _Cuda2PBackend:
         s = self.slab
         s._ck(s._lib.lbm2p_halo_pack(s._ctx, stage, side, ctypes.c_void_p(self.send[side].data_ptr()), self._stream()),
               "lbm2p_halo_pack")
-        return self.send[side][:self.count[stage]]
+        return self.send[side][:self.per_node[stage] * self.nodes[1 if side == 0 else 2]]
 
     def unpack(self, stage, side, tensor):
         s = self.slab
@@ -403,7 +407,7 @@ class _Cuda2PBackend:
               "lbm2p_halo_unpack")
 
     def recv_buffer(self, stage, side):
-        return self.recv[side][:self.count[stage]]
+        return self.recv[side][:self.per_node[stage] * self.nodes[0 if side == 0 else 3]]
 
 
 class TwoPhaseSlabSolver:
@@ -416,7 +420,7 @@ class TwoPhaseSlabSolver:
     colour record (60 B per face node).  transport="native": ncclSend/ncclRecv inside the C
     library (lbm2p_run_slab); "torch": the same schedule over torch.distributed P2P ops."""
 
-    def __init__(self, nx, ny, nz, strict=False, transport="native"):
+    def __init__(self, nx, ny, nz, strict=False, transport="native", sparse_storage=False):
         if transport not in ("native", "torch"):
             raise ValueError("transport must be 'native' or 'torch'")
         import torch
@@ -427,7 +431,7 @@ class TwoPhaseSlabSolver:
         rank = self.dist.get_rank() if self.dist else 0
         self.nx, self.ny, self.nz = nx, ny, nz
         self.part = SlabPartition(nx, world, rank)
-        self.local = _two_phase_slab_class()(self.part, ny, nz, strict=strict)
+        self.local = _two_phase_slab_class()(self.part, ny, nz, strict=strict, sparse_storage=sparse_storage)
         self._started = False
 
     # ---- setup -------------------------------------------------------------------------------

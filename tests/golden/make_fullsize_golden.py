@@ -44,7 +44,7 @@ def fullsize_case(name):
         return cases.case_cavity(256), 1000, SP_FIELDS, (3, 128, 254), RefSinglePhaseC
     if name == "cfg3":        # 512^3 periodic sphere pack, porosity 0.20, fx = 1e-6, all faces periodic
         solid = sphere_pack(512, 512, 512, 0.80, 8.0, 16.0, seed=512, periodic=True)
-        return cases.Case("cfg3", solid, force=[1e-6, 0.0, 0.0]), 300, SP_FIELDS, (0, 200, 511), RefSinglePhaseC
+        return cases.Case("cfg3", solid, force=[1e-6, 0.0, 0.0]), 100, SP_FIELDS, (0, 200, 511), RefSinglePhaseC
     if name == "cfg4":        # 131^3 drainage, README parameters, psi = -1 entering from x0
         solid = ftb131_standin()
         psi = np.ones(solid.shape, np.float32)

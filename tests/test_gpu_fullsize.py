@@ -7,7 +7,7 @@ float64 sums over all fluid nodes, and per field the oracle's own fp32 round-off
 (|oracle32 - oracle64|, max over the fluid nodes).
 
   cfg2  256^3 lid-driven cavity, dense storage (two buffers and in place), 1000 steps
-  cfg3  512^3 periodic sphere pack, porosity 0.20, fx = 1e-6, sparse storage (A-B and in place), 300 steps
+  cfg3  512^3 periodic sphere pack, porosity 0.20, fx = 1e-6, sparse storage (A-B and in place), 100 steps
   cfg4  131^3 colour-gradient drainage, README parameters, dense and sparse storage, 1000 steps
 
 Bars.  Verification arithmetic: BIT-IDENTICAL on the sample (and on the sums where the whole field

@@ -32,22 +32,23 @@ def _configure(lb, case):
         lb.set_bc_psi(face, val)
 
 
-def _single(case, steps, strict):
-    lb = case.make_solver(strict=strict)
+def _single(case, steps, strict, sparse=False):
+    lb = case.make_solver(strict=strict, sparse=sparse)
     lb.run(steps)
     return {n: getattr(lb, n).to_numpy() for n in FIELDS}
 
 
 @pytest.mark.parametrize("make", CASES)
 @pytest.mark.parametrize("transport", ["native", "torch"])
-def test_single_slab_ring_equals_plain_solver(cuda, make, transport):
+@pytest.mark.parametrize("sparse", [False, True])
+def test_single_slab_ring_equals_plain_solver(cuda, make, transport, sparse):
     """world = 1: the ghost planes are fed by the slab's own opposite faces (periodic ring);
     x-face flow and psi BCs live on the first / last owned plane."""
     from taichi_lbm3d_b200.multi_gpu import TwoPhaseSlabSolver
     case = make()
     steps = 9
     want = _single(case, steps, True)
-    ss = TwoPhaseSlabSolver(*case.shape, strict=True, transport=transport)
+    ss = TwoPhaseSlabSolver(*case.shape, strict=True, transport=transport, sparse_storage=sparse)
     ss.set_fields(case.solid, case.psi)
     _configure(ss.local, case)
     ss.init_simulation()
@@ -62,17 +63,18 @@ def test_single_slab_ring_equals_plain_solver(cuda, make, transport):
 @pytest.mark.parametrize("make", CASES)
 @pytest.mark.parametrize("world", [2, 3])
 @pytest.mark.parametrize("strict", [True, False])
-def test_emulated_ranks_equal_plain_solver(cuda, make, world, strict):
+@pytest.mark.parametrize("sparse", [False, True])
+def test_emulated_ranks_equal_plain_solver(cuda, make, world, strict, sparse):
     import torch
     from taichi_lbm3d_b200.multi_gpu import SlabPartition, _two_phase_slab_class
     case = make()
     steps = 7
-    want = _single(case, steps, strict)
+    want = _single(case, steps, strict, sparse)       # sparse slabs against the sparse single-domain solver
     parts = [SlabPartition(case.shape[0], world, r) for r in range(world)]
     Slab = _two_phase_slab_class()
     slabs = []
     for p in parts:
-        s = Slab(p, case.shape[1], case.shape[2], strict=strict)
+        s = Slab(p, case.shape[1], case.shape[2], strict=strict, sparse_storage=sparse)
         s.solid.from_numpy(p.local_solid(case.solid))
         s.psi.from_numpy(np.ascontiguousarray(np.take(case.psi, p.local_planes(), axis=0)))
         _configure(s, case)
@@ -80,7 +82,7 @@ def test_emulated_ranks_equal_plain_solver(cuda, make, world, strict):
         slabs.append(s)
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     lib = slabs[0]._lib
-    n0 = int(lib.lbm2p_halo_floats(slabs[0]._ctx, 0))
+    n0 = max(int(lib.lbm2p_halo_floats(s._ctx, 0)) for s in slabs)      # sparse slabs: planes differ in size
 
     def exchange(stage):
         packed = []
