@@ -309,6 +309,12 @@ def make_cavity_solver(env, gnx, ny, nz, in_place=False, pinned=None):
     return lb
 
 
+def release(lb):
+    """drop a solver; a multi-GPU one collectively (peer mappings first, see SlabSolver.close)"""
+    if hasattr(lb, "close"):
+        lb.close()
+
+
 def roofline(nfl_per_gpu, steps, ms, bytes_per_update, kernel, traffic=None):
     peak, peak_src = measured_peak()
     achieved = bytes_per_update * nfl_per_gpu * steps / (ms * 1e-3) / 1e9        # GB/s per GPU
@@ -324,12 +330,15 @@ def sub_strong_1024(env, args):
     lb = make_cavity_solver(env, n, n, n, in_place=(env.world == 1))
     ms, launches, _ = env.timed(lb, steps, warm)
     max_v = lb.get_max_v()
-    del lb
+    peer = bool(getattr(lb, "peer_memory", False))
+    release(lb)
     env.torch.cuda.empty_cache()
     nfl = cavity_fluid_nodes(n, n, n)
     out = {"workload": "lid-driven cavity %d^3 (BASELINE config 5), dense storage, %s"
                        % (n, "one GPU stepped in place (AA pattern, one population buffer)" if env.world == 1
-                          else "x-slabs over %d GPUs, two buffers, 5+5 populations per cut over NCCL" % env.world),
+                          else "x-slabs over %d GPUs, two buffers, 5+5 populations per cut %s"
+                          % (env.world, "stored straight into the neighbours' ghost planes (peer memory over NVLink)"
+                             if peer else "over NCCL")),
            "scaling": "strong", "n_gpus": env.world, "fluid_nodes": nfl, "steps": steps, "warmup": warm,
            "ms_per_step": ms / steps, "mlups": nfl * steps / (ms * 1e-3) / 1e6, "gpu_launches": launches,
            "max_v": max_v,
@@ -368,7 +377,11 @@ def sub_two_phase(env, args):
     import numpy as np
     from taichi_lbm3d_b200 import LB3D_Solver_Two_Phase
     from taichi_lbm3d_b200.geometry import ftb131_standin, sphere_pack
-    steps, warm = max(3, args.steps), max(3, min(args.warmup, 10))
+    # warm-up of 200 steps: psi = rho_r - rho_b/(rho_r + rho_b) (the reference's precedence) follows the
+    # density waves in the red phase, so from a sharp initial interface the region with C != 0 -- the
+    # nodes that carry the recolouring arithmetic and the interface part of the colour record -- grows
+    # at the lattice speed; timing the first 25 steps would flatter the kernels
+    steps, warm = max(3, args.steps), 200
 
     def run(name, solid, psi, sparse, traffic_key=None):
         lb = LB3D_Solver_Two_Phase(*solid.shape, sparse_storage=sparse)
@@ -442,7 +455,9 @@ def main():
     ms, launches, clocks = env.timed(lb, args.steps, args.warmup, sample_clocks=True)
     mlups = nfl_total * args.steps / (ms * 1e-3) / 1e6
     max_v = lb.get_max_v()
-    del lb
+    halo = None if world == 1 else ("stores into the neighbours' ghost planes (CUDA IPC peer memory over NVLink)"
+                                    if getattr(lb, "peer_memory", False) else "ncclSend/ncclRecv")
+    release(lb)
     torch.cuda.empty_cache()
 
     # ---- end to end through the public API with host buffers -----------------------------------
@@ -481,7 +496,7 @@ def main():
                   % (args.steps, "" if world == 1 else " (every rank its own slab)"),
            "seconds": dt, "seconds_init": t_init, "seconds_steps": t_steps,
            "seconds_readback": dt - t_init - t_steps, "max_v": mv}
-    del lb2
+    release(lb2)
     torch.cuda.empty_cache()
 
     # ---- the other BASELINE configs under the same clock -----------------------------------------
@@ -513,7 +528,7 @@ def main():
         "vs_baseline_note": "900 MLUPS: README.md:5 of the reference, one A100, grid size unstated",
         "dtype": "f32", "data": "synthetic",
         "config": headline_config(gnx, ny, nz, n_gpus),
-        "max_v": max_v,
+        "max_v": max_v, "halo_exchange": halo,
         "roofline": roofline(nfl_total / n_gpus, args.steps, ms, B_PER_LUP, "k_dense",
                              profiled_traffic("cavity%d_dense" % n)),
         "clocks": clocks, "gpu_launches": launches, "e2e": e2e,

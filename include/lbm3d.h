@@ -184,6 +184,20 @@ int lbm_halo_unpack(lbm_ctx *ctx, int side, int which, const float *src_dev, voi
  * lbm_run_slab = nsteps x { boundary planes ; ncclSend/ncclRecv of the 5+5 face populations
  * on a side stream || interior planes ; join } when overlap != 0.  world = 1 needs no NCCL
  * (the ring closes on the slab itself). */
+/* Direct peer-memory halo (dense storage, one process per GPU on one NVLink / NVSwitch node): the
+ * boundary-plane kernel of lbm_run_slab stores the five crossing populations straight into the
+ * neighbours' ghost planes and the ranks order themselves with flags in device memory, so a step
+ * has no pack, no ncclSend/ncclRecv and no unpack.  After lbm_comm_init: every rank exports a
+ * 256-byte blob (CUDA IPC handles of its two population buffers and its flag words + its layout),
+ * the host side exchanges the blobs, every rank connects to its left and right neighbour's, and
+ * -- only when EVERY rank connected -- all enable it; otherwise all keep the NCCL exchange. */
+#define LBM_P2P_BLOB_BYTES 256
+int lbm_p2p_export(lbm_ctx *ctx, void *blob256);
+int lbm_p2p_connect(lbm_ctx *ctx, const void *left_blob256, const void *right_blob256);
+int lbm_p2p_enable(lbm_ctx *ctx, int on);
+/* unmap the neighbours' buffers; every rank calls it (then a barrier) BEFORE any rank destroys its
+ * context: exported memory must outlive its mappings */
+int lbm_p2p_disconnect(lbm_ctx *ctx);
 int lbm_comm_unique_id(void *out128);
 int lbm_comm_init(lbm_ctx *ctx, const void *id128, int world, int rank);
 int lbm_run_slab(lbm_ctx *ctx, int nsteps, int overlap, void *cuda_stream);

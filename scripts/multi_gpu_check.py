@@ -43,8 +43,9 @@ def main():
                 fl = solid == 0
                 same = np.array_equal(rho[fl], ref.rho.to_numpy()[fl]) and np.array_equal(v[fl], ref.v.to_numpy()[fl])
                 ok &= same
-                print("multi_gpu_check world=%d %-28s overlap=%d transport=%-6s bit_identical=%s max_v=%.6g (ref %.6g)"
-                      % (world, name, overlap, transport, same, mv, ref.get_max_v()), flush=True)
+                print("multi_gpu_check world=%d %-28s overlap=%d transport=%-6s peer_memory=%d bit_identical=%s max_v=%.6g (ref %.6g)"
+                      % (world, name, overlap, transport, ss.peer_memory, same, mv, ref.get_max_v()), flush=True)
+            ss.close()
             dist.barrier()
     dist.destroy_process_group()
     return 0 if ok else 1

@@ -27,6 +27,7 @@ if tl:
 lb.run(20)
 env.barrier()
 if env.rank == 0:
-    print("timeline written to %s.rank*" % tl)
+    print("timeline written to %s.rank* (peer_memory=%s)" % (tl, getattr(lb, "peer_memory", False)))
+bench.release(lb)
 if env.dist:
     dist.destroy_process_group()

@@ -71,6 +71,10 @@ SIGNATURES = {
     "lbm_halo_count": (_I64, [_VP, _I]),
     "lbm_halo_pack": (_I, [_VP, _I, _I, _VP, _VP]),
     "lbm_halo_unpack": (_I, [_VP, _I, _I, _VP, _VP]),
+    "lbm_p2p_export": (_I, [_VP, _VP]),
+    "lbm_p2p_connect": (_I, [_VP, _VP, _VP]),
+    "lbm_p2p_enable": (_I, [_VP, _I]),
+    "lbm_p2p_disconnect": (_I, [_VP]),
     "lbm_comm_unique_id": (_I, [_VP]),
     "lbm_comm_init": (_I, [_VP, _VP, _I, _I]),
     "lbm_run_slab": (_I, [_VP, _I, _I, _VP]),

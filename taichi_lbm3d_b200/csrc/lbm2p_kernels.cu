@@ -230,8 +230,8 @@ __device__ __forceinline__ void write_record(const Step2Args &A, uint32_t node, 
     A.uq[node] = make_float4(ux, uy, uz, ccn > 0.f ? -q : q);
     if (ccn > 0.f) A.recC[node] = make_float4(Cx, Cy, Cz, 1.0f / ccn);
 #else
-    A.uq[node] = make_float4(ux, uy, uz, q);
-    A.recC[node] = make_float4(Cx * inv, Cy * inv, Cz * inv, 0.f);       // inv = 0 where C = 0
+    A.uq[node] = make_float4(ux, uy, uz, inv > 0.f ? -q : q);
+    if (inv > 0.f) A.recC[node] = make_float4(Cx * inv, Cy * inv, Cz * inv, 0.f);
 #endif
 }
 
@@ -255,11 +255,12 @@ struct ColourSum {
 // un-weighted (colour_acc weights them) and spells every rounding out with intrinsics: the term is
 // evaluated on the CONSUMER's lane for nodes next to solids / faces and on the SOURCE's lane
 // otherwise, and which of the two a node takes depends on the decomposition into slabs.
-// `rc` is the interface part of the record.  Verification arithmetic: (C, 1/|C|) as the collision
-// used them, present (and loaded by the caller) only for flagged records, uq.w < 0.  Production
-// arithmetic: the unit normal C/|C| of EVERY record, zero where C = 0 -- a few steps into a run
-// psi is nowhere exactly uniform any more, so the recolouring is evaluated everywhere, without
-// flags or branches: with t = q + eu (3 + 4.5 eu) the opposite direction has to = t - 6 eu, and the
+// `rc` is the interface part of the record, present (and loaded by the caller) only for flagged
+// records, uq.w < 0, zero otherwise.  Verification arithmetic: (C, 1/|C|) as the collision used
+// them.  Production arithmetic: the unit normal C/|C|, and the recolouring evaluated for every
+// record without a branch (a zero normal makes it vanish) -- a few steps into a run psi is exactly
+// uniform only in the bulk of the blue phase, so nearly every warp would take the branch anyway:
+// with t = q + eu (3 + 4.5 eu) the opposite direction has to = t - 6 eu, and the
 // four-way min of :351-356 is min(rho_r x, rho_b y) with x, y the smaller of (t, to) for a
 // non-negative density and the larger for a negative one (rounding is monotonic, so this is the
 // min of the four rounded products, bit for bit, while t, to > 0).
@@ -285,7 +286,7 @@ __device__ __forceinline__ void colour_term(float sg, const float2 ab, const flo
         gb = gb - cs;
     }
 #else
-    const float t = __fmaf_rn(eu, __fmaf_rn(4.5f, eu, 3.0f), uq.w);
+    const float t = __fmaf_rn(eu, __fmaf_rn(4.5f, eu, 3.0f), fabsf(uq.w));
     if (S > 0) {
         const float to = __fmaf_rn(-6.0f, eu, t);
         const float lo = fminf(t, to), hi = fmaxf(t, to);
@@ -299,14 +300,10 @@ __device__ __forceinline__ void colour_term(float sg, const float2 ab, const flo
     }
 #endif
 }
-// interface part of a record (see colour_term)
+// interface part of a record (see colour_term): stored, and fetched, only where the collision saw
+// C != 0 -- the sign of the record's q says so; a predicated load, no branch
 __device__ __forceinline__ float4 load_interface(const float4 *__restrict__ pc, float qflag) {
-#ifdef LBM_STRICT
     return qflag < 0.f ? __ldg(pc) : make_float4(0.f, 0.f, 0.f, 0.f);
-#else
-    (void)qflag;
-    return __ldg(pc);
-#endif
 }
 template <int S>
 __device__ __forceinline__ void colour_acc(ColourSum &acc, float gr, float gb) {

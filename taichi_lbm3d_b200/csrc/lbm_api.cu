@@ -100,7 +100,24 @@ struct lbm_ctx {
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_boundary = nullptr, ev_comm = nullptr, ev_interior = nullptr;
     float *d_send[2] = {nullptr, nullptr}, *d_recv[2] = {nullptr, nullptr};
+    // direct peer-memory halo (lbm_p2p_*): this rank's flag words, the neighbours' mapped buffers
+    int *d_p2p = nullptr;                    // [0],[1] launches completed by the left / right neighbour, [2] blocks done, [3] timeout
+    void *peer_map[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // opened IPC handles (side; f0, f1, flags)
+    bool peer_shared = false;                // left and right neighbour are the same rank (world of two)
+    float *peer_f[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // neighbour's population buffers (pad applied)
+    int *peer_flags[2] = {nullptr, nullptr};
+    long long peer_pstride[2] = {0, 0}, peer_delta[2] = {0, 0};
+    bool p2p_ready = false, p2p_on = false;
+    int p2p_launches = 0;
 };
+
+struct P2pBlob {                             // what lbm_p2p_export writes (<= LBM_P2P_BLOB_BYTES)
+    cudaIpcMemHandle_t f[2], flags;
+    int32_t nx, ny, nz, layout;
+    uint32_t prow;
+    uint64_t pad, pstride;
+};
+static_assert(sizeof(P2pBlob) <= LBM_P2P_BLOB_BYTES, "blob too large");
 
 #define CTX_CHECK(ctx)                                                                         \
     if ((ctx) == nullptr) return LBM_ERR_INVALID;
@@ -147,6 +164,20 @@ __global__ void k_decode_table(StepArgs a, uint32_t nf, int32_t *__restrict__ ou
     }
     D3Q19_DIRS(X)
 #undef X
+}
+
+// peer-memory halo: wait until both neighbours have completed `need` boundary launches, i.e. until
+// everything they store into this rank's ghost planes has landed (end of lbm_run_slab)
+__global__ void k_p2p_drain(int *p2p, int need) {
+    const long long t0 = clock64();
+    for (;;) {
+        int a, b;
+        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(a) : "l"(p2p) : "memory");
+        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(b) : "l"(p2p + 1) : "memory");
+        if (a >= need && b >= need) break;
+        if (clock64() - t0 > 4000000000ll) { atomicExch(p2p + 3, 1); break; }
+        __nanosleep(128);
+    }
 }
 
 // lbm_get_nodes: rows of a [N][width] array at selected nodes
@@ -293,6 +324,12 @@ int ensure_F(lbm_ctx *c) {
 int sync_fields(lbm_ctx *c, bool need_F) {
     if (!c->inited) FAIL(c, LBM_ERR_STATE, "lbm_init has not been called");
     CU(c, cudaSetDevice(c->cfg.device));
+    if (c->p2p_on) {                 // did a boundary kernel give up waiting for a neighbour?
+        int timed_out = 0;
+        CU(c, cudaStreamSynchronize(c->stream));
+        CU(c, cudaMemcpy(&timed_out, c->d_p2p + 3, sizeof(int), cudaMemcpyDeviceToHost));
+        if (timed_out) FAIL(c, LBM_ERR_STATE, "peer-memory halo: a neighbour rank did not arrive within the time-out; the state is invalid");
+    }
     if (need_F) {
         const bool fresh = c->d_F == nullptr;
         int r = ensure_F(c);
@@ -476,6 +513,10 @@ int exchange_merged(lbm_ctx *c, int which, cudaStream_t st, int step = -1) {
     return LBM_OK;
 }
 
+// the boundary-plane kernel doubles as the halo exchange (k_dense_peer): dense slabs whose neighbours
+// are mapped, uniform force (the per-node force variants have no peer form); the same on every rank
+bool p2p_active(const lbm_ctx *c) { return c->p2p_on && c->d_ff == nullptr && !c->cfg.sparse; }
+
 // first and last owned plane of a slab in one launch (buffer cur -> cur ^ 1)
 int launch_boundary_planes(lbm_ctx *c, cudaStream_t st) {
     const int own = c->cfg.nx - 2;
@@ -488,6 +529,20 @@ int launch_boundary_planes(lbm_ctx *c, cudaStream_t st) {
         a.row_count = 2 * ny;
         a.row_split = ny;
         a.row_skip = ny * (uint32_t)(own - 2);
+        if (p2p_active(c)) {
+            static const int kL[5] = {2, 8, 10, 12, 14}, kR[5] = {1, 7, 9, 11, 13};
+            const int out = c->cur ^ 1;             // every rank flips in lockstep
+            for (int q = 0; q < 5; ++q) {
+                a.peer_out[0][q] = c->peer_f[0][out] + (size_t)kL[q] * c->peer_pstride[0];
+                a.peer_out[1][q] = c->peer_f[1][out] + (size_t)kR[q] * c->peer_pstride[1];
+            }
+            a.peer_delta[0] = c->peer_delta[0];
+            a.peer_delta[1] = c->peer_delta[1];
+            a.p2p = c->d_p2p;
+            a.peer_flag[0] = c->peer_flags[0];
+            a.peer_flag[1] = c->peer_flags[1];
+            a.p2p_launch = c->p2p_launches++;
+        }
     } else {
         a.first = c->plane_rank[1];
         a.count = c->plane_rank[2] - a.first;
@@ -551,6 +606,8 @@ int lbm_create(const lbm_config *cfg, lbm_ctx **out) {
     return LBM_OK;
 }
 
+int lbm_p2p_disconnect(lbm_ctx *ctx);
+
 int lbm_destroy(lbm_ctx *ctx) {
     CTX_CHECK(ctx);
     cudaSetDevice(ctx->cfg.device);
@@ -560,6 +617,8 @@ int lbm_destroy(lbm_ctx *ctx) {
     if (ctx->ev_comm) cudaEventDestroy(ctx->ev_comm);
     if (ctx->ev_interior) cudaEventDestroy(ctx->ev_interior);
     for (int i = 0; i < 2; ++i) { cudaFree(ctx->d_send[i]); cudaFree(ctx->d_recv[i]); }
+    lbm_p2p_disconnect(ctx);
+    cudaFree(ctx->d_p2p);
     free_device(ctx);
     delete ctx;
     return LBM_OK;
@@ -1092,6 +1151,82 @@ int lbm_halo_unpack(lbm_ctx *c, int side, int which, const float *src, void *cud
     return halo_unpack_impl(c, side, which, src, (cudaStream_t)cuda_stream);
 }
 
+int lbm_p2p_export(lbm_ctx *c, void *blob256) {
+    CTX_CHECK(c);
+    if (!blob256) FAIL(c, LBM_ERR_INVALID, "null blob");
+    if (!c->inited || !c->cfg.halo_x) FAIL(c, LBM_ERR_STATE, "needs an initialised halo_x context");
+    if (c->cfg.sparse || c->aa) FAIL(c, LBM_ERR_STATE, "the peer-memory halo serves dense two-buffer slabs");
+    CU(c, cudaSetDevice(c->cfg.device));
+    if (!c->d_p2p) {
+        CU(c, cudaMalloc(&c->d_p2p, 64));
+        CU(c, cudaMemset(c->d_p2p, 0, 64));
+    }
+    P2pBlob b;
+    memset(&b, 0, sizeof b);
+    CU(c, cudaIpcGetMemHandle(&b.f[0], c->d_fbase[0]));
+    CU(c, cudaIpcGetMemHandle(&b.f[1], c->d_fbase[1]));
+    CU(c, cudaIpcGetMemHandle(&b.flags, c->d_p2p));
+    b.nx = c->cfg.nx; b.ny = c->cfg.ny; b.nz = c->cfg.nz; b.layout = c->layout;
+    b.prow = c->prow; b.pad = c->pad;
+    b.pstride = c->layout == 1 ? (uint64_t)c->nzp : (uint64_t)c->stride;
+    memset(blob256, 0, LBM_P2P_BLOB_BYTES);
+    memcpy(blob256, &b, sizeof b);
+    return LBM_OK;
+}
+
+int lbm_p2p_connect(lbm_ctx *c, const void *left_blob256, const void *right_blob256) {
+    CTX_CHECK(c);
+    if (!left_blob256 || !right_blob256) FAIL(c, LBM_ERR_INVALID, "null blob");
+    if (!c->d_p2p) FAIL(c, LBM_ERR_STATE, "lbm_p2p_export has not been called");
+    CU(c, cudaSetDevice(c->cfg.device));
+    P2pBlob b[2];
+    memcpy(&b[0], left_blob256, sizeof(P2pBlob));
+    memcpy(&b[1], right_blob256, sizeof(P2pBlob));
+    c->peer_shared = memcmp(&b[0], &b[1], sizeof(P2pBlob)) == 0;      // a world of two: one neighbour on both sides
+    for (int side = 0; side < 2; ++side) {
+        const P2pBlob &p = b[side];
+        if (p.ny != c->cfg.ny || p.nz != c->cfg.nz || p.layout != c->layout || p.prow != c->prow || p.pad != c->pad)
+            FAIL(c, LBM_ERR_INVALID, "neighbour slab has another cross-section or population layout");
+        if (side == 1 && c->peer_shared) {
+            for (int k = 0; k < 3; ++k) c->peer_map[1][k] = c->peer_map[0][k];
+        } else {
+            const cudaIpcMemHandle_t *h[3] = {&p.f[0], &p.f[1], &p.flags};
+            for (int k = 0; k < 3; ++k)
+                CU(c, cudaIpcOpenMemHandle(&c->peer_map[side][k], *h[k], cudaIpcMemLazyEnablePeerAccess));
+        }
+        c->peer_f[side][0] = (float *)c->peer_map[side][0] + p.pad;
+        c->peer_f[side][1] = (float *)c->peer_map[side][1] + p.pad;
+        c->peer_pstride[side] = (long long)p.pstride;
+        // the left neighbour counts my launches in its word [1] (I am its right neighbour) and v.v.
+        c->peer_flags[side] = (int *)c->peer_map[side][2] + (side == 0 ? 1 : 0);
+        // my first owned plane (1) -> the left neighbour's right ghost plane (its nx - 1);
+        // my last owned plane (nx - 2) -> the right neighbour's left ghost plane (0)
+        const long long rows = side == 0 ? (long long)(p.nx - 1 - 1) * c->cfg.ny : -(long long)(c->cfg.nx - 2) * c->cfg.ny;
+        c->peer_delta[side] = rows * (long long)c->prow;
+    }
+    c->p2p_ready = true;
+    return LBM_OK;
+}
+
+int lbm_p2p_disconnect(lbm_ctx *c) {
+    CTX_CHECK(c);
+    cudaSetDevice(c->cfg.device);
+    cudaDeviceSynchronize();
+    for (int side = 0; side < (c->peer_shared ? 1 : 2); ++side)
+        for (int k = 0; k < 3; ++k)
+            if (c->peer_map[side][k]) cudaIpcCloseMemHandle(c->peer_map[side][k]);
+    memset(c->peer_map, 0, sizeof c->peer_map);
+    c->p2p_on = c->p2p_ready = false;
+    return LBM_OK;
+}
+
+int lbm_p2p_enable(lbm_ctx *c, int on) {
+    CTX_CHECK(c);
+    if (on && !c->p2p_ready) FAIL(c, LBM_ERR_STATE, "lbm_p2p_connect has not succeeded");
+    c->p2p_on = on != 0;
+    return LBM_OK;
+}
+
 int lbm_comm_unique_id(void *out128) {
     std::string err;
     if (!out128) return LBM_ERR_INVALID;
@@ -1195,12 +1330,18 @@ int lbm_run_slab(lbm_ctx *c, int nsteps, int overlap, void *cuda_stream) {
         if (r) return r;
         g_timeline.mark("boundary_end", it, c->comm_stream);
         CU(c, cudaEventRecord(c->ev_boundary, c->comm_stream));
-        r = exchange_merged(c, 1, c->comm_stream, it);           // ghost planes of buffer cur ^ 1
-        if (r) return r;
+        if (!p2p_active(c)) {                                    // else the boundary kernel was the exchange
+            r = exchange_merged(c, 1, c->comm_stream, it);       // ghost planes of buffer cur ^ 1
+            if (r) return r;
+        }
         c->cur ^= 1;
         c->ffm_pending = false;
     }
     if (overlap) {                                               // st continues after both streams
+        if (p2p_active(c)) {                                     // ... and after the neighbours' last stores
+            k_p2p_drain<<<1, 1, 0, c->comm_stream>>>(c->d_p2p, c->p2p_launches);
+            CU(c, cudaGetLastError());
+        }
         CU(c, cudaEventRecord(c->ev_comm, c->comm_stream));
         CU(c, cudaStreamWaitEvent(st, c->ev_comm, 0));
     }

@@ -165,8 +165,11 @@ __device__ __forceinline__ void write_user_fields(const StepArgs &a, uint32_t li
 // ---------------------------------------------------------------------------------------------
 // dense lattice: direct addressing, node = linear index i*ny*nz + j*nz + k (z fastest)
 // ---------------------------------------------------------------------------------------------
-template <int FORCE, int MODE, bool SPEC>
-__global__ void __launch_bounds__(256) k_dense(const StepArgs a) {
+// one node of the dense lattice.  PEER (boundary planes of an x-slab whose neighbours are mapped
+// over NVLink): the five populations that cross the cut are also stored straight into the
+// neighbour's ghost plane.
+template <int FORCE, int MODE, bool SPEC, bool PEER>
+__device__ __forceinline__ void dense_node(const StepArgs &a) {
     // blockIdx.x walks the z-chunks of a row (fastest), (blockIdx.z, blockIdx.y) the row groups:
     // blocks that run together then cover whole z-rows, i.e. contiguous 19*nzp*4-byte chunks
     const uint32_t z = blockIdx.x * blockDim.x + threadIdx.x;
@@ -258,6 +261,69 @@ __global__ void __launch_bounds__(256) k_dense(const StepArgs a) {
     }
 #pragma unroll
     for (int s = 0; s < 19; ++s) a.pout[s][pidx] = f[s];
+    if (PEER && compute) {
+        // first owned plane (launch rows below row_split): e_x = -1 leaves to the left neighbour's
+        // right ghost plane; last owned plane: e_x = +1 to the right neighbour's left ghost plane
+        if (r < a.row_split) {
+            const long long q = (long long)pidx + a.peer_delta[0];
+            a.peer_out[0][0][q] = f[2]; a.peer_out[0][1][q] = f[8]; a.peer_out[0][2][q] = f[10];
+            a.peer_out[0][3][q] = f[12]; a.peer_out[0][4][q] = f[14];
+        } else {
+            const long long q = (long long)pidx + a.peer_delta[1];
+            a.peer_out[1][0][q] = f[1]; a.peer_out[1][1][q] = f[7]; a.peer_out[1][2][q] = f[9];
+            a.peer_out[1][3][q] = f[11]; a.peer_out[1][4][q] = f[13];
+        }
+    }
+}
+
+template <int FORCE, int MODE, bool SPEC>
+__global__ void __launch_bounds__(256) k_dense(const StepArgs a) {
+    dense_node<FORCE, MODE, SPEC, false>(a);
+}
+
+// ---- direct peer-memory halo (x-slabs on GPUs that map each other's buffers) -------------------
+// The boundary planes of a slab in ONE kernel that is also the halo exchange: no pack, no
+// ncclSend/Recv, no unpack.  Flags in device memory order the ranks (p2p[0], p2p[1]: how many of
+// these kernels the left / right neighbour has completed, written BY the neighbour over NVLink;
+// p2p[2]: blocks of this launch that are done; p2p[3]: set when a wait timed out):
+//   launch k waits until both neighbours have completed k of theirs -- their launch k-1 read the ghost
+//   planes this launch overwrites, and wrote the ghost planes this launch reads -- then updates its
+//   nodes and stores the crossing populations into the neighbours' ghost planes; the last block to
+//   finish publishes k+1 to both neighbours (system-scope release after every block's fence).
+__device__ __forceinline__ int ld_acquire_sys(const int *p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(int *p, int v) {
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+template <int FORCE, bool SPEC>
+__global__ void __launch_bounds__(256) k_dense_peer(const StepArgs a) {
+    const bool leader = threadIdx.x == 0 && threadIdx.y == 0;
+    if (leader) {
+        const long long t0 = clock64();
+        while (ld_acquire_sys(a.p2p + 0) < a.p2p_launch || ld_acquire_sys(a.p2p + 1) < a.p2p_launch) {
+            if (clock64() - t0 > 4000000000ll) {      // ~2 s: a neighbour is gone; do not hang the GPU
+                atomicExch(a.p2p + 3, 1);
+                break;
+            }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    dense_node<FORCE, MODE_STEP, SPEC, true>(a);
+    __threadfence_system();
+    __syncthreads();
+    if (leader) {
+        const unsigned total = gridDim.x * gridDim.y * gridDim.z;
+        if (atomicAdd((unsigned *)a.p2p + 2, 1u) == total - 1u) {
+            a.p2p[2] = 0;
+            __threadfence_system();
+            st_release_sys(a.peer_flag[0], a.p2p_launch + 1);
+            st_release_sys(a.peer_flag[1], a.p2p_launch + 1);
+        }
+    }
 }
 
 // Dense lattice stepped IN PLACE on one buffer (AA pattern, lbm_config.sparse = 3): the same two
@@ -375,7 +441,8 @@ __global__ void __launch_bounds__(256, 5) k_dense_aa(const StepArgs a) {
 // `parity`), BC, macro, collide, store
 template <int FORCE, int MODE, bool COMP, int AA>
 __device__ __forceinline__ void sparse_node(const StepArgs &a, SparseTable &s_tab, uint64_t *s_bar,
-                                            uint32_t blk, uint32_t i, uint32_t first, uint32_t count) {
+                                            uint32_t blk, uint32_t i, uint32_t first, uint32_t count,
+                                            uint32_t parity = 0u) {
     const bool active = i >= first && i < first + count;
     float f[19];
     uint32_t fl = 0;
@@ -396,7 +463,7 @@ __device__ __forceinline__ void sparse_node(const StepArgs &a, SparseTable &s_ta
             D3Q19_DIRS(X)
 #undef X
         } else if (COMP) {
-            table_wait(a, blk, s_tab, s_bar);
+            table_wait(a, blk, s_tab, s_bar, parity);
             if (!active) return;
             fl = s_tab.fl[threadIdx.x];
             if (!(fl & FL_EXCEPTION)) {
@@ -460,6 +527,10 @@ __device__ __forceinline__ void sparse_node(const StepArgs &a, SparseTable &s_ta
     }
 }
 
+// One 256-node table block per CTA.  (Measured again in round 2 and dropped again: several blocks
+// per CTA with the next slices prefetched into a 3-slot ring, full / empty mbarriers instead of a
+// block barrier -- 0.93 ms per step against 0.73 on the 512^3 pack.  Independent CTAs hide the
+// table fetch better than any coupling of the warps of one CTA.)
 // occupancy: 8 blocks (32 registers) per SM, except the in-place odd step, which keeps the 19
 // pull locations live across the collision and is faster unspilled at 6 blocks (40 registers)
 template <int FORCE, int MODE, bool COMP, int AA>
@@ -513,6 +584,13 @@ static void launch_dense_t(const StepArgs &a, int block, cudaStream_t st) {
             k_dense_aa<FORCE, MODE == MODE_COLLIDE ? MODE_STEP : MODE, AA_ODD><<<grid, blk, 0, st>>>(a);
         else
             k_dense_aa<FORCE, MODE == MODE_COLLIDE ? MODE_STEP : MODE, AA_EVEN><<<grid, blk, 0, st>>>(a);
+        return;
+    }
+    if (MODE == MODE_STEP && FORCE < 2 && a.p2p != nullptr) {      // boundary planes + peer-memory halo
+        if (a.spec)
+            k_dense_peer<FORCE < 2 ? FORCE : 0, true><<<grid, blk, 0, st>>>(a);
+        else
+            k_dense_peer<FORCE < 2 ? FORCE : 0, false><<<grid, blk, 0, st>>>(a);
         return;
     }
     if (a.spec)

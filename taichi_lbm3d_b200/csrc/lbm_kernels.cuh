@@ -103,6 +103,16 @@ struct StepArgs {
     const float *ff[3];
     const float *ffm[3];
     int has_bc;                     // any face with type != 0
+    // peer-memory halo of a dense x-slab (k_dense_peer, boundary-plane launch only; null otherwise):
+    // peer_out[side][q] = plane of the q-th crossing population in the side's neighbour's OUTPUT
+    // buffer, peer_delta[side] = element offset from this slab's boundary plane to that neighbour's
+    // ghost plane, p2p = this rank's flag words, peer_flag[side] = the word of the neighbour that
+    // counts this rank's completed launches, p2p_launch = index of this launch
+    float *peer_out[2][5];
+    long long peer_delta[2];
+    int *p2p;
+    int *peer_flag[2];
+    int p2p_launch;
     d3q19::LbmParams P;
 };
 

@@ -81,10 +81,14 @@ __device__ __forceinline__ void table_fetch(const StepArgs &a, uint32_t blk, Spa
     bulk_g2s(&tab.blk[0], a.blk + (size_t)blk * 16, 64u, bar);
 }
 
-// every thread of the block: wait for the slice
-__device__ __forceinline__ void table_wait(const StepArgs &a, uint32_t blk, SparseTable &tab, uint64_t *bar) {
+// every thread of the block: wait for the slice (`parity`: how often the barrier has completed before, & 1)
+__device__ __forceinline__ void table_wait(const StepArgs &a, uint32_t blk, SparseTable &tab, uint64_t *bar,
+                                           uint32_t parity = 0u) {
     (void)a; (void)blk; (void)tab;
-    mbar_wait(bar, 0u);
+    mbar_wait(bar, parity);
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 // neighbour-row ranks of stored node i (thread threadIdx.x of the block that fetched `tab`)

@@ -175,6 +175,7 @@ class SlabSolver:
         self.overlap = bool(overlap) and self.part.own >= 3
         self._started = False
         self._comm_stream = None
+        self.peer_memory = False
         # reference-style setters are forwarded to the local slab (x faces only act on the
         # ranks that hold them, through x_face_mask)
         for name in dir(LB3D_Solver_Single_Phase):
@@ -217,6 +218,47 @@ class SlabSolver:
                 self.dist.broadcast_object_list(box, src=0)
                 ident.raw = box[0]
             loc._ck(loc._lib.lbm_comm_init(loc._ctx, ident, self.part.world, self.part.rank), "lbm_comm_init")
+            self.peer_memory = self._connect_peer_memory()
+
+    def _connect_peer_memory(self):
+        """Direct peer-memory halo (include/lbm3d.h: lbm_p2p_*): every rank maps its neighbours'
+        population buffers (CUDA IPC over NVLink) and the boundary-plane kernel writes the crossing
+        populations straight into their ghost planes.  Used when EVERY rank could connect (dense
+        storage, overlapped schedule, one node); LBM3D_P2P=0 keeps the NCCL exchange."""
+        import os
+        loc, dist, part = self.local, self.dist, self.part
+        if part.world < 2 or not self.overlap or loc.sparse_storage or os.environ.get("LBM3D_P2P", "1") == "0":
+            return False
+        lib, ctx = loc._lib, loc._ctx
+        blob = (ctypes.c_char * 256)()
+        mine = bytes(blob.raw) if lib.lbm_p2p_export(ctx, blob) == 0 else None
+        blobs = [None] * part.world
+        dist.all_gather_object(blobs, mine)
+        ok = all(b is not None for b in blobs)
+        if ok:
+            left = (ctypes.c_char * 256).from_buffer_copy(blobs[part.left])
+            right = (ctypes.c_char * 256).from_buffer_copy(blobs[part.right])
+            ok = lib.lbm_p2p_connect(ctx, left, right) == 0
+        flag = self.torch.tensor([1 if ok else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)          # all ranks or none: the two exchanges do not mix
+        ok = bool(int(flag.item()))
+        if ok:
+            loc._ck(lib.lbm_p2p_enable(ctx, 1), "lbm_p2p_enable")
+        return ok
+
+    def close(self):
+        """collective: unmap the neighbours' buffers on every rank, then release the slab.  A solver
+        that used the peer-memory halo must be closed (not just dropped) before another is built:
+        memory exported to a neighbour has to outlive the neighbour's mapping of it."""
+        loc = self.local
+        if loc._ctx is not None and self.peer_memory:
+            loc._lib.lbm_p2p_disconnect(loc._ctx)
+            self.peer_memory = False
+            if self.dist:
+                self.dist.barrier()
+        if loc._ctx is not None:
+            loc._lib.lbm_destroy(loc._ctx)
+            loc._ctx = None
 
     # ---- stepping ------------------------------------------------------------------------------
     def _stream(self):

@@ -41,6 +41,8 @@ CASES = {
     # interpreted loops for the dense and the sparse run; the fixture is committed)
     "porous16": ((16, 16, 16), 0.2, 17, [("set_bc_rho_x0", 1.0), ("set_bc_rho_x1", 0.99),
                                          ("set_force", [0.0, 1e-5, 0.0])], 100),
+    "porous12": ((12, 12, 12), 0.2, 19, [("set_bc_rho_x0", 1.0), ("set_bc_rho_x1", 0.99),
+                                         ("set_force", [0.0, 1e-5, 0.0])], 60),
 }
 
 
