@@ -198,6 +198,9 @@ int lbm_p2p_enable(lbm_ctx *ctx, int on);
 /* unmap the neighbours' buffers; every rank calls it (then a barrier) BEFORE any rank destroys its
  * context: exported memory must outlive its mappings */
 int lbm_p2p_disconnect(lbm_ctx *ctx);
+/* 1 when this process already holds the NCCL communicator for (world, rank) on the current device
+ * (one per process, shared by all contexts): lbm_comm_init then needs no unique id */
+int lbm_comm_ready(int world, int rank);
 int lbm_comm_unique_id(void *out128);
 int lbm_comm_init(lbm_ctx *ctx, const void *id128, int world, int rank);
 int lbm_run_slab(lbm_ctx *ctx, int nsteps, int overlap, void *cuda_stream);

@@ -75,6 +75,7 @@ SIGNATURES = {
     "lbm_p2p_connect": (_I, [_VP, _VP, _VP]),
     "lbm_p2p_enable": (_I, [_VP, _I]),
     "lbm_p2p_disconnect": (_I, [_VP]),
+    "lbm_comm_ready": (_I, [_I, _I]),
     "lbm_comm_unique_id": (_I, [_VP]),
     "lbm_comm_init": (_I, [_VP, _VP, _I, _I]),
     "lbm_run_slab": (_I, [_VP, _I, _I, _VP]),

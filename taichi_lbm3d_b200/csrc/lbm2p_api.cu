@@ -832,11 +832,12 @@ int lbm2p_comm_init(lbm2p_ctx *c, const void *id128, int world, int rank) {
     if (world < 1 || rank < 0 || rank >= world) FAIL2(c, -1, "bad world/rank");
     CU2(c, cudaSetDevice(c->cfg.device));
     if (world > 1) {
-        if (!id128) FAIL2(c, -1, "null NCCL id");
         std::string err;
         if (!load_nccl(err)) FAIL2(c, -2, "%s", err.c_str());
         NcclId id;
-        memcpy(&id, id128, sizeof id);
+        memset(&id, 0, sizeof id);
+        if (id128) memcpy(&id, id128, sizeof id);
+        else if (!have_shared_comm(world, rank)) FAIL2(c, -1, "null NCCL id and no communicator yet");
         NC2(c, shared_comm(world, rank, id, &c->comm));
     }
     c->comm_world = world;

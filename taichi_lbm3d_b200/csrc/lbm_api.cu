@@ -1227,6 +1227,8 @@ int lbm_p2p_enable(lbm_ctx *c, int on) {
     return LBM_OK;
 }
 
+int lbm_comm_ready(int world, int rank) { return g_nccl.ok && have_shared_comm(world, rank) ? 1 : 0; }
+
 int lbm_comm_unique_id(void *out128) {
     std::string err;
     if (!out128) return LBM_ERR_INVALID;
@@ -1243,11 +1245,12 @@ int lbm_comm_init(lbm_ctx *c, const void *id128, int world, int rank) {
     if (world < 1 || rank < 0 || rank >= world) FAIL(c, LBM_ERR_INVALID, "bad world/rank");
     CU(c, cudaSetDevice(c->cfg.device));
     if (world > 1) {
-        if (!id128) FAIL(c, LBM_ERR_INVALID, "null NCCL id");
         std::string err;
         if (!load_nccl(err)) FAIL(c, LBM_ERR_CUDA, "%s", err.c_str());
         NcclId id;
-        memcpy(&id, id128, sizeof id);
+        memset(&id, 0, sizeof id);
+        if (id128) memcpy(&id, id128, sizeof id);
+        else if (!have_shared_comm(world, rank)) FAIL(c, LBM_ERR_INVALID, "null NCCL id and no communicator yet");
         NC(c, shared_comm(world, rank, id, &c->comm));
     }
     c->comm_world = world;

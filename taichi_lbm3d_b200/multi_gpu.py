@@ -211,12 +211,14 @@ class SlabSolver:
             if self.part.world > 1:
                 if self.dist.get_backend() != "nccl":
                     raise _lib.LbmError("transport='native' needs the nccl process group")
-                box = [None]
-                if self.part.rank == 0:
-                    loc._ck(loc._lib.lbm_comm_unique_id(ident), "lbm_comm_unique_id")
-                    box[0] = bytes(ident.raw)
-                self.dist.broadcast_object_list(box, src=0)
-                ident.raw = box[0]
+                # one NCCL communicator per process (lbm_nccl.cuh): only the first solver needs an id
+                if not loc._lib.lbm_comm_ready(self.part.world, self.part.rank):
+                    box = [None]
+                    if self.part.rank == 0:
+                        loc._ck(loc._lib.lbm_comm_unique_id(ident), "lbm_comm_unique_id")
+                        box[0] = bytes(ident.raw)
+                    self.dist.broadcast_object_list(box, src=0)
+                    ident.raw = box[0]
             loc._ck(loc._lib.lbm_comm_init(loc._ctx, ident, self.part.world, self.part.rank), "lbm_comm_init")
             self.peer_memory = self._connect_peer_memory()
 
@@ -230,16 +232,20 @@ class SlabSolver:
         if part.world < 2 or not self.overlap or loc.sparse_storage or os.environ.get("LBM3D_P2P", "1") == "0":
             return False
         lib, ctx = loc._lib, loc._ctx
+        torch = self.torch
         blob = (ctypes.c_char * 256)()
-        mine = bytes(blob.raw) if lib.lbm_p2p_export(ctx, blob) == 0 else None
-        blobs = [None] * part.world
-        dist.all_gather_object(blobs, mine)
-        ok = all(b is not None for b in blobs)
+        exported = lib.lbm_p2p_export(ctx, blob) == 0
+        # one all_gather of 257 bytes per rank: the blob and whether it is valid
+        mine = torch.frombuffer(bytearray(bytes(blob.raw) + (b"\x01" if exported else b"\x00")), dtype=torch.uint8).cuda()
+        everyone = torch.empty(part.world * 257, dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(everyone, mine)
+        everyone = everyone.cpu().numpy().reshape(part.world, 257)
+        ok = bool(everyone[:, 256].all())
         if ok:
-            left = (ctypes.c_char * 256).from_buffer_copy(blobs[part.left])
-            right = (ctypes.c_char * 256).from_buffer_copy(blobs[part.right])
+            left = (ctypes.c_char * 256).from_buffer_copy(everyone[part.left, :256].tobytes())
+            right = (ctypes.c_char * 256).from_buffer_copy(everyone[part.right, :256].tobytes())
             ok = lib.lbm_p2p_connect(ctx, left, right) == 0
-        flag = self.torch.tensor([1 if ok else 0], device="cuda")
+        flag = torch.tensor([1 if ok else 0], device="cuda")
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)          # all ranks or none: the two exchanges do not mix
         ok = bool(int(flag.item()))
         if ok:
@@ -498,12 +504,13 @@ class TwoPhaseSlabSolver:
             if self.part.world > 1:
                 if self.dist.get_backend() != "nccl":
                     raise _lib.LbmError("transport='native' needs the nccl process group")
-                box = [None]
-                if self.part.rank == 0:
-                    loc._ck(lib.lbm2p_comm_unique_id(ident), "lbm2p_comm_unique_id")
-                    box[0] = bytes(ident.raw)
-                self.dist.broadcast_object_list(box, src=0)
-                ident.raw = box[0]
+                if not lib.lbm_comm_ready(self.part.world, self.part.rank):      # one communicator per process
+                    box = [None]
+                    if self.part.rank == 0:
+                        loc._ck(lib.lbm2p_comm_unique_id(ident), "lbm2p_comm_unique_id")
+                        box[0] = bytes(ident.raw)
+                    self.dist.broadcast_object_list(box, src=0)
+                    ident.raw = box[0]
             loc._ck(lib.lbm2p_comm_init(ctx, ident, self.part.world, self.part.rank), "lbm2p_comm_init")
 
     # ---- stepping ------------------------------------------------------------------------------
