@@ -376,7 +376,7 @@ def sub_two_phase(env, args):
     """BASELINE config 4 (drainage, 131^3 stand-in geometry, both storages) and two larger boxes"""
     import numpy as np
     from taichi_lbm3d_b200 import LB3D_Solver_Two_Phase
-    from taichi_lbm3d_b200.geometry import ftb131_standin, sphere_pack
+    from taichi_lbm3d_b200.geometry import ftb131_geometry, sphere_pack
     # warm-up of 200 steps: psi = rho_r - rho_b/(rho_r + rho_b) (the reference's precedence) follows the
     # density waves in the red phase, so from a sharp initial interface the region with C != 0 -- the
     # nodes that carry the recolouring arithmetic and the interface part of the colour record -- grows
@@ -401,11 +401,11 @@ def sub_two_phase(env, args):
                                      profiled_traffic(traffic_key) if traffic_key else None)}
 
     out = []
-    solid = ftb131_standin()
+    solid, source = ftb131_geometry()        # LBM3D_FTB131 / ./img_ftb131.txt when present
     psi = np.ones(solid.shape, np.float32)
     psi[:13] = -1.0
     text = "colour-gradient drainage 131^3 (BASELINE config 4: niu_l=0.05, niu_g=0.2, CapA=0.005, " \
-           "psi_solid=0.7; sphere-pack stand-in for the missing ftb131 files), %s storage"
+           "psi_solid=0.7; " + source + "), %s storage"
     out.append(run(text % "dense", solid, psi, False))
     out.append(run(text % "sparse", solid, psi, True))
     n = 256

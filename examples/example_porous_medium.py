@@ -8,12 +8,15 @@ import os
 import LBM_3D_SinglePhase_Solver as lb3dsp
 from _progress import Progress
 
-IMAGE = "./img_ftb131.txt"
+IMAGE = os.environ.get("LBM3D_FTB131", "./img_ftb131.txt")
 if not os.path.exists(IMAGE):
+    if "LBM3D_FTB131" in os.environ:
+        raise FileNotFoundError("LBM3D_FTB131=%s does not exist" % IMAGE)
     from taichi_lbm3d_b200 import geometry
     geometry.save_geometry_text(IMAGE, geometry.ftb131_standin())
 
-solver = lb3dsp.LB3D_Solver_Single_Phase(nx=131, ny=131, nz=131, sparse_storage=True)
+# dense storage as in the reference script (:12); sparse_storage=True is the faster choice at 20 % porosity
+solver = lb3dsp.LB3D_Solver_Single_Phase(nx=131, ny=131, nz=131, sparse_storage=False)
 solver.init_geo(IMAGE)
 solver.set_bc_rho_x0(1.0)
 solver.set_bc_rho_x1(0.99)

@@ -106,3 +106,18 @@ def ftb131_standin():
     """Synthetic stand-in for the missing img_ftb131.txt: 131^3, seed 131,
     radii U[4,9], solid fraction >= 0.80, non-periodic in x."""
     return sphere_pack(131, 131, 131, 0.80, 4.0, 9.0, seed=131, periodic=False)
+
+
+def ftb131_geometry():
+    """(solid, where it came from): the micro-CT image of BASELINE configs 1 and 4 when the user
+    has it -- the file named by ``LBM3D_FTB131``, else ``./img_ftb131.txt`` (the name the
+    reference's example scripts open, Single_phase/example_porous_medium.py:13) -- and otherwise
+    the seeded stand-in.  A path given through the environment that does not load is
+    an error, not a silent fall-back."""
+    named = os.environ.get("LBM3D_FTB131")
+    for path in ([named] if named else []) + ["./img_ftb131.txt"]:
+        if os.path.exists(path):
+            return load_geometry(path, 131, 131, 131), "ftb131 image %s" % os.path.abspath(path)
+        if path == named:
+            raise FileNotFoundError("LBM3D_FTB131=%s does not exist" % named)
+    return ftb131_standin(), "sphere-pack stand-in for the missing ftb131 files"

@@ -220,7 +220,13 @@ class SlabSolver:
                     self.dist.broadcast_object_list(box, src=0)
                     ident.raw = box[0]
             loc._ck(loc._lib.lbm_comm_init(loc._ctx, ident, self.part.world, self.part.rank), "lbm_comm_init")
-            self.peer_memory = self._connect_peer_memory()
+            # Mapping the neighbours' buffers costs 50 ms (2 GPUs) to 200 ms (8): it is done at the first
+            # multi-step run(n), which announces a job long enough to repay it; a job of a few single
+            # step() calls stays on the NCCL exchange.  LBM3D_P2P=1 maps here, LBM3D_P2P=0 never.
+            import os
+            self._peer_tried = False
+            if os.environ.get("LBM3D_P2P", "") == "1":
+                self.peer_memory, self._peer_tried = self._connect_peer_memory(), True
 
     def _connect_peer_memory(self):
         """Direct peer-memory halo (include/lbm3d.h: lbm_p2p_*): every rank maps its neighbours'
@@ -229,7 +235,7 @@ class SlabSolver:
         storage, overlapped schedule, one node); LBM3D_P2P=0 keeps the NCCL exchange."""
         import os
         loc, dist, part = self.local, self.dist, self.part
-        if part.world < 2 or not self.overlap or loc.sparse_storage or os.environ.get("LBM3D_P2P", "1") == "0":
+        if part.world < 2 or not self.overlap or loc.sparse_storage or os.environ.get("LBM3D_P2P", "") == "0":
             return False
         lib, ctx = loc._lib, loc._ctx
         torch = self.torch
@@ -312,6 +318,8 @@ class SlabSolver:
             return
         if self.transport == "native":
             loc = self.local
+            if n > 1 and not getattr(self, "_peer_tried", True):
+                self.peer_memory, self._peer_tried = self._connect_peer_memory(), True
             loc._ck(loc._lib.lbm_run_slab(loc._ctx, n, int(self.overlap), self._stream()), "lbm_run_slab")
             self._started = True
             return

@@ -433,12 +433,14 @@ def test_launches_are_counted(cuda):
     assert lb.launch_count - n0 == 10
 
 
-def test_config1_ftb131_standin_1000_steps(cuda):
+def test_config1_ftb131_1000_steps(cuda):
     """BASELINE config 1 as example_porous_medium.py runs it: 131^3, rho(x0)=1.0, rho(x1)=0.99,
-    default viscosity, no force, dense storage -- on the seeded stand-in for the missing
-    img_ftb131.txt; populations, rho, v after 1000 steps against the oracle."""
-    from taichi_lbm3d_b200.geometry import ftb131_standin
-    case = cases.Case("cfg1_ftb131", ftb131_standin(), bc=[(1, "rho", 0.99), (0, "rho", 1.0)])
+    default viscosity, no force, dense storage -- on img_ftb131.txt when the user has it
+    (LBM3D_FTB131 or ./img_ftb131.txt), else on the seeded stand-in; populations,
+    rho, v after 1000 steps against the oracle."""
+    from taichi_lbm3d_b200.geometry import ftb131_geometry
+    solid, _source = ftb131_geometry()
+    case = cases.Case("cfg1_ftb131", solid, bc=[(1, "rho", 0.99), (0, "rho", 1.0)])
     o, _ = _oracle(case, 1000)
     lb = _run_solver(case, 1000, False, False, None)
     _compare(lb, o, False, case, 1000)
