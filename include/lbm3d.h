@@ -90,6 +90,16 @@ int lbm_set_bc(lbm_ctx *ctx, int face, int type, float rho, const float vel[3]);
  * 1 = the script copies of the solver (Single_phase/lbm_solver_3d.py:253,268), in place for
  * s = 0..18:  F[s] = feq(LR[s], 1, u) - F[LR[s]] + feq(s, 1, u).  Before lbm_init. */
 int lbm_set_vel_bc_form(lbm_ctx *ctx, int script_form);
+/* Grey-scale lattice (replaces ns.from_numpy of Grey_Scale/lbm_solver_3d_Macro_Sukop.py:343 and
+ * its streaming0 / streaming1, :233-247): float [nx][ny][nz], the solid fraction of every node.
+ * Post-collision populations are blended with the opposite population of the node ahead,
+ * f2[i][s] = f[i][s] + ns[i] (f[i+e_s][LR[s]] - f[i][s]), and streamed to every neighbour without
+ * bounce-back; links that leave a solid node (lbm_set_geometry; the script uses solid = int(ns))
+ * deliver the rest value w[s], as in the script, which never writes them.  With
+ * lbm_set_relaxation(3 niu + 1/2 ...), lbm_set_guo_form(1) this is that script's time step.
+ * Dense two-buffer storage on one GPU, periodic and fixed-pressure faces; NULL switches it off.
+ * Before lbm_init. */
+int lbm_set_grey_scale(lbm_ctx *ctx, const float *ns_host_or_dev);
 /* set_force (:457); force_flag as :137-140 */
 int lbm_set_force(lbm_ctx *ctx, const float force[3]);
 /* form of the Guo force term in the collision: 0 = the class (:236, parts divided by 3 and 9:

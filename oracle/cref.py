@@ -44,7 +44,7 @@ def _params_struct(ctype):
                     ("S", ctype * 19), ("invM", ctype * 361), ("w", ctype * 19),
                     ("force", ctype * 3), ("bc_rho", ctype * 6), ("bc_vel", (ctype * 3) * 6),
                     ("force_field", ctypes.c_void_p), ("guo_unscaled", ctypes.c_int),
-                    ("vel_bc_script", ctypes.c_int)]
+                    ("vel_bc_script", ctypes.c_int), ("ns", ctypes.c_void_p)]
     return P
 
 
@@ -98,6 +98,7 @@ class RefSinglePhaseC(_np_ref.RefSinglePhase):
         p.force_field = None if ff is None else ff.ctypes.data
         p.guo_unscaled = 1 if self.guo_mode == "unscaled" else 0
         p.vel_bc_script = 1 if self.vel_bc_mode == "script" else 0
+        p.ns = None if self.ns is None else self.ns.ctypes.data
         self._p = p
 
     def set_force_field(self, force):
@@ -113,6 +114,10 @@ class RefSinglePhaseC(_np_ref.RefSinglePhase):
     def streaming1(self):
         self._fn("ref_sp_streaming1")(ctypes.byref(self._p), self._ptr(self.solid), self._ptr(self.f),
                                       self._ptr(self.F))
+
+    def streaming_grey(self):
+        self._fn("ref_sp_streaming_grey")(ctypes.byref(self._p), self._ptr(self.solid), self._ptr(self.f),
+                                          self._ptr(self.F))
 
     def Boundary_condition(self):
         self._fn("ref_sp_boundary_condition")(ctypes.byref(self._p), self._ptr(self.solid),

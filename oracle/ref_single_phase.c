@@ -72,6 +72,7 @@ typedef struct {
     const REAL *force_field; /* [n][3] per-node force = cal_local_force(i,j,k) :217-220, or NULL */
     int guo_unscaled;        /* 1: Phase_change/LBM_3D_SinglePhase_Solver.py:235 (no /3, /9) */
     int vel_bc_script;       /* 1: Single_phase/lbm_solver_3d.py:253 (in-place velocity form) */
+    const REAL *ns;          /* [n] solid fraction per node (Grey_Scale/lbm_solver_3d_Macro_Sukop.py:42), or NULL */
 } FN(ref_params);
 typedef FN(ref_params) params_t;
 
@@ -159,6 +160,27 @@ void FN(ref_sp_streaming1)(const params_t *p, const int8_t *solid, const REAL *f
             }
 }
 
+/* Grey_Scale/lbm_solver_3d_Macro_Sukop.py:233-247 (streaming0 + streaming1): blend with the opposite
+ * population of the node ahead, weighted by the node's solid fraction, then push to ALL neighbours
+ * (no bounce-back; solid nodes never push, so the links that leave them keep their old value).
+ * f2 is evaluated on the fly: f is not written between the two passes. */
+void FN(ref_sp_streaming_grey)(const params_t *p, const int8_t *solid, const REAL *f, REAL *F) {
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int i = 0; i < p->nx; ++i)
+        for (int j = 0; j < p->ny; ++j)
+            for (int k = 0; k < p->nz; ++k) {
+                size_t c = nidx(p, i, j, k);
+                if (solid[c] != 0) continue;
+                for (int s = 0; s < 19; ++s) {
+                    size_t ip = nidx(p, wrap(i + Ei[s][0], p->nx), wrap(j + Ei[s][1], p->ny),
+                                     wrap(k + Ei[s][2], p->nz));
+                    REAL d = f[ip * 19 + LRi[s]] - f[c * 19 + s];
+                    REAL t = p->ns[c] * d;
+                    F[ip * 19 + s] = f[c * 19 + s] + t;
+                }
+            }
+}
+
 /* :272-370  faces x0,x1,y0,y1,z0,z1 in order, each a complete loop before the next. */
 void FN(ref_sp_boundary_condition)(const params_t *p, const int8_t *solid, const REAL *v, REAL *F) {
     const int n[3] = {p->nx, p->ny, p->nz};
@@ -225,7 +247,8 @@ void FN(ref_sp_step)(const params_t *p, const int8_t *solid, REAL *f, REAL *F, R
                      int nsteps) {
     for (int it = 0; it < nsteps; ++it) {
         FN(ref_sp_colission)(p, solid, F, rho, v, f);
-        FN(ref_sp_streaming1)(p, solid, f, F);
+        if (p->ns) FN(ref_sp_streaming_grey)(p, solid, f, F);
+        else FN(ref_sp_streaming1)(p, solid, f, F);
         FN(ref_sp_boundary_condition)(p, solid, v, F);
         FN(ref_sp_streaming3)(p, solid, F, f, rho, v);
     }

@@ -105,6 +105,7 @@ class RefSinglePhase:
         # :17-18
         self.fx, self.fy, self.fz = 0.0e-6, 0.0, 0.0
         self.force_field = None             # array form of an overridden cal_local_force
+        self.ns = None                      # solid fraction per node: Grey_Scale/lbm_solver_3d_Macro_Sukop.py:42
         self.niu = 0.16667
         # :23-28   [type, rho, vx, vy, vz] per face, order x0,x1,y0,y1,z0,z1
         self.bc_type = [0] * 6
@@ -131,6 +132,13 @@ class RefSinglePhase:
 
     def set_solid(self, arr):
         self.solid[...] = (np.asarray(arr) > 0).astype(np.int8)
+
+    def set_grey_scale(self, ns):
+        """Grey_Scale/lbm_solver_3d_Macro_Sukop.py:338-343: the solid fraction of every node; nodes
+        with int(ns) >= 1 are solid.  Switches the streaming to that script's partial bounce-back."""
+        a = np.asarray(ns)
+        self.ns = np.ascontiguousarray(a.astype(self.dtype))
+        self.solid[...] = (a.astype(int) > 0).astype(np.int8)
 
     def set_bc_vel(self, face, vel):      # :405-427
         self.bc_type[face] = 2
@@ -250,6 +258,23 @@ class RefSinglePhase:
             bounce = fluid & nb_solid
             self.F[..., LR[s]][bounce] = self.f[..., s][bounce]
 
+    def streaming_grey(self):
+        """Grey_Scale/lbm_solver_3d_Macro_Sukop.py:233-247 (streaming0 + streaming1): every fluid node
+        blends its post-collision population s with the opposite one of the node it moves to,
+            f2[i][s] = f[i][s] + ns[i] * (f[i + e_s][LR[s]] - f[i][s]),
+        and pushes f2[i][s] to i + e_s whatever that node is -- no bounce-back.  Solid nodes are
+        never collided (f = w for ever) and never push, so F[i][s] of a fluid node whose source
+        i - e_s is solid keeps its previous value."""
+        fluid = self.solid == 0
+        for s in range(19):
+            ex, ey, ez = (int(c) for c in E[s])
+            fs = self.f[..., s]
+            opp = np.roll(self.f[..., LR[s]], (-ex, -ey, -ez), axis=(0, 1, 2))    # f[ip][LR[s]] viewed at i
+            f2 = fs + self.ns * (opp - fs)
+            arriving = np.roll(f2, (ex, ey, ez), axis=(0, 1, 2))
+            src_fluid = np.roll(fluid, (ex, ey, ez), axis=(0, 1, 2))
+            self.F[..., s][src_fluid] = arriving[src_fluid]
+
     def Boundary_condition(self):
         """:272-370  faces in order x0,x1,y0,y1,z0,z1; later faces overwrite earlier."""
         dt = self.dtype.type
@@ -315,7 +340,10 @@ class RefSinglePhase:
     def step(self):
         """:477-481"""
         self.colission()
-        self.streaming1()
+        if self.ns is not None:
+            self.streaming_grey()
+        else:
+            self.streaming1()
         self.Boundary_condition()
         self.streaming3()
 

@@ -99,9 +99,15 @@ class LB3D_Solver_Single_Phase:
         self.device = device
         self._solid_host = np.zeros((nx, ny, nz), np.int8)
         self._force_field = None
+        self._ns_host = None
         self._ctx = None
         self._lib = None
         self.solid = _Field(self, "solid", (nx, ny, nz), np.int8)
+        # solid fraction per node of the grey-scale solver (Grey_Scale/lbm_solver_3d_Macro_Sukop.py:42):
+        # ns.from_numpy(a) switches the streaming to that script's partial bounce-back (:233-247) and, as
+        # the script does (:339), makes the nodes with int(a) >= 1 solid; with tau_mode="textbook",
+        # guo_mode="unscaled" the time step is the script's.  Dense two-buffer storage only.
+        self.ns = _Field(self, "ns", (nx, ny, nz), np.float32)
         self.rho = _Field(self, "rho", (nx, ny, nz), np.float32)
         self.v = _Field(self, "v", (nx, ny, nz, 3), np.float32)
         self.F = _Field(self, "F", (nx, ny, nz, 19), np.float32)
@@ -238,6 +244,8 @@ class LB3D_Solver_Single_Phase:
         self._ck(lib.lbm_set_force(ctx, fc), "lbm_set_force")
         self._ck(lib.lbm_set_guo_form(ctx, 1 if self.guo_mode == "unscaled" else 0), "lbm_set_guo_form")
         self._ck(lib.lbm_set_vel_bc_form(ctx, 1 if self.vel_bc_mode == "script" else 0), "lbm_set_vel_bc_form")
+        if self._ns_host is not None:
+            self._ck(lib.lbm_set_grey_scale(ctx, self._ns_host.ctypes.data_as(ctypes.c_void_p)), "lbm_set_grey_scale")
         self._ck(lib.lbm_set_relaxation(ctx, S.ctypes.data_as(_lib._FP)), "lbm_set_relaxation")
         if self.strict:
             from .constants import M_np
@@ -313,6 +321,8 @@ class LB3D_Solver_Single_Phase:
         force, BCs, tau/guo mode) as a compressed .npz (``.npz`` is appended if missing)"""
         import json
         extra = {} if self._force_field is None else {"force_field": self._force_field}
+        if self._ns_host is not None:
+            extra["ns"] = self._ns_host
         np.savez_compressed(self._ckpt_path(path), nx=self.nx, ny=self.ny, nz=self.nz, solid=self._solid_host,
                             F=self.F.to_numpy(), rho=self.rho.to_numpy(), v=self.v.to_numpy(),
                             settings=np.array(json.dumps(self._case_settings())), **extra)
@@ -327,6 +337,9 @@ class LB3D_Solver_Single_Phase:
         if (int(d["nx"]), int(d["ny"]), int(d["nz"])) != (self.nx, self.ny, self.nz) or \
                 not np.array_equal(d["solid"], self._solid_host):
             raise ValueError("checkpoint was written for a different lattice")
+        if ("ns" in d.files) != (self._ns_host is not None) or \
+                ("ns" in d.files and not np.array_equal(d["ns"], self._ns_host)):
+            raise ValueError("checkpoint was written for a different grey-scale lattice (ns differs)")
         if "settings" in d.files:
             saved, mine = json.loads(str(d["settings"])), self._case_settings()
             if saved != mine:
@@ -381,6 +394,13 @@ class LB3D_Solver_Single_Phase:
                 out[...] = self._solid_host
                 return out
             return self._solid_host.copy()
+        if name == "ns":
+            if self._ns_host is None:
+                raise _lib.LbmError("ns has not been assigned (the lattice is not a grey-scale one)")
+            if out is not None:
+                out[...] = self._ns_host
+                return out
+            return self._ns_host.copy()
         if self._ctx is None:
             raise _lib.LbmError("field %s is not available before init_simulation()" % name)
         shape = {"rho": (self.nx, self.ny, self.nz), "v": (self.nx, self.ny, self.nz, 3),
@@ -409,6 +429,16 @@ class LB3D_Solver_Single_Phase:
                 self._lib.lbm_destroy(self._ctx)
                 self._ctx = None
             self._solid_host = (a > 0).view(np.int8)        # init_geo :175 (bool viewed as 0/1 bytes: one pass)
+            return
+        if name == "ns":
+            a = np.asarray(arr)
+            if a.shape != (self.nx, self.ny, self.nz):
+                raise ValueError("ns must have shape %s" % ((self.nx, self.ny, self.nz),))
+            if self._ctx is not None:
+                self._lib.lbm_destroy(self._ctx)
+                self._ctx = None
+            self._ns_host = np.ascontiguousarray(a, dtype=np.float32)
+            self._solid_host = (a.astype(int) > 0).view(np.int8)     # solid_np = ns_np.astype(int), :339
             return
         if name == "f":
             return      # scratch in the reference: colission overwrites it before any read (:240)

@@ -48,6 +48,7 @@ SIGNATURES = {
     "lbm_set_force_field": (_I, [_VP, _VP]),
     "lbm_set_guo_form": (_I, [_VP, _I]),
     "lbm_set_vel_bc_form": (_I, [_VP, _I]),
+    "lbm_set_grey_scale": (_I, [_VP, _VP]),
     "lbm_set_viscosity": (_I, [_VP, _c.c_double, _I]),
     "lbm_set_relaxation": (_I, [_VP, _FP]),
     "lbm_set_inverse_matrix": (_I, [_VP, _FP]),

@@ -60,6 +60,7 @@ struct lbm_ctx {
     int xface0 = -1, xface1 = -1;            // local x index of the global x0 / x1 faces
     // device buffers
     int8_t *d_solid = nullptr;
+    float *d_ns = nullptr;         // grey-scale lattice: [N] solid fraction per node (kept across lbm_init, like d_solid)
     uint32_t *d_flags = nullptr;   // dense: [N] link words; sparse: [nf] BC words
     int32_t *d_nbr = nullptr;      // sparse, full table: [18][stride]
     uint8_t *d_rb8 = nullptr;      // sparse, compressed table: [8][stride] 8-bit offsets of rank - index; exception slots
@@ -260,6 +261,7 @@ void fill_args(const lbm_ctx *c, StepArgs &a) {
         }
     }
     a.has_bc = 0;
+    a.ns = c->d_ns;
     for (int i = 0; i < 19; ++i) a.P.S[i] = c->S[i];
     for (int i = 0; i < 3; ++i) a.P.force[i] = c->force[i];
     {
@@ -619,6 +621,7 @@ int lbm_destroy(lbm_ctx *ctx) {
     for (int i = 0; i < 2; ++i) { cudaFree(ctx->d_send[i]); cudaFree(ctx->d_recv[i]); }
     lbm_p2p_disconnect(ctx);
     cudaFree(ctx->d_p2p);
+    cudaFree(ctx->d_ns);
     free_device(ctx);
     delete ctx;
     return LBM_OK;
@@ -671,6 +674,23 @@ int lbm_set_vel_bc_form(lbm_ctx *ctx, int script_form) {
     CTX_CHECK(ctx);
     if (ctx->inited) FAIL(ctx, LBM_ERR_STATE, "the form of the velocity faces is fixed at lbm_init");
     ctx->vel_bc_script = script_form ? 1 : 0;
+    return LBM_OK;
+}
+
+int lbm_set_grey_scale(lbm_ctx *ctx, const float *ns) {
+    CTX_CHECK(ctx);
+    if (ctx->inited) FAIL(ctx, LBM_ERR_STATE, "the solid fractions are fixed at lbm_init");
+    if (ns && (ctx->cfg.sparse || ctx->cfg.halo_x))
+        FAIL(ctx, LBM_ERR_INVALID, "the grey-scale lattice needs dense two-buffer storage on one GPU "
+                                   "(not sparse, not in place, not an x-slab)");
+    CU(ctx, cudaSetDevice(ctx->cfg.device));
+    if (!ns) {
+        cudaFree(ctx->d_ns);
+        ctx->d_ns = nullptr;
+        return LBM_OK;
+    }
+    if (!ctx->d_ns) CU(ctx, cudaMalloc(&ctx->d_ns, ctx->N * sizeof(float)));
+    CU(ctx, cudaMemcpy(ctx->d_ns, ns, ctx->N * sizeof(float), cudaMemcpyDefault));
     return LBM_OK;
 }
 
@@ -764,6 +784,14 @@ int lbm_init(lbm_ctx *c) {
         c->d_solid = keep;
     }
     c->inited = false;
+    if (c->d_ns) {
+        // a link that leaves a solid node is never written by the grey-scale script and holds w[s];
+        // its in-place velocity face reads such slots back (F[LR[s]]) and would need them stored
+        for (int i = 0; i < 6; ++i)
+            if (c->face[i].type == 2)
+                FAIL(c, LBM_ERR_INVALID, "fixed-velocity faces are not available on a grey-scale lattice "
+                                         "(periodic and fixed-pressure faces are)");
+    }
     GeoParams g;
     g.nx = nx; g.ny = ny; g.nz = nz;
     g.halo_x = c->cfg.halo_x ? 1 : 0;

@@ -281,6 +281,69 @@ __global__ void __launch_bounds__(256) k_dense(const StepArgs a) {
     dense_node<FORCE, MODE, SPEC, false>(a);
 }
 
+// ---- grey-scale lattice: partial bounce-back streaming -------------------------------------------
+// Grey_Scale/lbm_solver_3d_Macro_Sukop.py:233-247.  The script blends, at every fluid node j and for
+// every direction s, the post-collision population with the opposite one of the node ahead,
+//     f2[j][s] = f*[j][s] + ns[j] (f*[j + e_s][LR[s]] - f*[j][s]),
+// and pushes f2[j][s] to j + e_s -- to every neighbour, there is no bounce-back.  Pulled from node i
+// (j = i - e_s, periodic wrap :222-231) that is
+//     F[i][s] = f*[j][s] + ns[j] (f*[i][LR[s]] - f*[j][s])        source j fluid
+//     F[i][s] = w[s]                                              source j solid (ns >= 1)
+// the second line because the script never collides or pushes from a solid node, so that slot of F
+// keeps the value init() gave it (tests/test_reference_pin.py::test_grey_scale_script pins this).
+// An option off the roofline path: besides the 19 pull sources a node reads its own 19 populations
+// and the solid fraction of its 18 neighbours; every node reads its link word, nothing is speculated.
+template <int FORCE, int MODE>
+__global__ void __launch_bounds__(256) k_dense_grey(const StepArgs a) {
+    const uint32_t z = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t r = (blockIdx.z * gridDim.y + blockIdx.y) * blockDim.y + threadIdx.y;
+    if (z >= (uint32_t)a.nz || r >= a.row_count) return;
+    const uint32_t row = a.row_first + r;
+    const uint32_t idx = row * (uint32_t)a.nz + z;
+    const uint32_t pidx = row * a.prow + z;
+    const uint32_t fl = a.flags[idx];
+    if (fl & FL_SOLID) return;                          // solid nodes keep f = F = w, rho = 1, v = 0
+    // steps to the x-1 / x+1 ... neighbours in lattice units, with the periodic wrap
+    const int xm = (fl & FL_AT_X0) ? a.nx - 1 : -1, xp = (fl & FL_AT_X1) ? -(a.nx - 1) : 1;
+    const int ym = (fl & FL_AT_Y0) ? a.ny - 1 : -1, yp = (fl & FL_AT_Y1) ? -(a.ny - 1) : 1;
+    const int zm = (fl & FL_AT_Z0) ? a.nz - 1 : -1, zp = (fl & FL_AT_Z1) ? -(a.nz - 1) : 1;
+    const int psy = (int)a.prow, psx = a.ny * psy;      // population planes: rows are prow apart
+    const int nsy = a.nz, nsx = a.ny * a.nz;            // node arrays
+    float f[19];
+#define X(s, ex, ey, ez, o)                                                                    \
+    if (s == 0) f[0] = __ldg(a.pown[0] + pidx);                                                \
+    else if ((fl >> s) & 1u) f[s] = weight(s);                                                 \
+    else {                                                                                     \
+        const int dx = ex > 0 ? xm : (ex < 0 ? xp : 0), dy = ey > 0 ? ym : (ey < 0 ? yp : 0),  \
+                  dz = ez > 0 ? zm : (ez < 0 ? zp : 0);                                        \
+        const float fs = __ldg(a.pown[s] + (pidx + (uint32_t)(dx * psx + dy * psy + dz)));     \
+        const float fo = __ldg(a.pown[o] + pidx);                                              \
+        const float g = __ldg(a.ns + (idx + (uint32_t)(dx * nsx + dy * nsy + dz)));            \
+        f[s] = fs + g * (fo - fs);                                                             \
+    }
+    D3Q19_DIRS(X)
+#undef X
+    bool pressure = false;
+    uint32_t slot = 0;
+    if (a.has_bc) pressure = face_bcs(f, a, fl, idx, slot);
+    float rho, ux, uy, uz, frc[3];
+    macro_force<FORCE>(a, idx, frc);
+    macro(f, frc, FORCE != 0, rho, ux, uy, uz);
+    if (MODE == MODE_EXTRACT) {
+        write_user_fields<MODE>(a, idx, f, rho, ux, uy, uz);
+        return;
+    }
+    if (pressure) {
+        a.vbc[3 * (size_t)slot + 0] = ux;
+        a.vbc[3 * (size_t)slot + 1] = uy;
+        a.vbc[3 * (size_t)slot + 2] = uz;
+    }
+    if (FORCE == 3) local_force<FORCE>(a, idx, frc);
+    collide(f, a.P, frc, FORCE != 0, rho, ux, uy, uz);
+#pragma unroll
+    for (int s = 0; s < 19; ++s) a.pout[s][pidx] = f[s];
+}
+
 // ---- direct peer-memory halo (x-slabs on GPUs that map each other's buffers) -------------------
 // The boundary planes of a slab in ONE kernel that is also the halo exchange: no pack, no
 // ncclSend/Recv, no unpack.  Flags in device memory order the ranks (p2p[0], p2p[1]: how many of
@@ -579,6 +642,10 @@ static void launch_dense_t(const StepArgs &a, int block, cudaStream_t st) {
     const unsigned rg = (a.row_count + by - 1) / by;
     const unsigned gy = rg < 32768u ? rg : 32768u;
     dim3 grid((a.nz + bx - 1) / bx, gy, (rg + gy - 1) / gy);
+    if (a.ns != nullptr && MODE != MODE_COLLIDE) {                  // grey-scale lattice (two buffers, no slabs)
+        k_dense_grey<FORCE, MODE == MODE_COLLIDE ? MODE_STEP : MODE><<<grid, blk, 0, st>>>(a);
+        return;
+    }
     if (a.aa != AA_OFF && MODE != MODE_COLLIDE) {
         if (a.aa == AA_ODD)
             k_dense_aa<FORCE, MODE == MODE_COLLIDE ? MODE_STEP : MODE, AA_ODD><<<grid, blk, 0, st>>>(a);

@@ -103,6 +103,9 @@ struct StepArgs {
     const float *ff[3];
     const float *ffm[3];
     int has_bc;                     // any face with type != 0
+    // grey-scale lattice (Grey_Scale/lbm_solver_3d_Macro_Sukop.py): solid fraction per node, dense
+    // node order [N]; null = ordinary half-way bounce-back streaming
+    const float *ns;
     // peer-memory halo of a dense x-slab (k_dense_peer, boundary-plane launch only; null otherwise):
     // peer_out[side][q] = plane of the q-th crossing population in the side's neighbour's OUTPUT
     // buffer, peer_delta[side] = element offset from this slab's boundary plane to that neighbour's

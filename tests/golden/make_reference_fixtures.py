@@ -280,6 +280,83 @@ def run_reference_sp_script(name):
     return out
 
 
+# ---- grey-scale script ---------------------------------------------------------------------------
+# Grey_Scale/lbm_solver_3d_Macro_Sukop.py: the script copy's physics (tau = 3 niu + 1/2, un-scaled Guo
+# term, in-place velocity faces) plus a per-node solid fraction ns: streaming0 (:233-239) blends every
+# post-collision population with the opposite one of the node it is about to move to,
+# f2[i,s] = f[i,s] + ns[i] (f[i+e_s, LR[s]] - f[i,s]), and streaming1 (:242-247) pushes f2 to ALL
+# neighbours -- no bounce-back; a node with ns = 1 is solid (solid = int(ns), :339) and is never
+# collided, so it keeps f = w for ever, and the links that leave it are never written.  Executed like
+# the other scripts: kernel part through the shim with the parameter lines replaced, ns assigned
+# directly instead of np.loadtxt('./BC.dat'), loop body :345-350 called from here.
+REFGS_SCRIPT = "/root/reference/Grey_Scale/lbm_solver_3d_Macro_Sukop.py"
+CASES_GREY = {
+    # name -> (shape, seed, parameter-line overrides, steps)
+    "periodic_force": ((6, 5, 4), 21, {"fx,fy,fz": "1.0e-5,-4.0e-6,2.0e-6", "niu": "0.1"}, 6),
+    "pressure_x": ((7, 5, 5), 23, {
+        "fx,fy,fz": "2.0e-6,0.0,0.0", "niu": "0.16",
+        "bc_x_left, rho_bcxl, vx_bcxl, vy_bcxl, vz_bcxl": "1, 1.0, 0.0, 0.0, 0.0",
+        "bc_x_right, rho_bcxr, vx_bcxr, vy_bcxr, vz_bcxr": "1, 0.99, 0.0, 0.0, 0.0"}, 6),
+}
+
+
+def case_grey_ns(name):
+    """solid fraction per node: a quarter of the nodes fully solid (1.0), a quarter open (0.0), the
+    rest grey with fractions in (0, 1)"""
+    shape, seed = CASES_GREY[name][0], CASES_GREY[name][1]
+    rng = np.random.default_rng(seed)
+    kind = rng.random(shape)
+    frac = rng.random(shape)
+    return np.where(kind < 0.25, 1.0, np.where(kind < 0.5, 0.0, frac)).astype(np.float32)
+
+
+def run_reference_grey_script(name):
+    import re
+    shape, _, overrides, steps = CASES_GREY[name]
+    src = open(REFGS_SCRIPT).read()
+    head = src[:src.index("time_init = time.time()")]
+    lines = dict(overrides)
+    lines["nx,ny,nz"] = "%d,%d,%d" % shape
+    for lhs, rhs in lines.items():
+        head, n = re.subn(r"^%s\s*=.*$" % re.escape(lhs), "%s = %s" % (lhs, rhs), head, count=1, flags=re.M)
+        assert n == 1, lhs
+    shim = os.path.join(ROOT, "tests", "taichi_shim")
+    sys.path.insert(0, shim)
+    try:
+        for m in ("taichi", "pyevtk", "pyevtk.hl", "evtk", "evtk.hl"):
+            sys.modules.pop(m, None)
+        g = {"__name__": "lbm_solver_3d_Macro_Sukop"}
+        exec(compile(head, REFGS_SCRIPT, "exec"), g)
+    finally:
+        sys.path.remove(shim)
+    for k, val in list(g.items()):       # Python-scope floats read by kernels are embedded as f32
+        if isinstance(val, float):
+            g[k] = np.float32(val)
+    ns_np = case_grey_ns(name)
+    g["solid"].from_numpy(ns_np.astype(int))       # :339
+    g["ns"].from_numpy(ns_np)                      # :343
+    g["static_init"]()
+    g["init"]()
+    for _ in range(steps):                         # :345-350
+        g["colission"]()
+        g["streaming0"]()
+        g["streaming1"]()
+        g["Boundary_condition"]()
+        g["streaming3"]()
+    out = {"ns": ns_np, "solid": ns_np.astype(int).astype(np.int8), "steps": steps}
+    for n in ("F", "rho", "v"):
+        out[n] = g[n].to_numpy()
+    out["S"] = np.asarray(g["S_dig"].to_numpy())
+    return out
+
+
+def write_grey(name):
+    out = run_reference_grey_script(name)
+    np.savez_compressed(os.path.join(HERE, "ref_grey_%s.npz" % name), **out)
+    print("grey-scale script", name, "steps", out["steps"], "max |v|", float(np.abs(out["v"]).max()),
+          "rho range", float(out["rho"][out["solid"] == 0].min()), float(out["rho"][out["solid"] == 0].max()))
+
+
 def write_script(name):
     out = run_reference_sp_script(name)
     np.savez_compressed(os.path.join(HERE, "ref_script_%s.npz" % name), **out)
@@ -295,6 +372,8 @@ def main():
                 write_single(mod, name)
             elif name in CASES_SCRIPT:
                 write_script(name)
+            elif name.startswith("grey_") and name[5:] in CASES_GREY:
+                write_grey(name[5:])
             else:
                 write_two_phase(name)
         return
@@ -304,6 +383,8 @@ def main():
         write_two_phase(name)
     for name in CASES_SCRIPT:
         write_script(name)
+    for name in CASES_GREY:
+        write_grey(name)
 
 
 def write_two_phase(name):

@@ -138,3 +138,44 @@ def make_solver_script(name, sparse=False, strict=True):
         getattr(lb, fn)(arg)
     lb.init_simulation()
     return lb
+
+
+# ---- grey-scale script (Grey_Scale/lbm_solver_3d_Macro_Sukop.py through the shim) ------------------
+NAMES_GREY = sorted(mk.CASES_GREY)
+_GREY_PHYSICS = dict(tau_mode="textbook", guo_mode="unscaled", vel_bc_mode="script")
+
+
+def fixture_grey(name):
+    return np.load(os.path.join(GOLD, "ref_grey_%s.npz" % name))
+
+
+def _grey_setup(name):
+    _, _, lines, _ = mk.CASES_GREY[name]
+    calls = [("set_force", [float(t) for t in lines["fx,fy,fz"].split(",")]), ("set_viscosity", float(lines["niu"]))]
+    for key, side in (("bc_x_left, rho_bcxl, vx_bcxl, vy_bcxl, vz_bcxl", "x0"),
+                      ("bc_x_right, rho_bcxr, vx_bcxr, vy_bcxr, vz_bcxr", "x1")):
+        if key in lines and int(float(lines[key].split(",")[0])) == 1:
+            calls.append(("set_bc_rho_" + side, float(lines[key].split(",")[1])))
+    return calls
+
+
+def make_oracle_grey(cls, name, ns=None, **kw):
+    o = cls(*mk.CASES_GREY[name][0], **_GREY_PHYSICS, **kw)
+    o.set_grey_scale(fixture_grey(name)["ns"] if ns is None else ns)
+    for fn, arg in _grey_setup(name):
+        if fn.startswith("set_bc_rho_"):
+            o.set_bc_rho(FACE[fn[-2:]], arg)
+        else:
+            getattr(o, fn)(arg)
+    o.init_simulation()
+    return o
+
+
+def make_solver_grey(name, strict=True, ns=None):
+    from taichi_lbm3d_b200 import LB3D_Solver_Single_Phase
+    lb = LB3D_Solver_Single_Phase(*mk.CASES_GREY[name][0], strict=strict, **_GREY_PHYSICS)
+    lb.ns.from_numpy(fixture_grey(name)["ns"] if ns is None else ns)
+    for fn, arg in _grey_setup(name):
+        getattr(lb, fn)(arg)
+    lb.init_simulation()
+    return lb

@@ -188,6 +188,113 @@ def test_reference_script_copy_fixtures(cuda, sparse):
         assert np.abs(lbf.v.to_numpy()[fl] - g["v"][fl]).max() <= 3e-7
 
 
+# ---- grey-scale lattice (Grey_Scale/lbm_solver_3d_Macro_Sukop.py) -----------------------------------
+def test_reference_grey_scale_fixtures(cuda):
+    """tests/golden/ref_grey_*.npz: what the grey-scale script computes through the shim on lattices
+    with open, grey and fully solid nodes (periodic + body force; fixed-pressure x faces): verification
+    arithmetic bit for bit, production arithmetic to the north_star's 1e-5"""
+    from tests import refpin
+    for name in refpin.NAMES_GREY:
+        g = refpin.fixture_grey(name)
+        fl = g["solid"] == 0
+        lb = refpin.make_solver_grey(name, strict=True)
+        assert np.array_equal(lb.solid.to_numpy(), g["solid"]) and np.array_equal(lb.ns.to_numpy(), g["ns"])
+        lb.run(int(g["steps"]))
+        for n in ("F", "rho", "v"):
+            assert np.array_equal(getattr(lb, n).to_numpy()[fl], g[n][fl]), (name, n)
+        lbf = refpin.make_solver_grey(name, strict=False)
+        for _ in range(int(g["steps"])):
+            lbf.step()
+        assert rel_linf(lbf.F.to_numpy()[fl], g["F"][fl]) <= TOL and rel_linf(lbf.rho.to_numpy()[fl], g["rho"][fl]) <= TOL
+        assert np.abs(lbf.v.to_numpy()[fl] - g["v"][fl]).max() <= 3e-7
+
+
+def _grey_pair(shape, seed, strict, steps, faces=()):
+    from oracle.cref import RefSinglePhaseC
+    from taichi_lbm3d_b200 import LB3D_Solver_Single_Phase
+    rng = np.random.default_rng(seed)
+    kind, frac = rng.random(shape), rng.random(shape)
+    ns = np.where(kind < 0.2, 1.0, np.where(kind < 0.5, 0.0, frac)).astype(np.float32)
+    phys = dict(tau_mode="textbook", guo_mode="unscaled")
+    o = RefSinglePhaseC(*shape, **phys)
+    o.set_grey_scale(ns)
+    lb = LB3D_Solver_Single_Phase(*shape, strict=strict, **phys)
+    lb.ns.from_numpy(ns)
+    for face, rho in faces:
+        o.set_bc_rho(face, rho)
+        getattr(lb, cases.FACE_SETTERS_RHO[face])(rho)
+    for s in (o, lb):
+        s.set_force([2e-5, -1e-5, 5e-6])
+        s.set_viscosity(0.12)
+        s.init_simulation()
+    o.run(steps)
+    return o, lb
+
+
+@pytest.mark.parametrize("faces", [(), ((2, 1.0), (3, 0.99)), ((0, 1.0), (1, 0.995), (4, 1.01), (5, 1.0))])
+def test_grey_scale_against_the_oracle(cuda, faces):
+    """a 20 x 18 x 33 grey lattice (periodic wrap on every axis, z rows longer than a warp), 40 steps:
+    verification arithmetic bit-identical to the C oracle, step() and run() alike; production
+    arithmetic within 1e-5"""
+    o, lb = _grey_pair((20, 18, 33), 5, True, 40, faces)
+    lb.run(17)
+    assert np.isfinite(lb.rho.to_numpy()).all()            # a read in between closes and re-opens the pipeline
+    for _ in range(3):
+        lb.step()
+    lb.run(20)
+    _compare(lb, o, exact=True)
+    o, lbf = _grey_pair((20, 18, 33), 5, False, 40, faces)
+    lbf.run(40)
+    fl = o.solid == 0
+    assert rel_linf(lbf.F.to_numpy()[fl], o.F[fl]) <= TOL and rel_linf(lbf.rho.to_numpy()[fl], o.rho[fl]) <= TOL
+    assert np.abs(lbf.v.to_numpy()[fl] - o.v[fl]).max() <= max(TOL * float(np.abs(o.v[fl]).max()), 3e-7)
+
+
+def test_grey_scale_with_zero_fraction_is_the_plain_lattice_without_walls(cuda):
+    """ns = 0 everywhere: the blend vanishes, the step is the ordinary periodic one (no solid nodes)"""
+    from taichi_lbm3d_b200 import LB3D_Solver_Single_Phase
+    shape = (9, 8, 7)
+    a = LB3D_Solver_Single_Phase(*shape, strict=True)
+    b = LB3D_Solver_Single_Phase(*shape, strict=True)
+    b.ns.from_numpy(np.zeros(shape, np.float32))
+    for s in (a, b):
+        s.set_force([1e-5, 2e-5, -1e-5])
+        s.init_simulation()
+        s.run(12)
+    assert np.array_equal(a.F.to_numpy(), b.F.to_numpy()) and np.array_equal(a.v.to_numpy(), b.v.to_numpy())
+
+
+def test_grey_scale_refuses_what_it_cannot_reproduce(cuda):
+    """sparse / in-place storage and fixed-velocity faces are refused loudly, not approximated"""
+    from taichi_lbm3d_b200 import LB3D_Solver_Single_Phase
+    from taichi_lbm3d_b200._lib import LbmError
+    ns = np.full((6, 5, 4), 0.3, np.float32)
+    for kw in (dict(sparse_storage=True), dict(in_place=True)):
+        lb = LB3D_Solver_Single_Phase(6, 5, 4, **kw)
+        lb.ns.from_numpy(ns)
+        with pytest.raises(LbmError, match="grey-scale"):
+            lb.init_simulation()
+    lb = LB3D_Solver_Single_Phase(6, 5, 4)
+    lb.ns.from_numpy(ns)
+    lb.set_bc_vel_x0([0.01, 0.0, 0.0])
+    with pytest.raises(LbmError, match="grey-scale"):
+        lb.init_simulation()
+
+
+def test_grey_scale_checkpoint(cuda, tmp_path):
+    o, lb = _grey_pair((8, 7, 6), 9, True, 10)
+    lb.run(6)
+    path = str(tmp_path / "grey.npz")
+    lb.save_checkpoint(path)
+    _o2, lb2 = _grey_pair((8, 7, 6), 9, True, 0)
+    lb2.load_checkpoint(path)
+    lb2.run(4)
+    _compare(lb2, o, exact=True)
+    _o3, lb3 = _grey_pair((8, 7, 6), 10, True, 0)          # another ns on the same lattice size
+    with pytest.raises(ValueError):
+        lb3.load_checkpoint(path)
+
+
 @pytest.mark.parametrize("sparse", [False, True, "aa", "daa"])
 def test_script_velocity_faces_on_every_axis(cuda, sparse):
     """the in-place velocity form next to pressure faces on all six faces (the script copy has x

@@ -96,6 +96,31 @@ def test_script_copy_of_the_single_phase_solver(name, cls):
         assert np.array_equal(getattr(o, n)[fl], g[n][fl]), n
 
 
+@pytest.mark.parametrize("name", refpin.NAMES_GREY)
+@pytest.mark.parametrize("cls", [RefSinglePhase, RefSinglePhaseC])
+def test_grey_scale_script(name, cls):
+    """Grey_Scale/lbm_solver_3d_Macro_Sukop.py through the shim (parameter lines replaced, ns assigned
+    instead of read from BC.dat): the script copy's physics plus the partial bounce-back of
+    streaming0/streaming1 (:233-247) on a lattice with open, grey and fully solid nodes -- bit for bit
+    what set_grey_scale(ns) computes.  Also pins the side effect the fused kernels rely on: a link that
+    leaves a solid node is never written by the script, so it holds w[s] of init() for ever."""
+    from oracle.ref_single_phase import E, W64
+    g = refpin.fixture_grey(name)
+    o = refpin.make_oracle_grey(cls, name)
+    assert np.array_equal(o.S, g["S"]) and np.array_equal(o.solid, g["solid"])
+    for _ in range(int(g["steps"])):
+        o.step()
+    fl = g["solid"] == 0
+    for n in ("F", "rho", "v"):
+        assert np.array_equal(getattr(o, n)[fl], g[n][fl]), n
+    interior = np.zeros(fl.shape, bool)
+    interior[1:-1] = True                      # x faces may carry a boundary condition that overwrites F
+    for s in range(1, 19):
+        src_solid = np.roll(g["solid"], tuple(int(c) for c in E[s]), axis=(0, 1, 2)) > 0
+        m = fl & src_solid & interior
+        assert m.any() and np.all(g["F"][..., s][m] == np.float32(W64[s])), s
+
+
 @pytest.mark.parametrize("name", refpin.NAMES)
 def test_reference_sparse_storage_semantics(name):
     """sparse_storage=True of the reference (pointer SNode tree of 3^3 blocks, :36-44, modelled by
