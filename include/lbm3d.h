@@ -80,6 +80,11 @@ int lbm_abi_version(void);
 int lbm_create(const lbm_config *cfg, lbm_ctx **out);
 int lbm_destroy(lbm_ctx *ctx);
 const char *lbm_last_error(const lbm_ctx *ctx);   /* ctx may be NULL: last create error */
+/* lbm_destroy / a repeated lbm_init keep the device buffers of a context (at most LBM3D_POOL_MB
+ * MiB in total, default 8192, 0 = never) for the next context of this process that asks for the
+ * same sizes, which then makes no cudaMalloc / cudaFree call (csrc/lbm_devpool.cuh).  This gives the cached memory back to the driver; returns the bytes freed.
+ * (No counterpart in the reference: Taichi's runtime owns its device memory pool.) */
+long long lbm_pool_trim(void);
 
 /* ---- parameters (setters :405-458; all must precede lbm_init) ------------------------- */
 /* solid.from_numpy / init_geo (:173-177): int8 [nx][ny][nz], >0 = solid */

@@ -15,6 +15,7 @@ LIB = os.path.join(ROOT, "taichi_lbm3d_b200", "lib", "liblbm3d_b200.so")
 HOT = ["lbm_fast::k_dense<0, 0, true>", "lbm_fast::k_dense<1, 0, true>", "lbm_fast::k_dense_aa<0, 0, 1>",
        "lbm_fast::k_dense_aa<0, 0, 2>", "lbm_fast::k_sparse<1, 0, true, 0>", "lbm_fast::k_sparse<0, 0, true, 0>",
        "lbm_fast::k_sparse<1, 0, true, 1>", "lbm_fast::k_sparse<1, 0, true, 2>",
+       "lbm_fast::k_dense_peer<0, true>", "lbm_fast::k_dense_grey<1, 0>",
        "lbm2p_fast::k2p_main<true, 0, true>", "lbm2p_fast::k2p_colour<false>", "lbm2p_fast::k2p_colour<true>",
        "lbm2p_fast::k2p_main_sparse<true, 0>", "lbm2p_fast::k2p_colour_sparse"]
 OPS = ["UBLKCP", "SYNCS", "LDG", "STG", "LDS", "STS", "SHFL", "BAR", "FFMA", "FADD", "FMUL", "MUFU", "UTMALDG", "UTCMMA"]

@@ -97,7 +97,7 @@ class LB3D_Solver_Single_Phase:
             raise ValueError("vel_bc_mode must be 'class' or 'script'")
         self.vel_bc_mode = vel_bc_mode
         self.device = device
-        self._solid_host = np.zeros((nx, ny, nz), np.int8)
+        self._solid = None           # host copy of the geometry, all-fluid until assigned (see _solid_host)
         self._force_field = None
         self._ns_host = None
         self._ctx = None
@@ -117,6 +117,17 @@ class LB3D_Solver_Single_Phase:
         self.x = np.linspace(0, nx, nx)
         self.y = np.linspace(0, ny, ny)
         self.z = np.linspace(0, nz, nz)
+
+    @property
+    def _solid_host(self):
+        # allocated on first need: a solver whose geometry is assigned never touches the zeros
+        if self._solid is None:
+            self._solid = np.zeros((self.nx, self.ny, self.nz), np.int8)
+        return self._solid
+
+    @_solid_host.setter
+    def _solid_host(self, arr):
+        self._solid = arr
 
     # ---- setters, reference :405-458 ----------------------------------------------------
     def set_bc_vel_x1(self, vel):
@@ -451,6 +462,14 @@ class LB3D_Solver_Single_Phase:
             # init_simulation() never survive; refuse instead of silently dropping them
             raise _lib.LbmError("assign %s after init_simulation(), which resets it" % name)
         self._upload(name, a)
+
+    def close(self):
+        """release the device state now (addition; the reference leaves it to Taichi's runtime).  The
+        large buffers stay cached in the library for the next solver of the same size
+        (``lbm_pool_trim``); the object can be set up again with init_simulation()."""
+        if self._ctx is not None and self._lib is not None:
+            self._lib.lbm_destroy(self._ctx)
+            self._ctx = None
 
     def __del__(self):
         try:

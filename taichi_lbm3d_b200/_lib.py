@@ -49,6 +49,7 @@ SIGNATURES = {
     "lbm_set_guo_form": (_I, [_VP, _I]),
     "lbm_set_vel_bc_form": (_I, [_VP, _I]),
     "lbm_set_grey_scale": (_I, [_VP, _VP]),
+    "lbm_pool_trim": (ctypes.c_longlong, []),
     "lbm_set_viscosity": (_I, [_VP, _c.c_double, _I]),
     "lbm_set_relaxation": (_I, [_VP, _FP]),
     "lbm_set_inverse_matrix": (_I, [_VP, _FP]),

@@ -18,6 +18,7 @@
 #include "lbm_kernels.cuh"
 #include "lbm_geometry.cuh"
 #include "lbm_nccl.cuh"
+#include "lbm_devpool.cuh"
 #include "lbm_sparse_build.cuh"
 
 namespace {
@@ -210,17 +211,28 @@ void default_relaxation(double niu, int textbook, float S[19]) {
 }
 
 void free_device(lbm_ctx *c) {
-    cudaFree(c->d_solid); cudaFree(c->d_flags); cudaFree(c->d_nbr); cudaFree(c->d_lin);
-    cudaFree(c->d_rank); cudaFree(c->d_fbase[0]); cudaFree(c->d_fbase[1]); cudaFree(c->d_rho);
-    cudaFree(c->d_rb8); cudaFree(c->d_blk); cudaFree(c->d_exc);
+    // the buffers go back to the process-wide cache (lbm_devpool.cuh)
+    lbm_pool::release(c->d_flags); lbm_pool::release(c->d_fbase[0]); lbm_pool::release(c->d_fbase[1]);
+    lbm_pool::release(c->d_rho); lbm_pool::release(c->d_v); lbm_pool::release(c->d_F);
+    lbm_pool::release(c->d_solid); lbm_pool::release(c->d_nbr); lbm_pool::release(c->d_lin);
+    lbm_pool::release(c->d_rank);
+    lbm_pool::release(c->d_rb8); lbm_pool::release(c->d_blk); lbm_pool::release(c->d_exc);
     c->d_rb8 = nullptr; c->d_blk = nullptr; c->d_exc = nullptr;
-    cudaFree(c->d_cls); c->d_cls = nullptr; c->d_fbase[0] = c->d_fbase[1] = nullptr;
-    cudaFree(c->d_v); cudaFree(c->d_F); cudaFree(c->d_vbc); cudaFree(c->d_scalar);
-    cudaFree(c->d_ff); c->d_ff = nullptr;
-    cudaFree(c->d_ffm); c->d_ffm = nullptr; c->ffm_pending = false;
+    lbm_pool::release(c->d_cls); c->d_cls = nullptr; c->d_fbase[0] = c->d_fbase[1] = nullptr;
+    lbm_pool::release(c->d_vbc); lbm_pool::release(c->d_scalar);
+    lbm_pool::release(c->d_ff); c->d_ff = nullptr;
+    lbm_pool::release(c->d_ffm); c->d_ffm = nullptr; c->ffm_pending = false;
     c->d_solid = nullptr; c->d_flags = nullptr; c->d_nbr = nullptr; c->d_lin = nullptr;
     c->d_rank = nullptr; c->d_f[0] = c->d_f[1] = nullptr; c->d_rho = c->d_v = c->d_F = nullptr;
     c->d_vbc = nullptr; c->d_scalar = nullptr;
+}
+
+// cudaMalloc through the cache (every release in this file goes through lbm_pool::release, which
+// passes what it does not know on to cudaFree), except for x-slab contexts: their buffers are
+// exported to other processes (CUDA IPC), which is simplest to reason about with allocations of
+// their own
+static cudaError_t big_alloc(const lbm_ctx *c, void **p, size_t bytes) {
+    return c->cfg.halo_x ? cudaMalloc(p, bytes) : lbm_pool::alloc(p, bytes);
 }
 
 void fill_args(const lbm_ctx *c, StepArgs &a) {
@@ -314,7 +326,7 @@ int launch(lbm_ctx *c, int mode, const StepArgs &a, cudaStream_t st) {
 // user-visible F array, allocated on first need; solid nodes hold w (:164-169)
 int ensure_F(lbm_ctx *c) {
     if (c->d_F != nullptr) return LBM_OK;
-    CU(c, cudaMalloc(&c->d_F, c->N * 19 * sizeof(float)));
+    CU(c, big_alloc(c, (void **)&c->d_F, c->N * 19 * sizeof(float)));
     k_fill_weights<<<nblocks(c->N * 19, 256), 256, 0, c->stream>>>(c->d_F, c->N);
     CU(c, cudaGetLastError());
     c->launches++;
@@ -597,7 +609,7 @@ int lbm_create(const lbm_config *cfg, lbm_ctx **out) {
     default_relaxation(0.16667, 0, c->S);        // :18 niu default
     for (int i = 0; i < 19; ++i)
         for (int j = 0; j < 19; ++j) c->invM[i * 19 + j] = (float)kInvM[i][j];
-    e = cudaMalloc(&c->d_solid, N);
+    e = big_alloc(c, (void **)&c->d_solid, N);
     if (e == cudaSuccess) e = cudaMemset(c->d_solid, 0, N);
     if (e != cudaSuccess) {
         g_create_error = std::string("cudaMalloc(solid): ") + cudaGetErrorString(e);
@@ -618,14 +630,16 @@ int lbm_destroy(lbm_ctx *ctx) {
     if (ctx->ev_boundary) cudaEventDestroy(ctx->ev_boundary);
     if (ctx->ev_comm) cudaEventDestroy(ctx->ev_comm);
     if (ctx->ev_interior) cudaEventDestroy(ctx->ev_interior);
-    for (int i = 0; i < 2; ++i) { cudaFree(ctx->d_send[i]); cudaFree(ctx->d_recv[i]); }
+    for (int i = 0; i < 2; ++i) { lbm_pool::release(ctx->d_send[i]); lbm_pool::release(ctx->d_recv[i]); }
     lbm_p2p_disconnect(ctx);
-    cudaFree(ctx->d_p2p);
-    cudaFree(ctx->d_ns);
+    lbm_pool::release(ctx->d_p2p);
+    lbm_pool::release(ctx->d_ns);
     free_device(ctx);
     delete ctx;
     return LBM_OK;
 }
+
+long long lbm_pool_trim(void) { return (long long)lbm_pool::trim(-1); }
 
 int lbm_set_geometry(lbm_ctx *ctx, const int8_t *solid) {
     CTX_CHECK(ctx);
@@ -680,16 +694,16 @@ int lbm_set_vel_bc_form(lbm_ctx *ctx, int script_form) {
 int lbm_set_grey_scale(lbm_ctx *ctx, const float *ns) {
     CTX_CHECK(ctx);
     if (ctx->inited) FAIL(ctx, LBM_ERR_STATE, "the solid fractions are fixed at lbm_init");
-    if (ns && (ctx->cfg.sparse || ctx->cfg.halo_x))
+    if (ns && (ctx->cfg.sparse || ctx->dense_aa || ctx->cfg.halo_x))
         FAIL(ctx, LBM_ERR_INVALID, "the grey-scale lattice needs dense two-buffer storage on one GPU "
                                    "(not sparse, not in place, not an x-slab)");
     CU(ctx, cudaSetDevice(ctx->cfg.device));
     if (!ns) {
-        cudaFree(ctx->d_ns);
+        lbm_pool::release(ctx->d_ns);
         ctx->d_ns = nullptr;
         return LBM_OK;
     }
-    if (!ctx->d_ns) CU(ctx, cudaMalloc(&ctx->d_ns, ctx->N * sizeof(float)));
+    if (!ctx->d_ns) CU(ctx, big_alloc(ctx, (void **)&ctx->d_ns, ctx->N * sizeof(float)));
     CU(ctx, cudaMemcpy(ctx->d_ns, ns, ctx->N * sizeof(float), cudaMemcpyDefault));
     return LBM_OK;
 }
@@ -707,7 +721,7 @@ int lbm_set_force_field(lbm_ctx *c, const float *force3) {
         if (r) return r;
     }
     if (!force3) {                       // back to the uniform force of lbm_set_force
-        cudaFree(c->d_ff); cudaFree(c->d_ffm);
+        lbm_pool::release(c->d_ff); lbm_pool::release(c->d_ffm);
         c->d_ff = c->d_ffm = nullptr;
         c->ffm_pending = false;
         return LBM_OK;
@@ -721,7 +735,7 @@ int lbm_set_force_field(lbm_ctx *c, const float *force3) {
         c->d_ff = t;
         c->ffm_pending = true;
     }
-    if (!c->d_ff) CU(c, cudaMalloc(&c->d_ff, bytes));
+    if (!c->d_ff) CU(c, big_alloc(c, (void **)&c->d_ff, bytes));
     // stage the caller's array on the device if it lives on the host
     cudaPointerAttributes at{};
     const bool dev = cudaPointerGetAttributes(&at, force3) == cudaSuccess && at.type == cudaMemoryTypeDevice;
@@ -729,9 +743,9 @@ int lbm_set_force_field(lbm_ctx *c, const float *force3) {
     const float *src = force3;
     float *tmp = nullptr;
     if (!dev) {
-        CU(c, cudaMalloc(&tmp, c->N * 3 * sizeof(float)));
+        CU(c, big_alloc(c, (void **)&tmp, c->N * 3 * sizeof(float)));
         cudaError_t e = cudaMemcpy(tmp, force3, c->N * 3 * sizeof(float), cudaMemcpyHostToDevice);
-        if (e != cudaSuccess) { cudaFree(tmp); CU(c, e); }
+        if (e != cudaSuccess) { lbm_pool::release(tmp); CU(c, e); }
         src = tmp;
     }
     cudaError_t e = cudaMemset(c->d_ff, 0, bytes);
@@ -740,7 +754,7 @@ int lbm_set_force_field(lbm_ctx *c, const float *force3) {
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
-    cudaFree(tmp);
+    lbm_pool::release(tmp);
     CU(c, e);
     c->launches++;
     return LBM_OK;
@@ -810,11 +824,11 @@ int lbm_init(lbm_ctx *c) {
     g.vel_in_place = c->vel_bc_script;
     for (int i = 0; i < 6; ++i) g.bc_psi_type[i] = 0;
 
-    CU(c, cudaMalloc(&c->d_scalar, 16));
+    CU(c, big_alloc(c, (void **)&c->d_scalar, 16));
     if (!c->cfg.sparse) {
         c->stride = (N + 31) / 32 * 32;
-        CU(c, cudaMalloc(&c->d_flags, N * sizeof(uint32_t)));
-        CU(c, cudaMalloc(&c->d_cls, N));
+        CU(c, big_alloc(c, (void **)&c->d_flags, N * sizeof(uint32_t)));
+        CU(c, big_alloc(c, (void **)&c->d_cls, N));
         k_build_flags<<<nblocks(N, 256), 256>>>(g, c->d_solid, c->d_flags, c->d_cls);
         CU(c, cudaGetLastError());
         c->launches++;
@@ -837,15 +851,15 @@ int lbm_init(lbm_ctx *c) {
             int64_t nfl = 0;
             auto it = thrust::make_transform_iterator((const int8_t *)c->d_solid, IsFluid());
             uint32_t *d_out = nullptr;
-            CU(c, cudaMalloc(&d_out, sizeof(uint32_t)));
+            CU(c, big_alloc(c, (void **)&d_out, sizeof(uint32_t)));
             size_t tmp_bytes = 0;
             void *tmp = nullptr;
             cub::DeviceReduce::Sum(nullptr, tmp_bytes, it, d_out, N);
-            CU(c, cudaMalloc(&tmp, tmp_bytes));
+            CU(c, big_alloc(c, (void **)&tmp, tmp_bytes));
             cudaError_t e = cub::DeviceReduce::Sum(tmp, tmp_bytes, it, d_out, N);
             uint32_t h = 0;
             cudaError_t e2 = cudaMemcpy(&h, d_out, sizeof h, cudaMemcpyDeviceToHost);
-            cudaFree(tmp); cudaFree(d_out);
+            lbm_pool::release(tmp); lbm_pool::release(d_out);
             CU(c, e); CU(c, e2);
             nfl = h;
             c->nf = (size_t)nfl;
@@ -905,13 +919,13 @@ int lbm_init(lbm_ctx *c) {
     c->aa = ((c->cfg.sparse == 2 && c->compressed) || c->dense_aa) && !c->cfg.halo_x;
     c->parity = 0;
     for (int b = 0; b < (c->aa ? 1 : 2); ++b) {
-        CU(c, cudaMalloc(&c->d_fbase[b], fbytes));
+        CU(c, big_alloc(c, (void **)&c->d_fbase[b], fbytes));
         CU(c, cudaMemset(c->d_fbase[b], 0, fbytes));
         c->d_f[b] = c->d_fbase[b] + c->pad;
     }
     if (c->aa) c->d_f[1] = c->d_f[0];
-    CU(c, cudaMalloc(&c->d_rho, N * sizeof(float)));
-    CU(c, cudaMalloc(&c->d_v, N * 3 * sizeof(float)));
+    CU(c, big_alloc(c, (void **)&c->d_rho, N * sizeof(float)));
+    CU(c, big_alloc(c, (void **)&c->d_v, N * 3 * sizeof(float)));
     k_fill<<<nblocks(N, 256), 256>>>(c->d_rho, N, 1.0f);      // init() :165
     CU(c, cudaGetLastError());
     c->launches++;
@@ -919,7 +933,7 @@ int lbm_init(lbm_ctx *c) {
     const size_t fs[6] = {plane, plane, (size_t)nx * nz, (size_t)nx * nz, (size_t)nx * ny, (size_t)nx * ny};
     size_t tot = 0;
     for (int i = 0; i < 6; ++i) { c->vbc_off[i] = (uint32_t)tot; tot += fs[i]; }
-    CU(c, cudaMalloc(&c->d_vbc, tot * 3 * sizeof(float)));
+    CU(c, big_alloc(c, (void **)&c->d_vbc, tot * 3 * sizeof(float)));
     CU(c, cudaMemset(c->d_vbc, 0, tot * 3 * sizeof(float)));
     if (c->cfg.strict) CU(c, lbm_strict::set_inverse_matrix(c->invM));
     CU(c, cudaDeviceSynchronize());
@@ -1063,9 +1077,9 @@ int lbm_get_nodes(lbm_ctx *c, int64_t n, const int64_t *index, float *F_out, flo
         if (host[i] < 0 || (size_t)host[i] >= c->N) FAIL(c, LBM_ERR_INVALID, "node index %lld outside the lattice", (long long)host[i]);
     int64_t *d_index = nullptr;
     float *d_tmp = nullptr;
-    CU(c, cudaMalloc(&d_index, n * sizeof(int64_t)));
+    CU(c, big_alloc(c, (void **)&d_index, n * sizeof(int64_t)));
     cudaError_t e = cudaMemcpy(d_index, host.data(), n * sizeof(int64_t), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMalloc(&d_tmp, (size_t)n * 19 * sizeof(float));
+    if (e == cudaSuccess) e = big_alloc(c, (void **)&d_tmp, (size_t)n * 19 * sizeof(float));
     const float *src[3] = {c->d_F, c->d_rho, c->d_v};
     float *dst[3] = {F_out, rho_out, v_out};
     const int width[3] = {19, 1, 3};
@@ -1076,8 +1090,8 @@ int lbm_get_nodes(lbm_ctx *c, int64_t n, const int64_t *index, float *F_out, flo
         if (e == cudaSuccess) e = cudaMemcpy(dst[k], d_tmp, (size_t)n * width[k] * sizeof(float), cudaMemcpyDefault);
         c->launches++;
     }
-    cudaFree(d_index);
-    cudaFree(d_tmp);
+    lbm_pool::release(d_index);
+    lbm_pool::release(d_tmp);
     CU(c, e);
     return LBM_OK;
 }
@@ -1091,15 +1105,15 @@ int lbm_get_num_fluid(lbm_ctx *c, int64_t *n) {
     CU(c, cudaSetDevice(c->cfg.device));
     auto it = thrust::make_transform_iterator((const int8_t *)c->d_solid, IsFluid());
     uint32_t *d_out = nullptr;
-    CU(c, cudaMalloc(&d_out, sizeof(uint32_t)));
+    CU(c, big_alloc(c, (void **)&d_out, sizeof(uint32_t)));
     size_t tmp_bytes = 0;
     void *tmp = nullptr;
     cub::DeviceReduce::Sum(nullptr, tmp_bytes, it, d_out, c->N);
-    CU(c, cudaMalloc(&tmp, tmp_bytes));
+    CU(c, big_alloc(c, (void **)&tmp, tmp_bytes));
     cudaError_t e = cub::DeviceReduce::Sum(tmp, tmp_bytes, it, d_out, c->N);
     uint32_t h = 0;
     cudaError_t e2 = cudaMemcpy(&h, d_out, sizeof h, cudaMemcpyDeviceToHost);
-    cudaFree(tmp); cudaFree(d_out);
+    lbm_pool::release(tmp); lbm_pool::release(d_out);
     CU(c, e); CU(c, e2);
     *n = h;
     return LBM_OK;
@@ -1134,13 +1148,13 @@ int lbm_get_neighbor_table(lbm_ctx *c, int32_t *dst) {
     if (!c->inited || !c->cfg.sparse) FAIL(c, LBM_ERR_STATE, "needs an initialised sparse context");
     CU(c, cudaSetDevice(c->cfg.device));
     int32_t *tmp = nullptr;
-    CU(c, cudaMalloc(&tmp, (c->nf ? c->nf : 1) * 18 * sizeof(int32_t)));
+    CU(c, big_alloc(c, (void **)&tmp, (c->nf ? c->nf : 1) * 18 * sizeof(int32_t)));
     StepArgs a;
     fill_args(c, a);
     if (c->nf) k_decode_table<<<nblocks(c->nf, 256), 256>>>(a, (uint32_t)c->nf, tmp);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpy(dst, tmp, c->nf * 18 * sizeof(int32_t), cudaMemcpyDefault);
-    cudaFree(tmp);
+    lbm_pool::release(tmp);
     CU(c, e);
     c->launches++;
     return LBM_OK;
@@ -1186,7 +1200,7 @@ int lbm_p2p_export(lbm_ctx *c, void *blob256) {
     if (c->cfg.sparse || c->aa) FAIL(c, LBM_ERR_STATE, "the peer-memory halo serves dense two-buffer slabs");
     CU(c, cudaSetDevice(c->cfg.device));
     if (!c->d_p2p) {
-        CU(c, cudaMalloc(&c->d_p2p, 64));
+        CU(c, big_alloc(c, (void **)&c->d_p2p, 64));
         CU(c, cudaMemset(c->d_p2p, 0, 64));
     }
     P2pBlob b;
@@ -1296,8 +1310,8 @@ int lbm_comm_init(lbm_ctx *c, const void *id128, int world, int rank) {
     if (!c->ev_interior) CU(c, cudaEventCreateWithFlags(&c->ev_interior, cudaEventDisableTiming));
     const uint32_t sc[2] = {c->plane_count[1], c->plane_count[2]}, rc[2] = {c->plane_count[0], c->plane_count[3]};
     for (int i = 0; i < 2; ++i) {
-        if (!c->d_send[i]) CU(c, cudaMalloc(&c->d_send[i], (size_t)5 * (sc[i] ? sc[i] : 1) * sizeof(float)));
-        if (!c->d_recv[i]) CU(c, cudaMalloc(&c->d_recv[i], (size_t)5 * (rc[i] ? rc[i] : 1) * sizeof(float)));
+        if (!c->d_send[i]) CU(c, big_alloc(c, (void **)&c->d_send[i], (size_t)5 * (sc[i] ? sc[i] : 1) * sizeof(float)));
+        if (!c->d_recv[i]) CU(c, big_alloc(c, (void **)&c->d_recv[i], (size_t)5 * (rc[i] ? rc[i] : 1) * sizeof(float)));
     }
     return LBM_OK;
 }

@@ -326,6 +326,38 @@ def test_script_velocity_faces_on_every_axis(cuda, sparse):
     _compare(lb, o, exact=True)
 
 
+def test_buffer_cache_reuses_dirty_buffers_without_changing_results(cuda):
+    """csrc/lbm_devpool.cuh: a solver set up after another one of the same size was closed gets that
+    one's device buffers back, contents and all (a 128 x 64 x 64 lattice: every large buffer is above
+    the cache's 1 MiB threshold) -- its results must not depend on what they held; lbm_pool_trim()
+    returns the memory to the driver"""
+    from taichi_lbm3d_b200 import LB3D_Solver_Single_Phase, _lib
+    shape = (128, 64, 64)
+    solid = cases.random_porous(shape, 0.1, 3)
+
+    def run(lid, steps, sparse=False):
+        lb = LB3D_Solver_Single_Phase(*shape, strict=True, sparse_storage=sparse)
+        lb.solid.from_numpy(solid)
+        lb.set_bc_vel_x1(lid)
+        lb.set_force([1e-5, 0.0, 0.0])
+        lb.init_simulation()
+        lb.run(steps)
+        out = lb.F.to_numpy(), lb.rho.to_numpy(), lb.v.to_numpy()
+        lb.close()
+        return out
+
+    lib = _lib.load()
+    lib.lbm_pool_trim()
+    clean = run([0.0, 0.0, 0.05], 6)
+    assert lib.lbm_pool_trim() > 0                      # the closed solver's buffers were cached
+    run([0.0, 0.08, -0.03], 9)                          # another flow leaves its state in the cache ...
+    run([0.0, 0.08, -0.03], 4, sparse=True)
+    again = run([0.0, 0.0, 0.05], 6)                    # ... and this solver starts on those buffers
+    for a, b in zip(clean, again):
+        assert np.array_equal(a, b)
+    assert lib.lbm_pool_trim() > 0 and lib.lbm_pool_trim() == 0
+
+
 def test_step_by_step_equals_run(cuda):
     """step() x n, with field reads in between, equals run(n) (state machine, :477-481)."""
     case = cases.case_mixed_bc()
