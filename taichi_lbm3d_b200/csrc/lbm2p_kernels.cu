@@ -323,7 +323,7 @@ __device__ __forceinline__ void colour_acc(ColourSum &acc, float gr, float gb) {
 #define LBM2P_COLOUR_MINB 8
 #endif
 #ifndef LBM2P_COLOUR_MINB_ROWS
-#define LBM2P_COLOUR_MINB_ROWS 4
+#define LBM2P_COLOUR_MINB_ROWS 5      // 48 registers, no spills (6: 40 registers, 20 B of spills, no faster)
 #endif
 #ifndef LBM2P_MAIN_MINB
 #define LBM2P_MAIN_MINB 5
@@ -360,6 +360,29 @@ __device__ __forceinline__ void colour_finish(const Step2Args &A, uint32_t node,
 // every fluid node when GATHER = true (porous media, where almost every node has a solid link) --
 // evaluates its 19 terms itself from gathered records.
 #define COLOUR_TILE 30
+// Order in which a node adds its 19 terms.  Verification arithmetic: ascending direction, the order
+// of the oracle.  Production arithmetic: row by row as the warp tiles produce them -- (own, up, dn)
+// of the five axis rows, then the four diagonal rows -- so that a handed-over term is added as soon
+// as it arrives instead of waiting in a register for its turn (48 registers instead of 64: 5 blocks
+// of 8 warps per SM instead of 4; worth 2 % of a step on the 256^3 droplet, 1.065 -> 1.045 ms -- the
+// pass is held back by the L1 data path as much as by latency); the gather paths below and the sparse
+// kernel use the same order, which keeps the three bit-identical to each other.
+#ifndef LBM2P_COLOUR_TILE_ORDER
+#define LBM2P_COLOUR_TILE_ORDER 1
+#endif
+#if defined(LBM_STRICT) || !LBM2P_COLOUR_TILE_ORDER
+#define COLOUR_ROW_ORDER 0
+#define D3Q19_DIRS_COLOUR(X) D3Q19_DIRS(X)
+#else
+#define COLOUR_ROW_ORDER 1
+#define D3Q19_DIRS_COLOUR(X)                                                               \
+    X(0, 0, 0, 0, 0) X(5, 0, 0, 1, 6) X(6, 0, 0, -1, 5)                                    \
+    X(1, 1, 0, 0, 2) X(11, 1, 0, 1, 12) X(13, 1, 0, -1, 14)                                \
+    X(2, -1, 0, 0, 1) X(14, -1, 0, 1, 13) X(12, -1, 0, -1, 11)                             \
+    X(3, 0, 1, 0, 4) X(15, 0, 1, 1, 16) X(17, 0, 1, -1, 18)                                \
+    X(4, 0, -1, 0, 3) X(18, 0, -1, 1, 17) X(16, 0, -1, -1, 15)                             \
+    X(7, 1, 1, 0, 8) X(8, -1, -1, 0, 7) X(9, 1, -1, 0, 10) X(10, -1, 1, 0, 9)
+#endif
 template <bool GATHER>
 __global__ void __launch_bounds__(256, GATHER ? LBM2P_COLOUR_MINB : LBM2P_COLOUR_MINB_ROWS) k2p_colour(const Step2Args A) {
     const StepArgs &a = A.a;
@@ -395,6 +418,23 @@ __global__ void __launch_bounds__(256, GATHER ? LBM2P_COLOUR_MINB : LBM2P_COLOUR
         // neighbour rows with the periodic wrap (in an x-slab the ghost planes make x +- 1 exist)
         const uint32_t xm = x > 0 ? x - 1 : nx - 1, xp = x + 1 < nx ? x + 1 : 0;
         const uint32_t ym = y > 0 ? y - 1 : ny - 1, yp = y + 1 < ny ? y + 1 : 0;
+#if COLOUR_ROW_ORDER
+        // axis rows: own term (e_z = 0), up term (e_z = +1, for the node above), dn term (e_z = -1)
+#define AXIS_ROW(k, X_, Y_, SO, SU, SD, ex, ey)                                                \
+    {                                                                                          \
+        const uint32_t nb = ((X_) * ny + (Y_)) * nz + z;                                       \
+        const float4 q4 = __ldg(A.uq + nb);                                                    \
+        const float2 ab = __ldg(A.rrb + nb);                                                   \
+        const float4 n4 = load_interface(A.recC + nb, q4.w);                                   \
+        float gr, gb, ur, ub, dr, db;                                                          \
+        colour_term<SO, ex, ey, 0>(1.0f, ab, q4, n4, gr, gb);                                  \
+        colour_term<SU, ex, ey, 1>(1.0f, ab, q4, n4, ur, ub);                                  \
+        colour_term<SD, ex, ey, -1>(1.0f, ab, q4, n4, dr, db);                                 \
+        colour_acc<SO>(acc, gr, gb);                                                           \
+        colour_acc<SU>(acc, __shfl_up_sync(0xffffffffu, ur, 1), __shfl_up_sync(0xffffffffu, ub, 1));     \
+        colour_acc<SD>(acc, __shfl_down_sync(0xffffffffu, dr, 1), __shfl_down_sync(0xffffffffu, db, 1)); \
+    }
+#else
         float up[5][2], dn[5][2];
         // axis rows: own term (e_z = 0), up term (e_z = +1, for the node above), dn term (e_z = -1)
 #define AXIS_ROW(k, X_, Y_, SO, SU, SD, ex, ey)                                                \
@@ -413,14 +453,17 @@ __global__ void __launch_bounds__(256, GATHER ? LBM2P_COLOUR_MINB : LBM2P_COLOUR
         dn[k][0] = __shfl_down_sync(0xffffffffu, dr, 1);                                       \
         dn[k][1] = __shfl_down_sync(0xffffffffu, db, 1);                                       \
     }
+#endif
         AXIS_ROW(0, x, y, 0, 5, 6, 0, 0)           // s = 0 ; 5 = (0,0,1) ; 6 = (0,0,-1)
         AXIS_ROW(1, xm, y, 1, 11, 13, 1, 0)        // s = 1 = (1,0,0) ; 11 = (1,0,1) ; 13 = (1,0,-1)
         AXIS_ROW(2, xp, y, 2, 14, 12, -1, 0)       // s = 2 ; 14 = (-1,0,1) ; 12 = (-1,0,-1)
         AXIS_ROW(3, x, ym, 3, 15, 17, 0, 1)        // s = 3 ; 15 = (0,1,1) ; 17 = (0,1,-1)
         AXIS_ROW(4, x, yp, 4, 18, 16, 0, -1)       // s = 4 ; 18 = (0,-1,1) ; 16 = (0,-1,-1)
 #undef AXIS_ROW
+#if !COLOUR_ROW_ORDER
         colour_acc<5>(acc, up[0][0], up[0][1]);
         colour_acc<6>(acc, dn[0][0], dn[0][1]);
+#endif
 #define DIAG_ROW(S, X_, Y_, ex, ey)                                                            \
     {                                                                                          \
         const uint32_t nb = ((X_) * ny + (Y_)) * nz + z;                                       \
@@ -434,6 +477,7 @@ __global__ void __launch_bounds__(256, GATHER ? LBM2P_COLOUR_MINB : LBM2P_COLOUR
         DIAG_ROW(9, xm, yp, 1, -1)
         DIAG_ROW(10, xp, ym, -1, 1)
 #undef DIAG_ROW
+#if !COLOUR_ROW_ORDER
         colour_acc<11>(acc, up[1][0], up[1][1]);
         colour_acc<12>(acc, dn[2][0], dn[2][1]);
         colour_acc<13>(acc, dn[1][0], dn[1][1]);
@@ -442,6 +486,7 @@ __global__ void __launch_bounds__(256, GATHER ? LBM2P_COLOUR_MINB : LBM2P_COLOUR
         colour_acc<16>(acc, dn[4][0], dn[4][1]);
         colour_acc<17>(acc, dn[3][0], dn[3][1]);
         colour_acc<18>(acc, up[4][0], up[4][1]);
+#endif
         if (!fluid) return;
         done = (fl & FL_LINK_MASK) == 0u;          // no solid link: nothing bounced back
     }
@@ -472,7 +517,7 @@ __global__ void __launch_bounds__(256, GATHER ? LBM2P_COLOUR_MINB : LBM2P_COLOUR
         colour_term<s, ex, ey, ez>(bounce ? -1.0f : 1.0f, __ldg(pR + off), q4, load_interface(pC + off, q4.w), gr, gb); \
         colour_acc<s>(acc, gr, gb);                                                            \
     }
-        D3Q19_DIRS(X)
+        D3Q19_DIRS_COLOUR(X)
 #undef X
 #undef OFF
     }
@@ -742,7 +787,7 @@ __global__ void __launch_bounds__(SPARSE_BLOCK, LBM2P_COLOUR_MINB) k2p_colour_sp
         colour_term<s, ex, ey, ez>(bounce ? -1.0f : 1.0f, __ldg(A.rrb + j), q4, load_interface(A.recC + j, q4.w), gr, gb); \
         colour_acc<s>(acc, gr, gb);                                                            \
     }
-    D3Q19_DIRS(X)
+    D3Q19_DIRS_COLOUR(X)
 #undef X
     colour_finish(A, i, fl, acc.r, acc.b);
 }
