@@ -328,6 +328,9 @@ __device__ __forceinline__ void colour_acc(ColourSum &acc, float gr, float gb) {
 #ifndef LBM2P_MAIN_MINB
 #define LBM2P_MAIN_MINB 5
 #endif
+#ifndef LBM2P_MAIN_SPARSE_MINB
+#define LBM2P_MAIN_SPARSE_MINB 6      // 40 registers: 384^3 pack 1.259 -> 1.206 ms per step (the dense kernel gains nothing)
+#endif
 // psi (:605) and Boundary_condition_psi (:445-486) from the colour sums; stores the node's state
 __device__ __forceinline__ void colour_finish(const Step2Args &A, uint32_t node, uint32_t fl, float rr, float rb) {
     float psi = rr - rb / (rr + rb);         // :605, precedence as written
@@ -793,7 +796,7 @@ __global__ void __launch_bounds__(SPARSE_BLOCK, LBM2P_COLOUR_MINB) k2p_colour_sp
 }
 
 template <bool FORCE, int MODE>
-__global__ void __launch_bounds__(SPARSE_BLOCK, LBM2P_MAIN_MINB) k2p_main_sparse(const __grid_constant__ Step2Args A) {
+__global__ void __launch_bounds__(SPARSE_BLOCK, LBM2P_MAIN_SPARSE_MINB) k2p_main_sparse(const __grid_constant__ Step2Args A) {
     const StepArgs &a = A.a;
     __shared__ SparseTable s_tab;
     __shared__ uint64_t s_bar;
