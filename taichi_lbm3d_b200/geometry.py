@@ -50,6 +50,26 @@ def save_geometry_text(filename, solid):
     np.savetxt(filename, out.T, fmt='%d')
 
 
+def load_grey_scale(filename, nx, ny, nz):
+    """Solid fraction per node as the grey-scale script reads it (Grey_Scale/
+    lbm_solver_3d_Macro_Sukop.py:142-145): text, one value per line, Fortran order; for
+    ``solver.ns.from_numpy``."""
+    in_dat = np.loadtxt(filename)
+    if in_dat.size != nx * ny * nz:
+        raise ValueError("%s holds %d values, expected %d" % (filename, in_dat.size, nx * ny * nz))
+    return np.ascontiguousarray(np.reshape(in_dat, (nx, ny, nz), order='F').astype(np.float32))
+
+
+def grey_channel(nx=60, ny=50, nz=5, layer=19, fraction=0.2):
+    """The case of the reference's Grey_Scale/BC.dat: a channel between solid walls at y = 0 and
+    y = ny-1 with a grey layer of the given solid fraction on the lower wall (y = 1 .. layer)."""
+    ns = np.zeros((nx, ny, nz), np.float32)
+    ns[:, 0, :] = 1.0
+    ns[:, ny - 1, :] = 1.0
+    ns[:, 1:1 + layer, :] = fraction
+    return ns
+
+
 def cavity(nx, ny, nz):
     """flow_domain_geo_generation_2D.py:18-23: walls on x=0, y=0, y=-1, z=0, z=-1 (the lid is
     the open x=nx-1 face, driven by set_bc_vel_x1)."""

@@ -132,6 +132,23 @@ def test_generators():
     assert np.array_equal(a, b) and 0.7 <= a.mean() < 0.9
 
 
+def test_grey_scale_geometry(tmp_path):
+    """grey_channel() is the reference's Grey_Scale/BC.dat (walls at y = 0, 49; solid fraction 0.2 on
+    y = 1..19; checked against the file where the reference is mounted), and load_grey_scale reads
+    the script's text format (Fortran order, :142-145)"""
+    import os
+    from taichi_lbm3d_b200 import geometry
+    ns = geometry.grey_channel()
+    assert ns.shape == (60, 50, 5) and ns.dtype == np.float32
+    assert np.all(ns[:, 0] == 1) and np.all(ns[:, 49] == 1) and np.all(ns[:, 1:20] == np.float32(0.2)) and not ns[:, 20:49].any()
+    path = str(tmp_path / "BC.dat")
+    np.savetxt(path, ns.reshape(-1, order="F"), fmt="%g")
+    assert np.array_equal(geometry.load_grey_scale(path, 60, 50, 5), ns)
+    ref = "/root/reference/Grey_Scale/BC.dat"
+    if os.path.exists(ref):
+        assert np.array_equal(geometry.load_grey_scale(ref, 60, 50, 5), ns)
+
+
 def test_vtr_roundtrip(tmp_path):
     from taichi_lbm3d_b200 import vtk
     rng = np.random.default_rng(1)

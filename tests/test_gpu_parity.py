@@ -250,6 +250,29 @@ def test_grey_scale_against_the_oracle(cuda, faces):
     assert np.abs(lbf.v.to_numpy()[fl] - o.v[fl]).max() <= max(TOL * float(np.abs(o.v[fl]).max()), 3e-7)
 
 
+def test_grey_scale_reference_case(cuda):
+    """the case the grey-scale script ships (BC.dat: 60 x 50 x 5 channel with a grey layer, fx = 1e-6,
+    niu = 0.1, all faces periodic; examples/example_grey_scale.py), 300 steps against the C oracle:
+    verification arithmetic bit for bit; the flow in the grey layer is slower than in the open part"""
+    from oracle.cref import RefSinglePhaseC
+    from taichi_lbm3d_b200 import LB3D_Solver_Single_Phase, geometry
+    ns = geometry.grey_channel()
+    phys = dict(tau_mode="textbook", guo_mode="unscaled")
+    o = RefSinglePhaseC(*ns.shape, **phys)
+    o.set_grey_scale(ns)
+    lb = LB3D_Solver_Single_Phase(*ns.shape, strict=True, **phys)
+    lb.ns.from_numpy(ns)
+    for s in (o, lb):
+        s.set_force([1.0e-6, 0.0, 0.0])
+        s.set_viscosity(0.1)
+        s.init_simulation()
+    o.run(300)
+    lb.run(300)
+    _compare(lb, o, exact=True)
+    v = lb.v.to_numpy()
+    assert 0 < v[:, 10, :, 0].mean() < 0.5 * v[:, 35, :, 0].mean()
+
+
 def test_grey_scale_with_zero_fraction_is_the_plain_lattice_without_walls(cuda):
     """ns = 0 everywhere: the blend vanishes, the step is the ordinary periodic one (no solid nodes)"""
     from taichi_lbm3d_b200 import LB3D_Solver_Single_Phase
