@@ -98,6 +98,7 @@ class LB3D_Solver_Single_Phase:
         self.vel_bc_mode = vel_bc_mode
         self.device = device
         self._solid = None           # host copy of the geometry, all-fluid until assigned (see _solid_host)
+        self._solid_dev = None       # or: the assigned array as it was copied to the device (see _set_field)
         self._force_field = None
         self._ns_host = None
         self._ctx = None
@@ -120,14 +121,19 @@ class LB3D_Solver_Single_Phase:
 
     @property
     def _solid_host(self):
-        # allocated on first need: a solver whose geometry is assigned never touches the zeros
+        # made on first need: a solver whose geometry went straight to the device (or is never read
+        # back) does not touch 16 MB of host memory per 256^3 for it
         if self._solid is None:
-            self._solid = np.zeros((self.nx, self.ny, self.nz), np.int8)
+            if self._solid_dev is not None:
+                self._solid = (self._solid_dev > 0).cpu().numpy().view(np.int8)    # init_geo :175
+            else:
+                self._solid = np.zeros((self.nx, self.ny, self.nz), np.int8)
         return self._solid
 
     @_solid_host.setter
     def _solid_host(self, arr):
         self._solid = arr
+        self._solid_dev = None
 
     # ---- setters, reference :405-458 ----------------------------------------------------
     def set_bc_vel_x1(self, vel):
@@ -245,8 +251,12 @@ class LB3D_Solver_Single_Phase:
         self.s_other = 8.0 * (2.0 - self.s_v) / (8.0 - self.s_v)
         S = relaxation_rates(self.niu, self.tau_mode)
         self.force_flag = 1 if (abs(self.fx) > 0 or abs(self.fy) > 0 or abs(self.fz) > 0) else 0   # :137-140
-        solid = np.ascontiguousarray(self._solid_host, dtype=np.int8)
-        self._ck(lib.lbm_set_geometry(ctx, solid.ctypes.data_as(ctypes.c_void_p)), "lbm_set_geometry")
+        if self._solid_dev is not None and self._solid_dev.device.index == cfg.device:
+            # the array went to the device when it was assigned; lbm_set_geometry turns > 0 into 1 there
+            self._ck(lib.lbm_set_geometry(ctx, ctypes.c_void_p(self._solid_dev.data_ptr())), "lbm_set_geometry")
+        else:
+            solid = np.ascontiguousarray(self._solid_host, dtype=np.int8)
+            self._ck(lib.lbm_set_geometry(ctx, solid.ctypes.data_as(ctypes.c_void_p)), "lbm_set_geometry")
         for face in range(6):
             t, rho, vel = self._bc_tuple(face)
             velc = (ctypes.c_float * 3)(*[float(np.float32(c)) for c in vel])
@@ -425,6 +435,21 @@ class LB3D_Solver_Single_Phase:
         self._ck(fn(self._ctx, out.ctypes.data_as(ctypes.c_void_p)), "lbm_get_" + name)
         return out
 
+    def _device_for_geometry(self, a):
+        """the CUDA device a geometry array can be copied to as it is, or None"""
+        if a.dtype not in (np.int8, np.uint8, np.bool_) or not a.flags["C_CONTIGUOUS"] or not a.flags["WRITEABLE"]:
+            return None
+        if a.dtype == np.uint8 and a.size and int(a.max()) > 127:      # would read as negative = fluid
+            return None
+        try:
+            import torch
+            if not torch.cuda.is_available():
+                return None
+            idx = torch.cuda.current_device() if self.device is None else (torch.device(self.device).index or 0)
+            return torch.device("cuda", idx)
+        except Exception:  # noqa: BLE001
+            return None
+
     def _upload(self, name, arr):
         fn = {"rho": self._lib.lbm_set_rho, "v": self._lib.lbm_set_v, "F": self._lib.lbm_set_F}[name]
         self._ck(fn(self._ctx, arr.ctypes.data_as(ctypes.c_void_p)), "lbm_set_" + name)
@@ -439,7 +464,18 @@ class LB3D_Solver_Single_Phase:
             if self._ctx is not None:
                 self._lib.lbm_destroy(self._ctx)
                 self._ctx = None
-            self._solid_host = (a > 0).view(np.int8)        # init_geo :175 (bool viewed as 0/1 bytes: one pass)
+            # Like a Taichi field, the solver keeps a COPY taken now.  A byte array on a machine with
+            # a GPU is copied straight to the device (one DMA; from pinned memory at PCIe speed) and
+            # turned into 0 / 1 there; the host copy is made only if somebody asks for it.  Anything
+            # else is reduced to 0 / 1 bytes on the host first (init_geo :175).
+            dev = self._device_for_geometry(a)
+            if dev is not None:
+                import torch
+                src = a.view(np.int8) if a.dtype != np.int8 else a
+                self._solid = None
+                self._solid_dev = torch.from_numpy(src).to(dev)
+            else:
+                self._solid_host = (a > 0).view(np.int8)    # bool viewed as 0/1 bytes: one pass
             return
         if name == "ns":
             a = np.asarray(arr)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Full-size oracle fixtures for BASELINE configs 2, 3 and 4 at the north_star's horizon.
 
-    OMP_NUM_THREADS=6 python tests/golden/make_fullsize_golden.py cfg4 [cfg2] [cfg3]
+    OMP_NUM_THREADS=6 python tests/golden/make_fullsize_golden.py cfg4 [cfg2] [cfg3] [cfg3k]
 
 The C oracle (oracle/ref_*.c, the build whose results are bit-identical to the NumPy restatement
 and to the reference source run through tests/taichi_shim) needs minutes to an hour of host time
@@ -45,6 +45,9 @@ def fullsize_case(name):
     if name == "cfg3":        # 512^3 periodic sphere pack, porosity 0.20, fx = 1e-6, all faces periodic
         solid = sphere_pack(512, 512, 512, 0.80, 8.0, 16.0, seed=512, periodic=True)
         return cases.Case("cfg3", solid, force=[1e-6, 0.0, 0.0]), 100, SP_FIELDS, (0, 200, 511), RefSinglePhaseC
+    if name == "cfg3k":       # the same medium at 256^3 over the north_star's full horizon of 1000 steps
+        solid = sphere_pack(256, 256, 256, 0.80, 8.0, 16.0, seed=256, periodic=True)
+        return cases.Case("cfg3k", solid, force=[1e-6, 0.0, 0.0]), 1000, SP_FIELDS, (0, 100, 255), RefSinglePhaseC
     if name == "cfg4":        # 131^3 drainage, README parameters, psi = -1 entering from x0
         solid = ftb131_standin()
         psi = np.ones(solid.shape, np.float32)

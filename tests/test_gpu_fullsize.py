@@ -8,6 +8,7 @@ float64 sums over all fluid nodes, and per field the oracle's own fp32 round-off
 
   cfg2  256^3 lid-driven cavity, dense storage (two buffers and in place), 1000 steps
   cfg3  512^3 periodic sphere pack, porosity 0.20, fx = 1e-6, sparse storage (A-B and in place), 100 steps
+  cfg3k the same medium at 256^3 (seed 256), sparse storage (A-B and in place), 1000 steps
   cfg4  131^3 colour-gradient drainage, README parameters, dense and sparse storage, 1000 steps
 
 Bars.  Verification arithmetic: BIT-IDENTICAL on the sample (and on the sums where the whole field
@@ -56,7 +57,8 @@ def _check_distribution(g, f, got):
     assert np.all(mine <= bars), (f, mine.tolist(), bars.tolist())
 
 
-@pytest.mark.parametrize("name,storage", [("cfg2", False), ("cfg2", "daa"), ("cfg3", True), ("cfg3", "aa")])
+@pytest.mark.parametrize("name,storage", [("cfg2", False), ("cfg2", "daa"), ("cfg3", True), ("cfg3", "aa"),
+                                          ("cfg3k", True), ("cfg3k", "aa")])
 @pytest.mark.parametrize("strict", [True, False])
 def test_single_phase_full_size(cuda, name, storage, strict):
     g = _fixture(name)
