@@ -228,6 +228,12 @@ class LB3D_Solver_Two_Phase:
         else:
             raise _lib.LbmError("only solid and psi can be assigned before init_simulation()")
 
+    def close(self):
+        """release the device state now (addition); init_simulation() sets the solver up again"""
+        if self._ctx is not None and self._lib is not None:
+            self._lib.lbm2p_destroy(self._ctx)
+            self._ctx = None
+
     def __del__(self):
         try:
             if self._ctx is not None and self._lib is not None:
