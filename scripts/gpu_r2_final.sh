@@ -5,4 +5,3 @@ tail -4 gpurun_out/pytest_full.log
 tail -3 gpurun_out/smoke.log
 timeout 400 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_r2f.json 2> gpurun_out/bench_r2f.err
 cut -c1-400 gpurun_out/bench_r2f.json; tail -2 gpurun_out/bench_r2f.err
-timeout 100 python scripts/e2e_probe.py > gpurun_out/e2e_probe.log 2>&1; tail -32 gpurun_out/e2e_probe.log | head -8
