@@ -25,7 +25,9 @@ def main():
             ("cavity96 dense", cavity(96, 64, 64), lambda s: s.set_bc_vel_x1([0.0, 0.0, 0.1]), False),
             ("porous96 sparse, pressure x", sphere_pack(96, 64, 64, 0.7, 3.0, 6.0, seed=3, periodic=False),
              lambda s: (s.set_bc_rho_x0(1.0), s.set_bc_rho_x1(0.99), s.set_force([1e-6, 0, 0])), True)):
-        for overlap, transport in ((False, "native"), (True, "native"), (True, "torch")):
+        # the peer-memory case twice: the second solver gets the first one's buffers back from the library's
+        # cache and exports them to its neighbours again
+        for overlap, transport in ((False, "native"), (True, "native"), (True, "native"), (True, "torch")):
             ss = SlabSolver(*solid.shape, sparse_storage=sparse, overlap=overlap, transport=transport)
             ss.set_solid(solid)
             setup(ss)

@@ -228,11 +228,13 @@ void free_device(lbm_ctx *c) {
 }
 
 // cudaMalloc through the cache (every release in this file goes through lbm_pool::release, which
-// passes what it does not know on to cudaFree), except for x-slab contexts: their buffers are
-// exported to other processes (CUDA IPC), which is simplest to reason about with allocations of
-// their own
+// passes what it does not know on to cudaFree).  x-slab contexts too: a block that was exported to
+// the neighbours (CUDA IPC) comes back only after lbm_p2p_disconnect on every rank has unmapped it
+// (SlabSolver.close is collective), and exporting it again for the next context yields the same
+// handle, which the neighbours may open again.
 static cudaError_t big_alloc(const lbm_ctx *c, void **p, size_t bytes) {
-    return c->cfg.halo_x ? cudaMalloc(p, bytes) : lbm_pool::alloc(p, bytes);
+    static const bool slabs_too = getenv("LBM3D_POOL_SLABS") ? atoi(getenv("LBM3D_POOL_SLABS")) != 0 : true;
+    return (c->cfg.halo_x && !slabs_too) ? cudaMalloc(p, bytes) : lbm_pool::alloc(p, bytes);
 }
 
 void fill_args(const lbm_ctx *c, StepArgs &a) {
