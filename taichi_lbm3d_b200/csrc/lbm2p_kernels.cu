@@ -325,8 +325,11 @@ __device__ __forceinline__ void colour_acc(ColourSum &acc, float gr, float gb) {
 #ifndef LBM2P_COLOUR_MINB_ROWS
 #define LBM2P_COLOUR_MINB_ROWS 5      // 48 registers, no spills (6: 40 registers, 20 B of spills, no faster)
 #endif
+#ifndef LBM2P_COLOUR_ROWS
+#define LBM2P_COLOUR_ROWS 8           // y-rows (warps) of a block of the row-sharing colour kernel (256^3 droplet: 4 -> 1.048, 8 -> 1.042, 16 -> 1.128 ms per step)
+#endif
 #ifndef LBM2P_MAIN_MINB
-#define LBM2P_MAIN_MINB 5
+#define LBM2P_MAIN_MINB 5             // 48 registers (4: 62 registers, 1.078 instead of 1.042 ms per step)
 #endif
 #ifndef LBM2P_MAIN_SPARSE_MINB
 #define LBM2P_MAIN_SPARSE_MINB 6      // 40 registers: 384^3 pack 1.259 -> 1.206 ms per step (the dense kernel gains nothing)
@@ -387,7 +390,7 @@ __device__ __forceinline__ void colour_finish(const Step2Args &A, uint32_t node,
     X(7, 1, 1, 0, 8) X(8, -1, -1, 0, 7) X(9, 1, -1, 0, 10) X(10, -1, 1, 0, 9)
 #endif
 template <bool GATHER>
-__global__ void __launch_bounds__(256, GATHER ? LBM2P_COLOUR_MINB : LBM2P_COLOUR_MINB_ROWS) k2p_colour(const Step2Args A) {
+__global__ void __launch_bounds__(GATHER ? 256 : 32 * LBM2P_COLOUR_ROWS, GATHER ? LBM2P_COLOUR_MINB : LBM2P_COLOUR_MINB_ROWS) k2p_colour(const Step2Args A) {
     const StepArgs &a = A.a;
     // blockIdx.x walks the z-chunks of a row (fastest), (blockIdx.z, blockIdx.y) the row groups
     const uint32_t r = (blockIdx.z * gridDim.y + blockIdx.y) * blockDim.y + threadIdx.y;
@@ -1007,7 +1010,7 @@ cudaError_t launch_colour(const Step2Args &A, int block, cudaStream_t st) {
     }
     if (!A.gather) {
         // mostly bulk fluid: a warp per 30 nodes of a z-row (+ one either side), 8 y-rows per block
-        const unsigned by = 8, rg = (A.a.row_count + by - 1) / by, gy = rg < 32768u ? rg : 32768u;
+        const unsigned by = LBM2P_COLOUR_ROWS, rg = (A.a.row_count + by - 1) / by, gy = rg < 32768u ? rg : 32768u;
         blk = dim3(32, by, 1);
         grid = dim3((A.a.nz + COLOUR_TILE - 1) / COLOUR_TILE, gy, (rg + gy - 1) / gy);
         k2p_colour<false><<<grid, blk, 0, st>>>(A);
