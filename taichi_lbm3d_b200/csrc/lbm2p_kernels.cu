@@ -332,7 +332,7 @@ __device__ __forceinline__ void colour_acc(ColourSum &acc, float gr, float gb) {
 #define LBM2P_MAIN_MINB 5             // 48 registers (4: 62 registers, 1.078 instead of 1.042 ms per step)
 #endif
 #ifndef LBM2P_MAIN_SPARSE_MINB
-#define LBM2P_MAIN_SPARSE_MINB 6      // 40 registers: 384^3 pack 1.259 -> 1.206 ms per step (the dense kernel gains nothing)
+#define LBM2P_MAIN_SPARSE_MINB 6      // 40 registers; 384^3 pack, ms per step by blocks per SM: 3 -> 1.628, 4 -> 1.384, 5 -> 1.259, 6 -> 1.207, 8 -> 1.426
 #endif
 // psi (:605) and Boundary_condition_psi (:445-486) from the colour sums; stores the node's state
 __device__ __forceinline__ void colour_finish(const Step2Args &A, uint32_t node, uint32_t fl, float rr, float rb) {
